@@ -1,0 +1,106 @@
+"""ctypes binding of libdct_b200.so (the C ABI declared in include/dct_b200.h).
+
+There is no CPU fallback: if the shared library is missing it is built from
+csrc/ with nvcc (sm_100a), and if that is impossible the import fails loudly.
+"""
+import ctypes as C
+import os
+import subprocess
+import threading
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_PKG, "libdct_b200.so")
+_CSRC = os.path.join(_PKG, "csrc")
+
+OK = 0
+IN_PROBS, IN_LOGITS = 0, 1
+FLAG_SIMPLEX, FLAG_LABEL, FLAG_PRED, NUM_FLAGS = 0, 1, 2, 4
+MAX_VIEWS, MAX_CLASSES = 8, 64
+
+_p, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+
+# name -> argtypes (restype is int unless listed in _RESTYPES); must match include/dct_b200.h
+_SIGNATURES = {
+    "dct_abi_version": [],
+    "dct_error_string": [_i],
+    "dct_last_cuda_error": [],
+    "dct_device_check": [_i],
+    "dct_workspace_bytes": [],
+    "dct_jsd_fwd_f32": [_p, _i, _i, _i64, _i64, _i, _p, _p, _p, _p, _p],
+    "dct_jsd_bwd_f32": [_p, _i, _i, _i64, _i64, _i, _p, _p, _f, _p, _p],
+    "dct_jsd_fwdbwd_f32": [_p, _i, _i, _i64, _i64, _i, _f, _p, _p, _p, _p, _p, _p, _p, _p],
+    "dct_scale_if_not_one_f32": [_p, _i64, _p, _p],
+    "dct_kl_fwd_f32": [_p, _p, _i, _i64, _i64, _f, _p, _p, _p, _p, _p],
+    "dct_kl_bwd_f32": [_p, _p, _i, _i64, _i64, _f, _p, _p, _f, _p, _p, _p],
+    "dct_kl_logit_f32": [_p, _p, _i, _i64, _i64, _p, _p, _i, _p, _p, _f, _p, _p, _p, _p],
+    "dct_kl_from_logits_fwdbwd_f32": [_p, _p, _i, _i64, _i64, _f, _f, _p, _p, _p, _p, _p, _p],
+    "dct_kl_div_fwd_f32": [_p, _p, _i, _i64, _i64, _f, _p, _p, _p, _p, _p],
+    "dct_entropy_fwd_f32": [_p, _i, _i64, _i64, _p, _p, _p, _p, _p],
+    "dct_entropy_bwd_f32": [_p, _i, _i64, _i64, _p, _p, _f, _p, _p],
+    "dct_softmax_fwd_f32": [_p, _i, _i64, _i64, _p, _p],
+    "dct_softmax_bwd_f32": [_p, _p, _i, _i64, _i64, _p, _p],
+    "dct_l2_normalize_f32": [_p, _p, _i64, _i64, _f, _p, _p, _p, _p],
+    "dct_fgsm_f32": [_p, _p, _f, _p, _p, _i64, _p],
+    "dct_dice_counts_f32": [_p, _p, _i, _i64, _i64, _p, _i, _p, _p],
+    "dct_dice_from_counts_f32": [_p, _i64, _i, _i, _p, _p],
+    "dct_confusion_f32": [_p, _p, _i, _i64, _i64, _p, _p],
+    "dct_confusion_labels_i64": [_p, _p, _i64, _i, _p, _p, _p],
+}
+_RESTYPES = {"dct_error_string": C.c_char_p, "dct_last_cuda_error": C.c_char_p, "dct_workspace_bytes": C.c_size_t}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+_lock = threading.Lock()
+
+
+class DctError(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return _SO
+
+
+def build(force: bool = False, jobs: int = 8) -> str:
+    """Compile csrc/*.cu for sm_100a into libdct_b200.so (in-tree, next to this file)."""
+    cmd = ["make", "-C", _CSRC, f"-j{jobs}"] + (["-B"] if force else [])
+    subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(_SO):
+                    try:
+                        build()
+                    except Exception as e:  # no nvcc / no make: nothing to run on
+                        raise ImportError(
+                            f"{_SO} is missing and could not be built ({e}); "
+                            "run `python -c 'import __graft_entry__ as g; g.build()'` on a box with nvcc. "
+                            "There is no CPU fallback.") from e
+                h = C.CDLL(_SO)
+                for name, argtypes in _SIGNATURES.items():
+                    fn = getattr(h, name)  # AttributeError == ABI mismatch: fail loudly
+                    fn.argtypes = argtypes
+                    fn.restype = _RESTYPES.get(name, C.c_int)
+                if h.dct_abi_version() != 1:
+                    raise ImportError("libdct_b200.so ABI version mismatch; rebuild with build(force=True)")
+                _lib = h
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != OK:
+        h = lib()
+        msg = h.dct_error_string(rc).decode()
+        if rc == -4:
+            msg += ": " + h.dct_last_cuda_error().decode()
+        raise DctError(f"{what} failed: {msg} (code {rc})")
+
+
+def ptr_array(tensors):
+    """HOST array of device pointers (`const float* const*` in the ABI)."""
+    return (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])

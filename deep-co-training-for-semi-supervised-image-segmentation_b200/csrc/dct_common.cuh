@@ -1,0 +1,313 @@
+// dct_common.cuh -- shared device/host helpers for the sm_100a kernels of libdct_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <type_traits>
+
+#include "../../include/dct_b200.h"
+
+namespace dct {
+
+constexpr int kSMs = 148;             // B200: 2 dies x 74 SMs
+constexpr int kMaxPartials = 8192;    // per-launch CTA partial sums kept in the workspace
+constexpr float kEntEps = 1e-16f;     // Entropy / Entropy_2D epsilon (generalframework/loss/loss.py:64,81)
+
+// workspace layout: [0,8) uint32 ticket (+pad) | [64, 64+8*kMaxPartials) double partials
+struct Workspace {
+    unsigned int ticket;
+    unsigned int pad[15];
+    double partials[kMaxPartials];
+};
+
+struct Upstream {          // see "dct_upstream" in include/dct_b200.h
+    const float* gmap;     // [B,HW] or null
+    const float* gscalar;  // device scalar or null
+    float gconst;
+};
+
+template <int K>
+struct Views {
+    const float* in[K];
+    float* grad[K];
+};
+
+thread_local inline cudaError_t g_last_cuda_error = cudaSuccess;
+
+inline int check_launch() {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        g_last_cuda_error = e;
+        return DCT_ERR_CUDA;
+    }
+    return DCT_OK;
+}
+
+inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+// ---------------------------------------------------------------------------------------------
+// streaming 128/64/32-bit global accesses: every tensor on this path is touched exactly once,
+// so bypass L1 allocation on loads and mark stores streaming (evict-first in L2).
+// ---------------------------------------------------------------------------------------------
+template <int VEC>
+struct FVec;
+template <>
+struct FVec<1> {
+    float v[1];
+};
+template <>
+struct FVec<2> {
+    float v[2];
+};
+template <>
+struct FVec<4> {
+    float v[4];
+};
+
+template <int VEC>
+__device__ __forceinline__ FVec<VEC> ld_stream(const float* p) {
+    FVec<VEC> r;
+    if constexpr (VEC == 4) {
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3])
+                     : "l"(p));
+    } else if constexpr (VEC == 2) {
+        asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.v[0]), "=f"(r.v[1]) : "l"(p));
+    } else {
+        asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r.v[0]) : "l"(p));
+    }
+    return r;
+}
+
+template <int VEC>
+__device__ __forceinline__ void st_stream(float* p, const FVec<VEC>& r) {
+    if constexpr (VEC == 4) {
+        asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]),
+                     "f"(r.v[3])
+                     : "memory");
+    } else if constexpr (VEC == 2) {
+        asm volatile("st.global.cs.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]) : "memory");
+    } else {
+        asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(r.v[0]) : "memory");
+    }
+}
+
+// VEC int64 labels (VEC*8 bytes) as 128-bit streaming loads
+template <int VEC>
+__device__ __forceinline__ void ld_labels(const int64_t* p, long long (&g)[VEC]) {
+    if constexpr (VEC % 2 == 0) {
+#pragma unroll
+        for (int j = 0; j < VEC; j += 2) {
+            asm volatile("ld.global.nc.L1::no_allocate.v2.s64 {%0,%1}, [%2];" : "=l"(g[j]), "=l"(g[j + 1]) : "l"(p + j));
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) asm volatile("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(g[j]) : "l"(p + j));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// reductions
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic grid-wide sum of one double per thread.  Every CTA writes its partial to the
+// workspace; the CTA that draws the last ticket adds the partials in index order and writes
+// *out, then re-arms the ticket.  `out` may be null (nothing is done).
+__device__ __forceinline__ void grid_sum_to(double v, Workspace* ws, double* out, int cta_linear, int num_ctas) {
+    if (out == nullptr) return;
+    __shared__ double s_warp[32];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    if (lane == 0) s_warp[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        double t = lane < nw ? s_warp[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) {
+            ws->partials[cta_linear] = t;
+            __threadfence();
+            unsigned int ticket = atomicAdd(&ws->ticket, 1u);
+            s_last = (ticket == (unsigned int)num_ctas - 1u);
+        }
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        double acc = 0.0;
+        // fixed order: thread t sums partials t, t+T, ... ; then the same block tree as above
+        for (int i = threadIdx.x; i < num_ctas; i += blockDim.x) acc += __ldcg(&ws->partials[i]);
+        acc = warp_sum(acc);
+        __syncthreads();
+        if (lane == 0) s_warp[wid] = acc;
+        __syncthreads();
+        if (wid == 0) {
+            double t = lane < nw ? s_warp[lane] : 0.0;
+            t = warp_sum(t);
+            if (lane == 0) {
+                *out = t;
+                ws->ticket = 0u;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// grid geometry: blockIdx.y = image b, blockIdx.x strides over the image's pixel groups, so a CTA
+// never straddles two images (per-image integer counts and per-sample norms stay CTA-local).
+// One pixel group per thread (thousands of small CTAs: the hardware block scheduler balances the
+// tail); B <= 65535 is checked by the callers.
+// ---------------------------------------------------------------------------------------------
+inline dim3 image_grid(int64_t B, int64_t groups_per_image, int threads, int64_t max_ctas = kMaxPartials) {
+    int64_t gx = (groups_per_image + threads - 1) / threads;  // one pixel group per thread ...
+    int64_t cap = max_ctas / (B > 0 ? B : 1);                  // ... unless that exceeds the partial-sum slots
+    if (cap < 1) cap = 1;
+    if (gx > cap) gx = cap;                                    // then threads stride over the image
+    if (gx < 1) gx = 1;
+    return dim3((unsigned)gx, (unsigned)B, 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The pinned softmax arithmetic for the integer (Dice) path -- see DESIGN.md "Dice spec".
+// Explicit round-to-nearest intrinsics: never contracted, never flushed, independent of flags.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float spec_expf(float d) {
+    if (!(d >= -87.0f)) return (d != d) ? d : 0.0f;
+    float t = __fmul_rn(d, 1.44269504088896341f);
+    float n = rintf(t);
+    float r = __fmaf_rn(n, -0.693359375f, d);
+    r = __fmaf_rn(n, 2.12194440e-4f, r);
+    float y = __fmaf_rn(1.9875691500e-4f, r, 1.3981999507e-3f);
+    y = __fmaf_rn(y, r, 8.3334519073e-3f);
+    y = __fmaf_rn(y, r, 4.1665795894e-2f);
+    y = __fmaf_rn(y, r, 1.6666665459e-1f);
+    y = __fmaf_rn(y, r, 5.0000001201e-1f);
+    float z = __fmul_rn(r, r);
+    y = __fmaf_rn(y, z, r);
+    y = __fadd_rn(y, 1.0f);
+    int e = (int)n + 127;
+    float scale = __int_as_float(e << 23);
+    return __fmul_rn(y, scale);
+}
+
+// pred = argmax_c softmax_spec(x)_c.  Fast path: if every other class is more than 2^-16 below the
+// maximum its spec probability is strictly smaller (spec_expf(d) <= 1 - 2^-22 for d < -2^-16, and
+// IEEE division by the common sum keeps the order strict), so the raw arg-max IS the answer; only
+// near-ties / NaNs run the full pinned arithmetic.
+template <int C>
+__device__ __forceinline__ int spec_softmax_argmax(const float (&x)[C]) {
+    float m = x[0];
+    int am = 0;
+#pragma unroll
+    for (int c = 1; c < C; ++c)
+        if (x[c] > m) { m = x[c]; am = c; }
+    bool near = false;
+#pragma unroll
+    for (int c = 0; c < C; ++c) near |= (c != am) & !(__fsub_rn(x[c], m) < -1.52587890625e-05f);
+    // (c != am) is a runtime test, so x[am] itself never trips it; NaN anywhere makes `near` true
+    if (!near && (m == m)) return am;
+    float S = 0.0f;
+    bool any_nan = false;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        float d = __fsub_rn(x[c], m);
+        any_nan |= (d != d);
+        float e = spec_expf(d);
+        S = (c == 0) ? e : __fadd_rn(S, e);
+    }
+    if (any_nan) return 0;
+    int best = 0;
+    float qb = __fdiv_rn(spec_expf(__fsub_rn(x[0], m)), S);
+#pragma unroll
+    for (int c = 1; c < C; ++c) {
+        float q = __fdiv_rn(spec_expf(__fsub_rn(x[c], m)), S);
+        if (q > qb) { qb = q; best = c; }
+    }
+    return best;
+}
+
+// runtime-C variant reading a strided column (generic fallback kernels)
+__device__ __forceinline__ int spec_softmax_argmax_rt(const float* xb, int C, int64_t HW) {
+    float m = xb[0];
+    for (int c = 1; c < C; ++c) { float v = xb[(int64_t)c * HW]; if (v > m) m = v; }
+    float S = 0.0f;
+    bool any_nan = false;
+    for (int c = 0; c < C; ++c) {
+        float d = __fsub_rn(xb[(int64_t)c * HW], m);
+        any_nan |= (d != d);
+        float e = spec_expf(d);
+        S = (c == 0) ? e : __fadd_rn(S, e);
+    }
+    if (any_nan) return 0;
+    int best = 0;
+    float qb = __fdiv_rn(spec_expf(__fsub_rn(xb[0], m)), S);
+    for (int c = 1; c < C; ++c) {
+        float q = __fdiv_rn(spec_expf(__fsub_rn(xb[(int64_t)c * HW], m)), S);
+        if (q > qb) { qb = q; best = c; }
+    }
+    return best;
+}
+
+// torch.max(dim) semantics on raw scores: first index on ties, NaN is maximal (first NaN wins)
+template <int C>
+__device__ __forceinline__ int raw_argmax(const float (&x)[C]) {
+    float m = x[0];
+    int best = 0;
+    bool locked = (m != m);
+#pragma unroll
+    for (int c = 1; c < C; ++c) {
+        float v = x[c];
+        bool take = !locked && ((v != v) || (v > m));
+        if (take) { m = v; best = c; }
+        locked |= (v != v);
+    }
+    return best;
+}
+
+__device__ __forceinline__ int raw_argmax_rt(const float* xb, int C, int64_t HW) {
+    float m = xb[0];
+    int best = 0;
+    if (m != m) return 0;
+    for (int c = 1; c < C; ++c) {
+        float v = xb[(int64_t)c * HW];
+        if (v != v) return c;
+        if (v > m) { m = v; best = c; }
+    }
+    return best;
+}
+
+// ---------------------------------------------------------------------------------------------
+// transcendental wrappers for the floating-point kernels.  Default: MUFU-based intrinsics
+// (ex2.approx / lg2.approx / rcp.approx; errors ~1e-7 relative, see DESIGN.md "Accuracy budget").
+// -DDCT_ACCURATE_MATH switches to libdevice expf/logf and IEEE division for A/B checks.
+// ---------------------------------------------------------------------------------------------
+#ifdef DCT_ACCURATE_MATH
+__device__ __forceinline__ float fexp(float x) { return expf(x); }
+__device__ __forceinline__ float flog(float x) { return logf(x); }
+__device__ __forceinline__ float fdiv(float a, float b) { return a / b; }
+#else
+__device__ __forceinline__ float fexp(float x) { return __expf(x); }
+__device__ __forceinline__ float flog(float x) { return __logf(x); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdividef(a, b); }
+#endif
+
+// the reference's simplex predicate for one pixel: |sum - 1| <= 1e-8 + 1e-5 (utils/utils.py:142-151)
+__device__ __forceinline__ bool simplex_ok(float s) { return fabsf(s - 1.0f) <= (1e-8f + 1e-5f); }
+
+__device__ __forceinline__ float upstream_scalar(const Upstream& u) {
+    float g = u.gconst;
+    if (u.gscalar != nullptr) g *= __ldg(u.gscalar);
+    return g;
+}
+
+}  // namespace dct

@@ -1,0 +1,92 @@
+// dct_jsd.cu -- C-ABI entry points of the JSD family (include/dct_b200.h), argument validation and
+// dispatch to the register-tiled instantiations (dct_jsd_k*.cu) or the runtime-(K,C) fallback.
+#include "dct_jsd_kernels.cuh"
+
+namespace dct {
+
+static int jsd_launch_rt(const JsdCall& c) {
+    JsdArgsRt a;
+    for (int k = 0; k < DCT_MAX_VIEWS; ++k) {
+        a.in[k] = k < c.K ? c.views[k] : nullptr;
+        a.grad[k] = (k < c.K && c.grads) ? c.grads[k] : nullptr;
+    }
+    a.K = c.K; a.C = c.C; a.HW = c.HW; a.map = c.map; a.sum = c.sum; a.up = c.up; a.flags = c.flags; a.ws = c.ws;
+    const int threads = 256;
+    dim3 grid = image_grid(c.B, c.HW, threads);
+#define DCT_JSD_RT(LG, MD) jsd_kernel_rt<LG, MD><<<grid, threads, 0, c.stream>>>(a)
+    if (c.in_kind == DCT_IN_LOGITS) {
+        if (c.mode == kFwd) DCT_JSD_RT(true, kFwd);
+        else if (c.mode == kBwd) DCT_JSD_RT(true, kBwd);
+        else DCT_JSD_RT(true, kFwdBwd);
+    } else {
+        if (c.mode == kFwd) DCT_JSD_RT(false, kFwd);
+        else if (c.mode == kBwd) DCT_JSD_RT(false, kBwd);
+        else DCT_JSD_RT(false, kFwdBwd);
+    }
+#undef DCT_JSD_RT
+    return check_launch();
+}
+
+static int jsd_dispatch(const JsdCall& c) {
+    if (c.views == nullptr || c.K < 1 || c.C < 1 || c.B < 1 || c.HW < 1) return DCT_ERR_BAD_ARG;
+    if (c.K > DCT_MAX_VIEWS || c.C > DCT_MAX_CLASSES || c.B > 65535) return DCT_ERR_UNSUPPORTED;
+    if (c.in_kind != DCT_IN_PROBS && c.in_kind != DCT_IN_LOGITS) return DCT_ERR_BAD_ARG;
+    for (int k = 0; k < c.K; ++k) {
+        if (c.views[k] == nullptr) return DCT_ERR_BAD_ARG;
+        if (!aligned(c.views[k], 4)) return DCT_ERR_MISALIGNED;
+        if (c.mode != kFwd) {
+            if (c.grads == nullptr || c.grads[k] == nullptr) return DCT_ERR_BAD_ARG;
+            if (!aligned(c.grads[k], 4)) return DCT_ERR_MISALIGNED;
+        }
+    }
+    if (c.mode != kBwd && c.sum != nullptr && c.ws == nullptr) return DCT_ERR_BAD_ARG;
+    int rc = DCT_ERR_UNSUPPORTED;
+    switch (c.K) {
+        case 2: rc = jsd_launch_k2(c); break;
+        case 3: rc = jsd_launch_k3(c); break;
+        case 4: rc = jsd_launch_k4(c); break;
+        default: break;
+    }
+    if (rc == DCT_ERR_UNSUPPORTED) rc = jsd_launch_rt(c);
+    return rc;
+}
+
+}  // namespace dct
+
+using namespace dct;
+
+extern "C" int dct_jsd_fwd_f32(const float* const* views, int K, int C, int64_t B, int64_t HW, int in_kind,
+                               float* map, double* sum, int32_t* flags, void* workspace, void* stream) {
+    JsdCall c{views, nullptr, K, C, B, HW, in_kind, kFwd, map, sum, Upstream{nullptr, nullptr, 0.0f}, flags,
+              static_cast<Workspace*>(workspace), static_cast<cudaStream_t>(stream)};
+    return jsd_dispatch(c);
+}
+
+extern "C" int dct_jsd_bwd_f32(const float* const* views, int K, int C, int64_t B, int64_t HW, int in_kind,
+                               const float* gmap, const float* gscalar, float gconst, float* const* grad_views,
+                               void* stream) {
+    JsdCall c{views, grad_views, K, C, B, HW, in_kind, kBwd, nullptr, nullptr, Upstream{gmap, gscalar, gconst},
+              nullptr, nullptr, static_cast<cudaStream_t>(stream)};
+    return jsd_dispatch(c);
+}
+
+extern "C" int dct_jsd_fwdbwd_f32(const float* const* views, int K, int C, int64_t B, int64_t HW, int in_kind,
+                                  float gconst, float* map, double* sum, float* const* grad_views,
+                                  const int64_t* labels, int64_t* counts, int32_t* flags, void* workspace,
+                                  void* stream) {
+    JsdCall c{views, grad_views, K, C, B, HW, in_kind, kFwdBwd, map, sum, Upstream{nullptr, nullptr, gconst},
+              flags, static_cast<Workspace*>(workspace), static_cast<cudaStream_t>(stream)};
+    int rc = jsd_dispatch(c);
+    if (rc != DCT_OK) return rc;
+    if (labels != nullptr) {
+        if (counts == nullptr) return DCT_ERR_BAD_ARG;
+        // Dice counting of the K views against the same labels (unlabdiceMeters,
+        // generalframework/trainer/cotraining_totalloss.py:224); the views were just streamed
+        // through L2 by the loss kernel.
+        for (int k = 0; k < K; ++k) {
+            rc = dct_dice_counts_f32(views[k], labels, C, B, HW, counts + (int64_t)k * B * C * 3, 1, flags, stream);
+            if (rc != DCT_OK) return rc;
+        }
+    }
+    return DCT_OK;
+}

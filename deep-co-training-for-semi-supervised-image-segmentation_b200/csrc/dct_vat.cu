@@ -1,0 +1,231 @@
+// dct_vat.cu -- VAT / FGSM perturbation arithmetic on image-shaped tensors.
+//
+// Replaces VATGenerator._l2_normalize (generalframework/utils/AEGenerator.py:68-76), the scale /
+// add / clamp tail of VATGenerator.__call__ (:103,:112-117) and FSGMGenerator.adversarial_fgsm
+// (:35-51).
+//
+// _l2_normalize is a per-sample reduction followed by a per-sample rescale.  On B200 a sample of
+// M*4 bytes is spread over a thread-block CLUSTER: every CTA of the cluster keeps its slice of
+// the sample in registers, the partial sums of squares are exchanged through distributed shared
+// memory, and each CTA rescales and stores its slice -- the sample is read from HBM once and
+// written once (2*M*4 bytes, the algorithmic minimum) in a single launch.  Samples too large for
+// 8 CTAs x 256 threads x 64 floats fall back to a two-launch path (sum of squares into the
+// workspace, then rescale; the second read is served by the 126 MB L2).
+#include <cooperative_groups.h>
+
+#include "dct_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace dct {
+
+constexpr int kL2Threads = 256;
+constexpr int kL2Cluster = 8;       // portable maximum cluster size
+constexpr int kL2MaxVecPerThread = 16;  // float4 per thread held in registers (64 floats)
+
+struct L2Args {
+    const float* d;
+    float* out;
+    int64_t M;
+    float scale;
+    const float* img;  // nullable
+    float* adv;        // nullable
+    Workspace* ws;
+};
+
+__device__ __forceinline__ float block_sum_f(float v, float* s_warp) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_sum(v);
+    if (lane == 0) s_warp[wid] = v;
+    __syncthreads();
+    float t = 0.0f;
+    if (wid == 0) {
+        t = lane < nw ? s_warp[lane] : 0.0f;
+        t = warp_sum(t);
+        if (lane == 0) s_warp[0] = t;
+    }
+    __syncthreads();
+    t = s_warp[0];
+    __syncthreads();
+    return t;
+}
+
+__device__ __forceinline__ void l2_emit(const L2Args& a, int64_t off, const FVec<4>& v, float nrm) {
+    FVec<4> o;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o.v[j] = a.scale * __fdiv_rn(v.v[j], nrm);  // d /= norm ; then scale * d
+    st_stream<4>(a.out + off, o);
+    if (a.img != nullptr) {
+        FVec<4> im = ld_stream<4>(a.img + off), ad;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ad.v[j] = fminf(fmaxf(im.v[j] + o.v[j], 0.0f), 1.0f);
+        st_stream<4>(a.adv + off, ad);
+    }
+}
+
+// One cluster per sample; NV float4 per thread (compile-time so the slice lives in registers).
+template <int NV>
+__global__ void __cluster_dims__(kL2Cluster, 1, 1) __launch_bounds__(kL2Threads)
+l2_cluster_kernel(const L2Args a) {
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ float s_warp[32];
+    __shared__ float s_part;  // this CTA's partial sum of squares, read by its cluster peers
+    const unsigned int rank = cluster.block_rank();
+    const int64_t b = blockIdx.x / kL2Cluster;
+    const int64_t base = b * a.M;
+    const int64_t nvec = a.M / 4;
+    FVec<4> v[NV];
+    float ss = 0.0f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int64_t q = ((int64_t)j * kL2Cluster + rank) * kL2Threads + threadIdx.x;  // float4 index in sample
+        if (q < nvec) {
+            v[j] = ld_stream<4>(a.d + base + q * 4);
+            ss += v[j].v[0] * v[j].v[0] + v[j].v[1] * v[j].v[1] + v[j].v[2] * v[j].v[2] + v[j].v[3] * v[j].v[3];
+        }
+    }
+    float cta = block_sum_f(ss, s_warp);
+    if (threadIdx.x == 0) s_part = cta;
+    cluster.sync();
+    float tot = 0.0f;
+#pragma unroll
+    for (int r = 0; r < kL2Cluster; ++r) tot += *cluster.map_shared_rank(&s_part, r);  // DSMEM, fixed order
+    cluster.sync();  // peers may not exit (and free s_part) before everyone has read it
+    const float nrm = sqrtf(tot) + 1e-16f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int64_t q = ((int64_t)j * kL2Cluster + rank) * kL2Threads + threadIdx.x;
+        if (q < nvec) l2_emit(a, base + q * 4, v[j], nrm);
+    }
+}
+
+// fallback pass 1: per-(sample, CTA) sum of squares -> workspace partials[b * gx + x] (double)
+__global__ void __launch_bounds__(256) l2_sumsq_kernel(const float* d, int64_t M, Workspace* ws) {
+    __shared__ double s_warp[32];
+    const int64_t base = (int64_t)blockIdx.y * M;
+    double ss = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (int64_t)gridDim.x * blockDim.x) {
+        float v = d[base + i];
+        ss += (double)v * (double)v;
+    }
+    ss = warp_sum(ss);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) s_warp[wid] = ss;
+    __syncthreads();
+    if (wid == 0) {
+        double t = lane < (blockDim.x >> 5) ? s_warp[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) ws->partials[blockIdx.y * gridDim.x + blockIdx.x] = t;
+    }
+}
+
+// fallback pass 2: rescale (scalar accesses: serves any M / alignment)
+__global__ void __launch_bounds__(256) l2_scale_kernel(const L2Args a, int npart) {
+    __shared__ float s_nrm;
+    const int64_t base = (int64_t)blockIdx.y * a.M;
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int j = 0; j < npart; ++j) t += a.ws->partials[blockIdx.y * npart + j];
+        s_nrm = sqrtf((float)t) + 1e-16f;
+    }
+    __syncthreads();
+    const float nrm = s_nrm;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.M; i += (int64_t)gridDim.x * blockDim.x) {
+        float o = a.scale * __fdiv_rn(a.d[base + i], nrm);
+        a.out[base + i] = o;
+        if (a.img != nullptr) a.adv[base + i] = fminf(fmaxf(a.img[base + i] + o, 0.0f), 1.0f);
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) fgsm_kernel(const float* img, const float* grad, float eps, float* adv,
+                                                   float* noise, int64_t n) {
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC; i < n; i += (int64_t)gridDim.x * blockDim.x * VEC) {
+        FVec<VEC> im = ld_stream<VEC>(img + i), g = ld_stream<VEC>(grad + i), nz, ad;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            float s = (float)((g.v[j] > 0.0f) - (g.v[j] < 0.0f));  // torch.sign: 0 -> 0, NaN -> 0
+            nz.v[j] = eps * s;
+            ad.v[j] = im.v[j] + nz.v[j];
+        }
+        st_stream<VEC>(noise + i, nz);
+        st_stream<VEC>(adv + i, ad);
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) scale_if_not_one_kernel(float* grad, int64_t n, const float* gscalar) {
+    const float g = __ldg(gscalar);
+    if (g == 1.0f) return;  // uniform: the whole grid leaves without touching `grad`
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC; i < n; i += (int64_t)gridDim.x * blockDim.x * VEC) {
+        FVec<VEC> v = ld_stream<VEC>(grad + i);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) v.v[j] *= g;
+        st_stream<VEC>(grad + i, v);
+    }
+}
+
+static inline unsigned ew_blocks(int64_t n, int vec) {
+    int64_t b = (n / vec + 255) / 256;
+    if (b < 1) b = 1;
+    if (b > 148 * 16) b = 148 * 16;
+    return (unsigned)b;
+}
+
+}  // namespace dct
+
+using namespace dct;
+
+extern "C" int dct_l2_normalize_f32(const float* d, float* out, int64_t B, int64_t M, float scale, const float* img,
+                                    float* adv, void* workspace, void* stream) {
+    if (d == nullptr || out == nullptr || B < 1 || M < 1) return DCT_ERR_BAD_ARG;
+    if ((img == nullptr) != (adv == nullptr)) return DCT_ERR_BAD_ARG;
+    if (!aligned(d, 4) || !aligned(out, 4) || !aligned(img, 4) || !aligned(adv, 4)) return DCT_ERR_MISALIGNED;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    L2Args a{d, out, M, scale, img, adv, static_cast<Workspace*>(workspace)};
+    const bool vec_ok = (M % 4) == 0 && aligned(d, 16) && aligned(out, 16) && aligned(img, 16) && aligned(adv, 16);
+    const int64_t per_wave = (int64_t)kL2Cluster * kL2Threads * 4;  // floats covered by one float4 per thread
+    const int64_t nv = (M + per_wave - 1) / per_wave;
+    if (vec_ok && nv <= kL2MaxVecPerThread && B * kL2Cluster <= 0x7fffffff) {
+        dim3 grid((unsigned)(B * kL2Cluster));
+        if (nv <= 1) l2_cluster_kernel<1><<<grid, kL2Threads, 0, s>>>(a);
+        else if (nv <= 2) l2_cluster_kernel<2><<<grid, kL2Threads, 0, s>>>(a);
+        else if (nv <= 4) l2_cluster_kernel<4><<<grid, kL2Threads, 0, s>>>(a);
+        else if (nv <= 8) l2_cluster_kernel<8><<<grid, kL2Threads, 0, s>>>(a);
+        else l2_cluster_kernel<16><<<grid, kL2Threads, 0, s>>>(a);
+        return check_launch();
+    }
+    if (workspace == nullptr) return DCT_ERR_BAD_ARG;
+    if (B > 65535) return DCT_ERR_UNSUPPORTED;
+    int64_t gx = (M + 256 * 16 - 1) / (256 * 16);
+    int64_t cap = kMaxPartials / B;
+    if (cap < 1) return DCT_ERR_UNSUPPORTED;
+    if (gx > cap) gx = cap;
+    if (gx > 1024) gx = 1024;
+    l2_sumsq_kernel<<<dim3((unsigned)gx, (unsigned)B), 256, 0, s>>>(d, M, a.ws);
+    int rc = check_launch();
+    if (rc != DCT_OK) return rc;
+    l2_scale_kernel<<<dim3((unsigned)gx, (unsigned)B), 256, 0, s>>>(a, (int)gx);
+    return check_launch();
+}
+
+extern "C" int dct_fgsm_f32(const float* img, const float* grad, float eps, float* adv, float* noise, int64_t n,
+                            void* stream) {
+    if (img == nullptr || grad == nullptr || adv == nullptr || noise == nullptr || n < 1) return DCT_ERR_BAD_ARG;
+    if (!aligned(img, 4) || !aligned(grad, 4) || !aligned(adv, 4) || !aligned(noise, 4)) return DCT_ERR_MISALIGNED;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if ((n % 4) == 0 && aligned(img, 16) && aligned(grad, 16) && aligned(adv, 16) && aligned(noise, 16))
+        fgsm_kernel<4><<<ew_blocks(n, 4), 256, 0, s>>>(img, grad, eps, adv, noise, n);
+    else
+        fgsm_kernel<1><<<ew_blocks(n, 1), 256, 0, s>>>(img, grad, eps, adv, noise, n);
+    return check_launch();
+}
+
+extern "C" int dct_scale_if_not_one_f32(float* grad, int64_t n, const float* gscalar, void* stream) {
+    if (grad == nullptr || gscalar == nullptr || n < 1) return DCT_ERR_BAD_ARG;
+    if (!aligned(grad, 4) || !aligned(gscalar, 4)) return DCT_ERR_MISALIGNED;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if ((n % 4) == 0 && aligned(grad, 16)) scale_if_not_one_kernel<4><<<ew_blocks(n, 4), 256, 0, s>>>(grad, n, gscalar);
+    else scale_if_not_one_kernel<1><<<ew_blocks(n, 1), 256, 0, s>>>(grad, n, gscalar);
+    return check_launch();
+}

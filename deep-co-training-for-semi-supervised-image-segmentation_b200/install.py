@@ -1,0 +1,61 @@
+"""Install the B200 drop-ins into an importable reference tree WITHOUT editing it.
+
+    import generalframework                      # the unmodified reference
+    import dct_b200
+    dct_b200.install()                           # rebinding only; configs and CoTrainer untouched
+
+After ``install()`` the reference's trainers pick up the CUDA-backed classes at
+their existing call sites:
+  get_loss_fn('jsd')                       -> loss.LOSS['jsd']                (loss/__init__.py:6-16)
+  KL_Divergence_2D(reduce=True)(adv, real) -> trainer-module globals           (cotraining_totalloss.py:13,392)
+  VATGenerator / FSGMGenerator             -> trainer-module globals           (cotraining_totalloss.py:15)
+  DiceMeter / IoU                          -> metrics package + trainer globals (cotraining_totalloss.py:18)
+``uninstall()`` restores the originals.
+"""
+import importlib
+import sys
+
+from . import generators, loss, metrics
+
+_REBIND = {
+    "JSD_2D": loss.JSD_2D, "JSD": loss.JSD, "Entropy_2D": loss.Entropy_2D, "Entropy": loss.Entropy,
+    "KL_Divergence_2D": loss.KL_Divergence_2D, "KL_Divergence_2D_Logit": loss.KL_Divergence_2D_Logit,
+    "KL_div": loss.KL_div,
+    "FSGMGenerator": generators.FSGMGenerator, "VATGenerator": generators.VATGenerator,
+    "DiceMeter": metrics.DiceMeter, "IoU": metrics.IoU, "ConfusionMatrix": metrics.ConfusionMatrix,
+}
+_saved = []
+
+
+def install(package: str = "generalframework") -> int:
+    """Rebind the hot-path names in every already-imported ``<package>.*`` module. Returns #rebindings."""
+    try:
+        importlib.import_module(package + ".loss")
+        importlib.import_module(package + ".metrics")
+    except Exception:
+        pass
+    n = 0
+    for modname, mod in list(sys.modules.items()):
+        if mod is None or not (modname == package or modname.startswith(package + ".")):
+            continue
+        for name, repl in _REBIND.items():
+            cur = mod.__dict__.get(name)
+            if cur is not None and cur is not repl and isinstance(cur, type):
+                _saved.append((mod, name, cur))
+                setattr(mod, name, repl)
+                n += 1
+        reg = mod.__dict__.get("LOSS")
+        if isinstance(reg, dict) and "jsd" in reg and reg["jsd"] is not loss.JSD_2D:
+            _saved.append((reg, "jsd", reg["jsd"]))
+            reg["jsd"] = loss.JSD_2D
+            n += 1
+    return n
+
+
+def uninstall() -> None:
+    while _saved:
+        holder, name, orig = _saved.pop()
+        if isinstance(holder, dict):
+            holder[name] = orig
+        else:
+            setattr(holder, name, orig)

@@ -1,0 +1,486 @@
+"""Drop-in losses of the consistency path, backed by the sm_100a kernels.
+
+Mirrors ``generalframework/loss/loss.py`` of the reference (class names, ctor
+arguments, call signatures, return shapes/dtypes, AssertionError behaviour):
+
+  JSD_2D, JSD            loss.py:183-196, 165-180
+  Entropy_2D, Entropy    loss.py:70-84, 53-67
+  KL_Divergence_2D       loss.py:110-134
+  KL_Divergence_2D_Logit loss.py:137-162
+  KL_div                 loss.py:87-107
+  get_loss_fn / LOSS     loss/__init__.py:6-16   (only the consistency entries)
+
+plus the fast path the north star asks for -- one pass over the K views' LOGITS
+producing the weighted mean JSD, its gradient and (optionally) the K Dice count
+tensors: :func:`jsd_consistency_from_logits` / :class:`FusedJSDConsistency`, and
+:func:`kl_consistency_from_logits` for the adversarial KL.
+
+Every forward/backward is a ``torch.autograd.Function`` whose body is one call
+into the C ABI (``include/dct_b200.h``); inputs must be CUDA float32 tensors.
+"""
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import _lib, _runtime
+
+
+def _prep(t: torch.Tensor, what: str) -> torch.Tensor:
+    _runtime.require_cuda(t, what)
+    if t.dtype != torch.float32:
+        raise TypeError(f"{what}: float32 expected, got {t.dtype}")
+    return t.contiguous()
+
+
+def _bchw(t: torch.Tensor):
+    b, c = t.shape[0], t.shape[1]
+    hw = 1
+    for s in t.shape[2:]:
+        hw *= s
+    return b, c, hw
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _views_args(views: Sequence[torch.Tensor], what: str):
+    assert len(views) >= 1
+    vs = [_prep(v, what) for v in views]
+    for v in vs[1:]:
+        assert v.shape == vs[0].shape, "all views must have the same shape"
+    if len(vs) > _lib.MAX_VIEWS or vs[0].shape[1] > _lib.MAX_CLASSES:
+        raise ValueError(f"{what}: at most {_lib.MAX_VIEWS} views and {_lib.MAX_CLASSES} classes are supported")
+    return vs
+
+
+# ------------------------------------------------------------------------------------------------
+# JSD
+# ------------------------------------------------------------------------------------------------
+class _JSDFn(torch.autograd.Function):
+    """map = JSD(views) with views given as probs or logits; backward recomputes from the inputs."""
+
+    @staticmethod
+    def forward(ctx, in_kind: int, reduce: bool, *views):
+        vs = _views_args(views, "JSD")
+        b, c, hw = _bchw(vs[0])
+        dev = vs[0].device
+        st = _runtime.state(dev)
+        h = _lib.lib()
+        out_map = None if reduce else torch.empty((b,) + tuple(vs[0].shape[2:]), dtype=torch.float32, device=dev)
+        total = torch.empty(1, dtype=torch.float64, device=dev) if reduce else None
+        _lib.check(h.dct_jsd_fwd_f32(_lib.ptr_array(vs), len(vs), c, b, hw, in_kind, _ptr(out_map), _ptr(total),
+                                     _runtime.flags_ptr(st) if in_kind == _lib.IN_PROBS else None,
+                                     st.workspace.data_ptr(), _runtime.stream_ptr(dev)), "dct_jsd_fwd_f32")
+        if in_kind == _lib.IN_PROBS:
+            _runtime.after_call(st)
+        ctx.save_for_backward(*vs)
+        ctx.in_kind, ctx.reduce, ctx.n = in_kind, reduce, b * hw
+        if reduce:
+            return (total / float(b * hw)).to(torch.float32).reshape(())
+        return out_map
+
+    @staticmethod
+    def backward(ctx, g):
+        vs = ctx.saved_tensors
+        b, c, hw = _bchw(vs[0])
+        dev = vs[0].device
+        g = g.contiguous().to(torch.float32)
+        grads = [torch.empty_like(v) for v in vs]
+        if ctx.reduce:
+            gmap, gscalar, gconst = None, g, 1.0 / ctx.n
+        else:
+            gmap, gscalar, gconst = g, None, 1.0
+        _lib.check(_lib.lib().dct_jsd_bwd_f32(_lib.ptr_array(vs), len(vs), c, b, hw, ctx.in_kind, _ptr(gmap),
+                                              _ptr(gscalar), gconst, _lib.ptr_array(grads),
+                                              _runtime.stream_ptr(dev)), "dct_jsd_bwd_f32")
+        return (None, None) + tuple(grads)
+
+
+class JSD_2D(nn.Module):
+    """K-view Jensen-Shannon divergence map; drop-in for ``JSD_2D`` (loss.py:183-196).
+
+    ``forward(List[Tensor[B,C,H,W]] of probabilities) -> Tensor[B,H,W]``, differentiable w.r.t.
+    every list element; AssertionError on non-4-D or non-simplex input (unless ``python -O``).
+    """
+
+    def __init__(self):
+        super().__init__()
+
+    def forward(self, input: List[torch.Tensor]):
+        for inprob in input:
+            assert inprob.shape.__len__() == 4
+        return _JSDFn.apply(_lib.IN_PROBS, False, *input)
+
+
+class JSD(nn.Module):
+    """N-d variant with optional mean; drop-in for ``JSD`` (loss.py:165-180)."""
+
+    def __init__(self):
+        super().__init__()
+
+    def forward(self, input: List[torch.Tensor], reduce=True):
+        for inprob in input:
+            assert inprob.shape.__len__() >= 2
+        return _JSDFn.apply(_lib.IN_PROBS, bool(reduce), *input)
+
+
+def jsd_map_from_logits(logits: Sequence[torch.Tensor]) -> torch.Tensor:
+    """``JSD_2D([softmax(z, 1) for z in logits])`` without materialising the probabilities."""
+    return _JSDFn.apply(_lib.IN_LOGITS, False, *logits)
+
+
+class _FusedJSDFn(torch.autograd.Function):
+    """weight * mean(JSD(softmax(logits))) and its gradient in ONE pass (dct_jsd_fwdbwd_f32)."""
+
+    @staticmethod
+    def forward(ctx, weight: float, n_global: Optional[int], labels, counts, in_kind: int, *views):
+        vs = _views_args(views, "jsd_consistency")
+        b, c, hw = _bchw(vs[0])
+        dev = vs[0].device
+        st = _runtime.state(dev)
+        n = b * hw if n_global is None else int(n_global)
+        need_grad = any(ctx.needs_input_grad[5:])
+        total = torch.empty(1, dtype=torch.float64, device=dev)
+        h = _lib.lib()
+        lab = None
+        if labels is not None:
+            _runtime.require_cuda(labels, "labels")
+            assert labels.dtype == torch.int64 and labels.numel() == b * hw
+            assert counts is not None and counts.dtype == torch.int64 and counts.numel() == len(vs) * b * c * 3
+            lab = labels.contiguous()
+        fl = _runtime.flags_ptr(st)
+        if need_grad:
+            grads = [torch.empty_like(v) for v in vs]
+            _lib.check(h.dct_jsd_fwdbwd_f32(_lib.ptr_array(vs), len(vs), c, b, hw, in_kind, float(weight) / n, None,
+                                            _ptr(total), _lib.ptr_array(grads), _ptr(lab), _ptr(counts), fl,
+                                            st.workspace.data_ptr(), _runtime.stream_ptr(dev)), "dct_jsd_fwdbwd_f32")
+            ctx.grads = grads
+        else:
+            _lib.check(h.dct_jsd_fwd_f32(_lib.ptr_array(vs), len(vs), c, b, hw, in_kind, None, _ptr(total), fl,
+                                         st.workspace.data_ptr(), _runtime.stream_ptr(dev)), "dct_jsd_fwd_f32")
+            if lab is not None:
+                for k, v in enumerate(vs):
+                    _lib.check(h.dct_dice_counts_f32(v.data_ptr(), lab.data_ptr(), c, b, hw,
+                                                     counts.data_ptr() + k * b * c * 3 * 8, 1, fl,
+                                                     _runtime.stream_ptr(dev)), "dct_dice_counts_f32")
+            ctx.grads = None
+        if lab is not None or in_kind == _lib.IN_PROBS:
+            _runtime.after_call(st)
+        return (total * (float(weight) / n)).to(torch.float32).reshape(())
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        grads = ctx.grads
+        ctx.grads = None
+        if grads is None:
+            raise RuntimeError("jsd_consistency: backward called twice or without grad-requiring inputs")
+        g = g.contiguous().to(torch.float32)
+        h = _lib.lib()
+        dev = grads[0].device
+        for gr in grads:  # no-op launch (zero traffic) for the usual upstream of exactly 1
+            _lib.check(h.dct_scale_if_not_one_f32(gr.data_ptr(), gr.numel(), g.data_ptr(), _runtime.stream_ptr(dev)),
+                       "dct_scale_if_not_one_f32")
+        return (None, None, None, None, None) + tuple(grads)
+
+
+def jsd_consistency_from_logits(logits: Sequence[torch.Tensor], weight: float = 1.0,
+                                labels: Optional[torch.Tensor] = None, dice_counts: Optional[torch.Tensor] = None,
+                                n_global: Optional[int] = None) -> torch.Tensor:
+    """``weight * JSD_2D([softmax(z,1) for z in logits]).mean()`` in one pass over the logits.
+
+    The gradient w.r.t. every logits tensor is produced by the same kernel launch (upstream
+    ``weight / N`` folded in), so ``loss.backward()`` costs no further pass.  If ``labels``
+    ([B,1,H,W] / [B,H,W] int64) and ``dice_counts`` (int64 ``[K,B,C,3]``, accumulated into) are
+    given, the K views' Dice counts (I, G, P) against ``labels`` are produced as well
+    (what ``unlabdiceMeters[k].add`` computes, cotraining_totalloss.py:224).
+    ``n_global``: total pixel count over all data-parallel ranks (defaults to the local B*H*W).
+    """
+    return _FusedJSDFn.apply(float(weight), n_global, labels, dice_counts, _lib.IN_LOGITS, *logits)
+
+
+class FusedJSDConsistency(nn.Module):
+    """Module form of :func:`jsd_consistency_from_logits` (logits in, weighted scalar loss out)."""
+
+    def __init__(self, weight: float = 1.0):
+        super().__init__()
+        self.weight = weight
+
+    def forward(self, logits: List[torch.Tensor], labels=None, dice_counts=None, n_global=None):
+        return jsd_consistency_from_logits(logits, self.weight, labels, dice_counts, n_global)
+
+
+# ------------------------------------------------------------------------------------------------
+# Entropy
+# ------------------------------------------------------------------------------------------------
+class _EntropyFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p):
+        p = _prep(p, "Entropy")
+        b, c, hw = _bchw(p)
+        st = _runtime.state(p.device)
+        out = torch.empty((b,) + tuple(p.shape[2:]), dtype=torch.float32, device=p.device)
+        _lib.check(_lib.lib().dct_entropy_fwd_f32(p.data_ptr(), c, b, hw, out.data_ptr(), None, _runtime.flags_ptr(st),
+                                                  st.workspace.data_ptr(), _runtime.stream_ptr(p.device)),
+                   "dct_entropy_fwd_f32")
+        _runtime.after_call(st)
+        ctx.save_for_backward(p)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (p,) = ctx.saved_tensors
+        b, c, hw = _bchw(p)
+        gp = torch.empty_like(p)
+        g = g.contiguous().to(torch.float32)
+        _lib.check(_lib.lib().dct_entropy_bwd_f32(p.data_ptr(), c, b, hw, g.data_ptr(), None, 1.0, gp.data_ptr(),
+                                                  _runtime.stream_ptr(p.device)), "dct_entropy_bwd_f32")
+        return gp
+
+
+class Entropy(nn.Module):
+    """``-sum_c p log(p + 1e-16)`` over dim 1; drop-in for ``Entropy`` (loss.py:53-67)."""
+
+    def __init__(self):
+        super().__init__()
+
+    def forward(self, input: torch.Tensor):
+        assert input.shape.__len__() >= 2
+        return _EntropyFn.apply(input)
+
+
+class Entropy_2D(nn.Module):
+    """Drop-in for ``Entropy_2D`` (loss.py:70-84): 4-D input -> [B,H,W]."""
+
+    def __init__(self):
+        super().__init__()
+
+    def forward(self, input: torch.Tensor):
+        assert input.shape.__len__() == 4
+        return _EntropyFn.apply(input)
+
+
+# ------------------------------------------------------------------------------------------------
+# KL family
+# ------------------------------------------------------------------------------------------------
+class _KLProbFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p, y, reduce: bool, eps: float):
+        p = _prep(p, "KL_Divergence_2D"); y = _prep(y, "KL_Divergence_2D")
+        assert p.shape == y.shape
+        b, c, hw = _bchw(p)
+        dev = p.device
+        st = _runtime.state(dev)
+        out_map = None if reduce else torch.empty((b,) + tuple(p.shape[2:]), dtype=torch.float32, device=dev)
+        total = torch.empty(1, dtype=torch.float64, device=dev) if reduce else None
+        _lib.check(_lib.lib().dct_kl_fwd_f32(p.data_ptr(), y.data_ptr(), c, b, hw, float(eps), _ptr(out_map),
+                                             _ptr(total), _runtime.flags_ptr(st), st.workspace.data_ptr(),
+                                             _runtime.stream_ptr(dev)), "dct_kl_fwd_f32")
+        _runtime.after_call(st)
+        ctx.save_for_backward(p, y)
+        ctx.reduce, ctx.eps, ctx.n = reduce, float(eps), b * hw
+        if reduce:
+            return (total / float(b * hw)).to(torch.float32).reshape(())
+        return out_map
+
+    @staticmethod
+    def backward(ctx, g):
+        p, y = ctx.saved_tensors
+        b, c, hw = _bchw(p)
+        g = g.contiguous().to(torch.float32)
+        gp = torch.empty_like(p) if ctx.needs_input_grad[0] else None
+        gy = torch.empty_like(y) if ctx.needs_input_grad[1] else None
+        if gp is None and gy is None:
+            return None, None, None, None
+        if ctx.reduce:
+            gmap, gscalar, gconst = None, g, 1.0 / ctx.n
+        else:
+            gmap, gscalar, gconst = g, None, 1.0
+        _lib.check(_lib.lib().dct_kl_bwd_f32(p.data_ptr(), y.data_ptr(), c, b, hw, ctx.eps, _ptr(gmap), _ptr(gscalar),
+                                             gconst, _ptr(gp), _ptr(gy), _runtime.stream_ptr(p.device)),
+                   "dct_kl_bwd_f32")
+        return gp, gy, None, None
+
+
+class KL_Divergence_2D(nn.Module):
+    """Drop-in for ``KL_Divergence_2D`` (loss.py:110-134): ``sum_c y log(y+eps) - y log(p+eps)``."""
+
+    def __init__(self, reduce=False, eps=1e-10):
+        super().__init__()
+        self.reduce = reduce
+        self.eps = eps
+
+    def forward(self, p_prob: torch.Tensor, y_prob: torch.Tensor):
+        return _KLProbFn.apply(p_prob, y_prob, bool(self.reduce), self.eps)
+
+
+class _KLLogitFn(torch.autograd.Function):
+    """kl_div_with_logit(q_logit, p_logit): map and both gradients from one launch each way."""
+
+    @staticmethod
+    def forward(ctx, q_logit, p_logit, reduce: bool):
+        ql = _prep(q_logit, "kl_div_with_logit"); pl = _prep(p_logit, "kl_div_with_logit")
+        assert ql.shape == pl.shape
+        b, c, hw = _bchw(ql)
+        dev = ql.device
+        st = _runtime.state(dev)
+        out_map = None if reduce else torch.empty((b,) + tuple(ql.shape[2:]), dtype=torch.float32, device=dev)
+        total = torch.empty(1, dtype=torch.float64, device=dev) if reduce else None
+        _lib.check(_lib.lib().dct_kl_logit_f32(ql.data_ptr(), pl.data_ptr(), c, b, hw, _ptr(out_map), _ptr(total), 0,
+                                               None, None, 1.0, None, None, st.workspace.data_ptr(),
+                                               _runtime.stream_ptr(dev)), "dct_kl_logit_f32")
+        ctx.save_for_backward(ql, pl)
+        ctx.reduce, ctx.n = reduce, b * hw
+        if reduce:
+            return (total / float(b * hw)).to(torch.float32).reshape(())
+        return out_map
+
+    @staticmethod
+    def backward(ctx, g):
+        ql, pl = ctx.saved_tensors
+        b, c, hw = _bchw(ql)
+        dev = ql.device
+        g = g.contiguous().to(torch.float32)
+        gq = torch.empty_like(ql) if ctx.needs_input_grad[0] else None
+        gp = torch.empty_like(pl) if ctx.needs_input_grad[1] else None
+        if gq is None and gp is None:
+            return None, None, None
+        if ctx.reduce:
+            gmap, gscalar, gconst = None, g, 1.0 / ctx.n
+        else:
+            gmap, gscalar, gconst = g, None, 1.0
+        st = _runtime.state(dev)
+        _lib.check(_lib.lib().dct_kl_logit_f32(ql.data_ptr(), pl.data_ptr(), c, b, hw, None, None, 1, _ptr(gmap),
+                                               _ptr(gscalar), gconst, _ptr(gp), _ptr(gq), st.workspace.data_ptr(),
+                                               _runtime.stream_ptr(dev)), "dct_kl_logit_f32")
+        return gq, gp, None
+
+
+def kl_div_with_logit(q_logit: torch.Tensor, p_logit: torch.Tensor) -> torch.Tensor:
+    """Drop-in for ``VATGenerator.kl_div_with_logit`` (utils/AEGenerator.py:78-91) -> [B,H,W]."""
+    return _KLLogitFn.apply(q_logit, p_logit, False)
+
+
+class KL_Divergence_2D_Logit(nn.Module):
+    """Drop-in for ``KL_Divergence_2D_Logit`` (loss.py:137-162); ``y_logit`` plays the role of q."""
+
+    def __init__(self, reduce=False, eps=1e-10):
+        super().__init__()
+        self.reduce = reduce
+        self.eps = eps
+
+    def forward(self, p_logit: torch.Tensor, y_logit: torch.Tensor):
+        return _KLLogitFn.apply(y_logit, p_logit, bool(self.reduce))
+
+
+class KL_div(nn.Module):
+    """Drop-in for ``KL_div`` (loss.py:87-107), forward only (no trainer differentiates it)."""
+
+    def __init__(self, reduce=True, eps=1e-10):
+        super().__init__()
+        self.eps = eps
+        self.reduce = reduce
+
+    def forward(self, p, q, reduce=False):
+        p = _prep(p, "KL_div"); q = _prep(q, "KL_div")
+        assert p.shape == q.shape
+        b, c, hw = _bchw(p)
+        st = _runtime.state(p.device)
+        out = torch.empty((b,) + tuple(p.shape[2:]), dtype=torch.float32, device=p.device)
+        total = torch.empty(1, dtype=torch.float64, device=p.device)
+        _lib.check(_lib.lib().dct_kl_div_fwd_f32(p.data_ptr(), q.data_ptr(), c, b, hw, float(self.eps), out.data_ptr(),
+                                                 total.data_ptr(), _runtime.flags_ptr(st), st.workspace.data_ptr(),
+                                                 _runtime.stream_ptr(p.device)), "dct_kl_div_fwd_f32")
+        _runtime.after_call(st)
+        if self.reduce:
+            return (total / float(b * hw)).to(torch.float32).reshape(())
+        return out
+
+
+class _KLFromLogitsFn(torch.autograd.Function):
+    """weight * KL_Divergence_2D(reduce=True)(softmax(p_logit), y_prob.detach()) + grad in one pass."""
+
+    @staticmethod
+    def forward(ctx, p_logit, y_prob, weight: float, eps: float, n_global: Optional[int]):
+        pl = _prep(p_logit, "kl_consistency"); y = _prep(y_prob, "kl_consistency")
+        assert pl.shape == y.shape
+        b, c, hw = _bchw(pl)
+        dev = pl.device
+        st = _runtime.state(dev)
+        n = b * hw if n_global is None else int(n_global)
+        total = torch.empty(1, dtype=torch.float64, device=dev)
+        grad = torch.empty_like(pl) if ctx.needs_input_grad[0] else None
+        _lib.check(_lib.lib().dct_kl_from_logits_fwdbwd_f32(pl.data_ptr(), y.data_ptr(), c, b, hw, float(eps),
+                                                            float(weight) / n, None, total.data_ptr(), _ptr(grad),
+                                                            _runtime.flags_ptr(st), st.workspace.data_ptr(),
+                                                            _runtime.stream_ptr(dev)), "dct_kl_from_logits_fwdbwd_f32")
+        _runtime.after_call(st)
+        ctx.grad = grad
+        return (total * (float(weight) / n)).to(torch.float32).reshape(())
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        grad = ctx.grad
+        ctx.grad = None
+        if grad is None:
+            return None, None, None, None, None
+        g = g.contiguous().to(torch.float32)
+        _lib.check(_lib.lib().dct_scale_if_not_one_f32(grad.data_ptr(), grad.numel(), g.data_ptr(),
+                                                       _runtime.stream_ptr(grad.device)), "dct_scale_if_not_one_f32")
+        return grad, None, None, None, None
+
+
+def kl_consistency_from_logits(adv_logit: torch.Tensor, real_prob: torch.Tensor, weight: float = 1.0,
+                               eps: float = 1e-10, n_global: Optional[int] = None) -> torch.Tensor:
+    """``weight * KL_Divergence_2D(reduce=True)(softmax(adv_logit,1), real_prob.detach())`` in one pass.
+
+    The adversarial loss of ``CoTrainer._FSGM_adv_training`` (cotraining_totalloss.py:391-392) /
+    ``VatTrainer`` (vattrainer.py:152-154) with the softmax, the mean and the backward fused.
+    """
+    return _KLFromLogitsFn.apply(adv_logit, real_prob.detach(), float(weight), float(eps), n_global)
+
+
+# ------------------------------------------------------------------------------------------------
+# softmax as a standalone op (Segmentator.predict(logit=False), models/segmentators.py:46-50)
+# ------------------------------------------------------------------------------------------------
+class _SoftmaxFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _prep(x, "softmax")
+        b, c, hw = _bchw(x)
+        p = torch.empty_like(x)
+        _lib.check(_lib.lib().dct_softmax_fwd_f32(x.data_ptr(), c, b, hw, p.data_ptr(), _runtime.stream_ptr(x.device)),
+                   "dct_softmax_fwd_f32")
+        ctx.save_for_backward(p)
+        return p
+
+    @staticmethod
+    def backward(ctx, gp):
+        (p,) = ctx.saved_tensors
+        b, c, hw = _bchw(p)
+        gp = gp.contiguous().to(torch.float32)
+        gx = torch.empty_like(p)
+        _lib.check(_lib.lib().dct_softmax_bwd_f32(p.data_ptr(), gp.data_ptr(), c, b, hw, gx.data_ptr(),
+                                                  _runtime.stream_ptr(p.device)), "dct_softmax_bwd_f32")
+        return gx
+
+
+def softmax_dim1(x: torch.Tensor) -> torch.Tensor:
+    """``F.softmax(x, 1)`` for [B,C,*] CUDA float32 tensors."""
+    return _SoftmaxFn.apply(x)
+
+
+# ------------------------------------------------------------------------------------------------
+# registry (loss/__init__.py:6-16); only the entries that live on the consistency path
+# ------------------------------------------------------------------------------------------------
+LOSS = {"jsd": JSD_2D}
+
+
+def get_loss_fn(name: str, **kwargs):
+    try:
+        return LOSS.get(name)(**kwargs)
+    except Exception as e:
+        raise ValueError("name error when inputting the loss name, with %s" % str(e))

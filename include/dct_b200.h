@@ -1,0 +1,201 @@
+/*
+ * dct_b200.h -- C ABI of libdct_b200.so: the B200 (sm_100a) kernels for the
+ * consistency hot path of Deep Co-Training for semi-supervised segmentation.
+ *
+ * The reference (jizongFox/Deep-Co-Training-for-Semi-Supervised-Image-Segmentation,
+ * pure Python/PyTorch) has no FFI: its "plugin interface" for this path is the
+ * set of duck-typed Python objects the trainers call.  Each
+ * entry point below names the reference function(s) it replaces, as file:line
+ * into the reference tree.  The Python mirror of the reference interface lives in
+ * deep-co-training-for-semi-supervised-image-segmentation_b200/ and calls ONLY
+ * these functions (ctypes); INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer unless marked "host".  Tensors are NCHW
+ *    contiguous float32: element (b,c,i) of a [B,C,HW] tensor at (b*C+c)*HW+i;
+ *    maps are [B,HW] float32; labels are [B,HW] int64 (the reference's dtype).
+ *  - No allocation, no ownership transfer, no global state, re-entrant.  All
+ *    buffers belong to the caller and must stay alive until the stream reaches
+ *    the end of the call's work.  Calls enqueue on `stream` (a cudaStream_t,
+ *    NULL = legacy default stream) and never synchronise.
+ *  - `workspace`: >= dct_workspace_bytes() bytes, zero-initialised ONCE by the
+ *    caller, private to one stream at a time (kernels leave it zeroed again).
+ *  - `flags`: int32[DCT_NUM_FLAGS], caller-zeroed; kernels only ever add to it.
+ *      flags[DCT_FLAG_SIMPLEX]  += #pixels whose class sum fails the reference's
+ *                                  utils.simplex allclose(sum,1) (utils/utils.py:142-151)
+ *      flags[DCT_FLAG_LABEL]    += #labels outside [0,C) (class2one_hot's assert, utils.py:190)
+ *    May be NULL (checks compiled out of the launch).
+ *  - Upstream gradient of a [B,HW] map output ("dct_upstream"): the per-pixel
+ *    incoming gradient is   gconst * (gscalar ? *gscalar : 1) * (gmap ? gmap[b,i] : 1).
+ *  - Return value: DCT_OK (0) or a negative DCT_ERR_* code; nothing was launched
+ *    on error except where noted.
+ */
+#ifndef DCT_B200_H
+#define DCT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCT_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define DCT_API __attribute__((visibility("default")))
+#else
+#define DCT_API
+#endif
+
+enum {
+    DCT_OK = 0,
+    DCT_ERR_BAD_ARG = -1,      /* null pointer / non-positive size / K or C out of range */
+    DCT_ERR_UNSUPPORTED = -2,  /* shape not supported by any kernel (K > 8 or C > 64) */
+    DCT_ERR_MISALIGNED = -3,   /* a pointer is not 4-byte (float) / 8-byte (int64) aligned */
+    DCT_ERR_CUDA = -4,         /* the launch itself failed; see dct_last_cuda_error() */
+    DCT_ERR_NO_DEVICE = -5     /* no CUDA device / not an sm_100 device */
+};
+
+enum { DCT_FLAG_SIMPLEX = 0, DCT_FLAG_LABEL = 1, DCT_FLAG_PRED = 2, DCT_NUM_FLAGS = 4 };
+
+/* input kind of the K view tensors handed to the JSD entry points */
+enum { DCT_IN_PROBS = 0, DCT_IN_LOGITS = 1 };
+
+#define DCT_MAX_VIEWS 8
+#define DCT_MAX_CLASSES 64
+
+DCT_API int dct_abi_version(void);
+DCT_API const char* dct_error_string(int code);
+/* cudaGetErrorString of the last failing CUDA call made by this library on the calling thread */
+DCT_API const char* dct_last_cuda_error(void);
+/* DCT_OK if device `ordinal` is usable by this library (compute capability 10.x) */
+DCT_API int dct_device_check(int ordinal);
+DCT_API size_t dct_workspace_bytes(void);
+
+/* ------------------------------------------------------------------------------------------
+ * K-view Jensen-Shannon divergence.
+ * Replaces JSD_2D.forward (generalframework/loss/loss.py:183-196), JSD.forward (:165-180)
+ * and, with DCT_IN_LOGITS, the
+ * F.softmax(logits, 1) that produces their inputs (generalframework/models/segmentators.py:46-50).
+ *   m = ((x0+x1)+..)/K ; out = H(m) - (H(x0)+..)/K ; H(p) = -sum_c p*log(p+1e-16)
+ * `views`: HOST array of K device pointers, each [B,C,HW].
+ * ------------------------------------------------------------------------------------------ */
+
+/* forward only: map (nullable) [B,HW]; sum (nullable) double[1] = sum over all pixels of the map
+ * (deterministic: fixed-order two-stage reduction). */
+DCT_API int dct_jsd_fwd_f32(const float* const* views, int K, int C, int64_t B, int64_t HW, int in_kind,
+                    float* map, double* sum, int32_t* flags, void* workspace, void* stream);
+
+/* backward: grad_views[k] = upstream * d out / d views[k]  (w.r.t. probs, or through the softmax
+ * w.r.t. logits when in_kind == DCT_IN_LOGITS).  `grad_views`: HOST array of K device pointers. */
+DCT_API int dct_jsd_bwd_f32(const float* const* views, int K, int C, int64_t B, int64_t HW, int in_kind,
+                    const float* gmap, const float* gscalar, float gconst,
+                    float* const* grad_views, void* stream);
+
+/* one pass: forward (map nullable, sum nullable) AND gradient with a per-pixel upstream `gconst`
+ * known up front (e.g. cot_weight / N for `weight * JSD_2D(..).mean()`,
+ * generalframework/trainer/cotraining_totalloss.py:225-226,246).
+ * Optional fused Dice counting for the K views on the same read (unlabdiceMeters,
+ * cotraining_totalloss.py:224): if `labels` != NULL, `counts` int64 [K][B][C][3] (I, G, P) is
+ * ACCUMULATED into with pred_k = argmax softmax(views[k]) exactly as dct_dice_counts_f32. */
+DCT_API int dct_jsd_fwdbwd_f32(const float* const* views, int K, int C, int64_t B, int64_t HW, int in_kind,
+                       float gconst, float* map, double* sum, float* const* grad_views,
+                       const int64_t* labels, int64_t* counts,
+                       int32_t* flags, void* workspace, void* stream);
+
+/* grad[i] *= *gscalar for i < n, skipped entirely (no memory traffic) when *gscalar == 1.0f.
+ * Used by the fused loss' backward: the upstream of `total = sup + fused_loss` is exactly 1. */
+DCT_API int dct_scale_if_not_one_f32(float* grad, int64_t n, const float* gscalar, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * KL family of the adversarial step.
+ * ------------------------------------------------------------------------------------------ */
+
+/* KL_Divergence_2D.forward (loss.py:110-134): out = sum_c y*log(y+eps) - sum_c y*log(p+eps).
+ * map nullable, sum nullable (as above). */
+DCT_API int dct_kl_fwd_f32(const float* p, const float* y, int C, int64_t B, int64_t HW, float eps,
+                   float* map, double* sum, int32_t* flags, void* workspace, void* stream);
+/* its backward: grad_p (nullable) = up * (-y/(p+eps)); grad_y (nullable) = up * (log(y+eps)+y/(y+eps)-log(p+eps)) */
+DCT_API int dct_kl_bwd_f32(const float* p, const float* y, int C, int64_t B, int64_t HW, float eps,
+                   const float* gmap, const float* gscalar, float gconst,
+                   float* grad_p, float* grad_y, void* stream);
+
+/* VATGenerator.kl_div_with_logit(q_logit, p_logit) (generalframework/utils/AEGenerator.py:78-91) and
+ * KL_Divergence_2D_Logit(p_logit, y_logit) (loss.py:137-162, with q := y):
+ *   q = softmax(q_logit); out = sum_c q*(log_softmax(q_logit) - log_softmax(p_logit)).
+ * One pass: map (nullable), sum (nullable), and if has_upstream != 0 the gradients
+ *   grad_p_logit (nullable) = up*(softmax(p_logit) - q),  grad_q_logit (nullable) = up*q*((logq-logp) - out). */
+DCT_API int dct_kl_logit_f32(const float* q_logit, const float* p_logit, int C, int64_t B, int64_t HW,
+                     float* map, double* sum,
+                     int has_upstream, const float* gmap, const float* gscalar, float gconst,
+                     float* grad_p_logit, float* grad_q_logit, void* workspace, void* stream);
+
+/* the trainers' composite  KL_Divergence_2D(reduce=True)(softmax(adv_logits), real_probs.detach())
+ * (cotraining_totalloss.py:391-392, vattrainer.py:152-154) in one pass over logits:
+ * sum (nullable) of the KL map, grad_logits (nullable) = gconst * softmax_backward(-y/(p+eps)). */
+DCT_API int dct_kl_from_logits_fwdbwd_f32(const float* p_logit, const float* y_prob, int C, int64_t B, int64_t HW,
+                                  float eps, float gconst, float* map, double* sum, float* grad_p_logit,
+                                  int32_t* flags, void* workspace, void* stream);
+
+/* Entropy_2D.forward / Entropy.forward (loss.py:53-84): H = -sum_c p*log(p+1e-16); map/sum nullable;
+ * backward grad_p = up * -(log(p+1e-16) + p/(p+1e-16)). */
+DCT_API int dct_entropy_fwd_f32(const float* p, int C, int64_t B, int64_t HW, float* map, double* sum,
+                                int32_t* flags, void* workspace, void* stream);
+DCT_API int dct_entropy_bwd_f32(const float* p, int C, int64_t B, int64_t HW, const float* gmap,
+                                const float* gscalar, float gconst, float* grad_p, void* stream);
+
+/* KL_div.forward (loss.py:87-107): out = sum_c -p*log(q/p + eps) (forward only; unused by the trainers) */
+DCT_API int dct_kl_div_fwd_f32(const float* p, const float* q, int C, int64_t B, int64_t HW, float eps,
+                       float* map, double* sum, int32_t* flags, void* workspace, void* stream);
+
+/* F.softmax(x, 1) forward (segmentators.py:50) and its backward gx = p*(gp - sum_c p*gp) */
+DCT_API int dct_softmax_fwd_f32(const float* x, int C, int64_t B, int64_t HW, float* p, void* stream);
+DCT_API int dct_softmax_bwd_f32(const float* p, const float* gp, int C, int64_t B, int64_t HW, float* gx, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * VAT / FGSM perturbation arithmetic (image-shaped tensors: B samples of M = Cin*H*W floats).
+ * ------------------------------------------------------------------------------------------ */
+
+/* VATGenerator._l2_normalize (AEGenerator.py:68-76): out_b = scale * (d_b / (||d_b||_2 + 1e-16)).
+ * `out` may alias `d` (the reference normalises in place); scale = 1 for the bare function,
+ * xi / eps for `xi * _l2_normalize(d)` (:103) and `eps * d` (:113-114).
+ * If img != NULL also writes adv = clamp(img + out, 0, 1) (:116-117). */
+DCT_API int dct_l2_normalize_f32(const float* d, float* out, int64_t B, int64_t M, float scale,
+                         const float* img, float* adv, void* workspace, void* stream);
+
+/* FSGMGenerator.adversarial_fgsm (AEGenerator.py:35-51): noise = eps*sign(grad); adv = img + noise */
+DCT_API int dct_fgsm_f32(const float* img, const float* grad, float eps, float* adv, float* noise,
+                 int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Integer metric reductions (bit-exact).
+ * ------------------------------------------------------------------------------------------ */
+
+/* DiceMeter.add counting (generalframework/metrics/dice_meter.py:12-33,50-55; utils/utils.py:154-217):
+ *   pred = argmax_c softmax(x)_c (first index on ties; pinned arithmetic, see DESIGN.md "Dice spec")
+ *   counts[b][c] = (I, G, P) = (#{pred==c & gt==c}, #{gt==c}, #{pred==c})  int64 [B][C][3]
+ * counts is zeroed first unless accumulate != 0.  Out-of-range labels are counted in
+ * flags[DCT_FLAG_LABEL] and excluded from I and G. */
+DCT_API int dct_dice_counts_f32(const float* x, const int64_t* labels, int C, int64_t B, int64_t HW,
+                        int64_t* counts, int accumulate, int32_t* flags, void* stream);
+
+/* meta_dice's final arithmetic (dice_meter.py:17-20): dice = (2*f32(I)+1e-8)/(f32(G+P)+1e-8).
+ * batch_sum == 0: rows = B ('2d', einsum bcwh->bc); != 0: counts summed over b first, 1 row ('3d', bcwh->c).
+ * dice float32 [rows][C]. */
+DCT_API int dct_dice_from_counts_f32(const int64_t* counts, int64_t B, int C, int batch_sum, float* dice, void* stream);
+
+/* IoU.add -> ConfusionMatrix.add (generalframework/metrics/iou.py:43-69, confusionmatrix.py:32-85):
+ *   pred = argmax_c x_c on the RAW scores (first index on ties, NaN maximal as torch.max);
+ *   over pixels with 0 <= gt < C:  conf[gt][pred] += 1.   conf int64 [C][C], ACCUMULATED into. */
+DCT_API int dct_confusion_f32(const float* x, const int64_t* labels, int C, int64_t B, int64_t HW,
+                      int64_t* conf, void* stream);
+/* same for an integer prediction map ([N] int64, iou.py:49-50); predictions outside [0,C) on a
+ * valid-label pixel are counted in flags[DCT_FLAG_PRED] (the reference's bincount-size assert). */
+DCT_API int dct_confusion_labels_i64(const int64_t* pred, const int64_t* labels, int64_t n, int C,
+                             int64_t* conf, int32_t* flags, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCT_B200_H */

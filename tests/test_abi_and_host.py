@@ -1,0 +1,127 @@
+"""CPU: the C-ABI library loads and exports every symbol include/dct_b200.h declares, the ctypes
+table matches the header, host-side logic (alias import, check modes, install rebinding)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "dct_b200.h")).read()
+    return sorted(set(re.findall(r"DCT_API\s+[\w\s\*]+?\b(dct_\w+)\s*\(", txt)))
+
+
+def test_header_symbols_are_exported_and_bound():
+    import dct_b200
+    names = _header_symbols()
+    assert len(names) >= 24
+    h = ctypes.CDLL(dct_b200.library_path())
+    for n in names:
+        assert hasattr(h, n), f"{n} declared in include/dct_b200.h but not exported"
+    assert sorted(dct_b200._lib.EXPORTED_SYMBOLS) == names  # ctypes table covers the whole header, nothing else
+
+
+def test_header_prototype_arity_matches_ctypes_table():
+    import dct_b200
+    txt = open(os.path.join(ROOT, "include", "dct_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    for name, argtypes in dct_b200._lib._SIGNATURES.items():
+        m = re.search(r"\b" + name + r"\s*\((.*?)\)\s*;", txt, flags=re.S)
+        assert m, name
+        params = m.group(1).strip()
+        n = 0 if params in ("", "void") else len(params.split(","))
+        assert n == len(argtypes), f"{name}: header has {n} params, ctypes table {len(argtypes)}"
+
+
+def test_library_basics_without_gpu():
+    import dct_b200
+    h = dct_b200._lib.lib()
+    assert h.dct_abi_version() == 1
+    assert h.dct_workspace_bytes() >= 8 * 8192
+    assert h.dct_error_string(0) == b"ok"
+    assert b"unsupported" in h.dct_error_string(-2)
+    if not torch.cuda.is_available():
+        assert h.dct_device_check(0) == -5
+
+
+def test_alias_import_shares_modules():
+    import dct_b200
+    import dct_b200.loss as L
+    from dct_b200.metrics import DiceMeter
+    assert L.JSD_2D is dct_b200.JSD_2D and DiceMeter is dct_b200.DiceMeter
+    assert dct_b200.get_loss_fn("jsd").__class__ is dct_b200.JSD_2D
+    with pytest.raises(ValueError):
+        dct_b200.get_loss_fn("nope")
+
+
+def test_no_cpu_fallback():
+    import dct_b200
+    p = torch.softmax(torch.randn(1, 3, 4, 4), 1)
+    for call in (lambda: dct_b200.JSD_2D()([p, p]),
+                 lambda: dct_b200.KL_Divergence_2D()(p, p),
+                 lambda: dct_b200.Entropy_2D()(p),
+                 lambda: dct_b200.jsd_consistency_from_logits([p, p]),
+                 lambda: dct_b200.DiceMeter(C=3).add(p, torch.zeros(1, 1, 4, 4, dtype=torch.long)),
+                 lambda: dct_b200.IoU(3).add(p, torch.zeros(1, 1, 4, 4, dtype=torch.long)),
+                 lambda: dct_b200.l2_normalize(torch.randn(2, 1, 4, 4))):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            call()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "deep-co-training-for-semi-supervised-image-segmentation_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "dct_oracle" not in src and "libdct_oracle" not in src, f
+
+
+def test_check_mode_switch():
+    import dct_b200
+    old = dct_b200.set_check_mode("deferred")
+    assert dct_b200.get_check_mode() == "deferred"
+    dct_b200.set_check_mode(old)
+    with pytest.raises(ValueError):
+        dct_b200.set_check_mode("sometimes")
+
+
+def test_meter_host_logic_matches_reference_structures():
+    import dct_b200
+    m = dct_b200.DiceMeter(method="2d", C=4, report_axises=[1, 2, 3])
+    (rm, rs), (ms, ss) = m.value()           # empty log fallback, dice_meter.py:68-71
+    assert ms.shape == (4,) and float(ms.sum()) == 0.0
+    m.diceLog.append(torch.tensor([[1.0, 0.5, 0.25, 0.75], [1.0, 0.0, 0.5, 0.25]]))
+    m._cat = None
+    (rm, rs), (ms, ss) = m.value()
+    assert torch.allclose(ms, torch.tensor([1.0, 0.25, 0.375, 0.5]))
+    assert abs(rm.item() - (0.5 + 0.25) / 2) < 1e-7
+    iou = dct_b200.IoU(3)
+    iou.conf_metric._host[:] = np.array([[5, 1, 0], [2, 3, 0], [0, 0, 0]])
+    v = iou.value()
+    assert v["Overall_Acc"] == 8 / 11 and np.isnan(v["Class_IoU"][2].item())
+    assert v["Validated_Mean_IoU"] == np.mean([5 / 8, 3 / 6])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/generalframework"), reason="reference tree not mounted")
+def test_install_rebinds_reference_call_sites():
+    import ref_shim
+    ref_shim.install()
+    import generalframework.loss as gl
+    import generalframework.trainer.cotraining_totalloss as ct
+    import dct_b200
+    orig = gl.LOSS["jsd"]
+    n = dct_b200.install()
+    try:
+        assert n > 0
+        assert gl.get_loss_fn("jsd").__class__ is dct_b200.JSD_2D          # registry path, loss/__init__.py:12-16
+        assert ct.KL_Divergence_2D is dct_b200.KL_Divergence_2D            # trainer global, cotraining_totalloss.py:13
+        assert ct.DiceMeter is dct_b200.DiceMeter and ct.FSGMGenerator is dct_b200.FSGMGenerator
+    finally:
+        dct_b200.uninstall()
+    assert gl.LOSS["jsd"] is orig and ct.DiceMeter is not dct_b200.DiceMeter
