@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py -- consistency-loss pixels/s (fwd+bwd) of the Deep Co-Training unlabeled-branch hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2]
+
+One "step" = one pass of the hot path over one synthetic unlabeled batch (BASELINE.json configs[1]:
+ACDC co-training, K=3 views, C=4 classes, 256x256, batch 32 per GPU, JSD + VAT adversarial):
+fused K-view JSD forward+backward from logits + the K Dice-count reductions, the three VAT
+L2-normalisations, kl_div_with_logit forward+backward, and the adversarial KL forward+backward.
+The networks between those points are out of scope (stock cuDNN); their outputs are seeded synthetic
+tensors.  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+WORKLOADS = {  # name: (K, C, B per GPU, H, W, Cin, description)
+    "c1": (2, 4, 4, 256, 256, 1, "ACDC 2 views C=4 256x256 B=4 (JSD only)"),
+    "c2": (3, 4, 32, 256, 256, 1, "ACDC 3 views C=4 256x256 B=32/GPU, JSD + VAT adversarial + Dice meters"),
+    "c3": (2, 2, 4, 512, 512, 1, "Spleen 2 views C=2 512x512 B=4/GPU"),
+    "c4": (2, 19, 16, 512, 1024, 3, "Cityscapes 2 views C=19 512x1024 B=16/GPU"),
+}
+METRIC = "consistency-loss pixels/sec (fwd+bwd)"
+UNIT = "pixels/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed regions run."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        top = sorted(sm)[len(sm) // 2:]  # under load = upper half of the samples
+        return {"sm_mhz": statistics.median(top), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (the reference is pure Python and cannot travel to the GPU box)
+# ---------------------------------------------------------------------------------------------------
+def cpu_step_inputs(K, C, B, H, W, cin, seed=1234):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    f = lambda *s: rng.standard_normal(s, dtype=np.float32)  # noqa: E731
+    z = [3 * f(B, C, H, W) for _ in range(K)]
+    gt = rng.integers(0, C, (B, 1, H, W), dtype=np.int64)
+    d, dg = f(B, cin, H, W), f(B, cin, H, W)
+    img = rng.random((B, cin, H, W), dtype=np.float32)
+    yhat, adv = 3 * f(B, C, H, W), 3 * f(B, C, H, W)
+    return z, gt, d, dg, img, yhat, adv
+
+
+def cpu_step(O, inp, K, C, with_vat=True):
+    """The same step as ConsistencyStep.run, on the CPU oracle (all OpenMP threads)."""
+    import numpy as np
+    z, gt, d, dg, img, yhat, adv = inp
+    n = z[0].shape[0] * z[0].shape[2] * z[0].shape[3]
+    mean, _, gz = O.jsd_logits_fwdbwd(z, 1.0, want_map=False, want_grad=True)
+    for k in range(K):
+        O.dice_counts(z[k], gt)
+    if with_vat:
+        d1 = O.l2_normalize(d)
+        d2 = O.l2_normalize(d1) * np.float32(1e-6)
+        gout = np.full((z[0].shape[0],) + z[0].shape[2:], 1.0 / n, np.float32)
+        O.kl_logit(z[0], yhat, gout)
+        r = O.l2_normalize(dg)
+        O.vat_apply(img, r, 10.0)
+        real = O.softmax(z[1])
+        p = O.softmax(adv)
+        O.kl_fwd(p, real)
+        gp, _ = O.kl_bwd(p, real, gout)
+        O.softmax_bwd(p, gp)
+    return mean
+
+
+def time_cpu(K, C, B, H, W, cin, steps, warmup, with_vat=True, budget_s=None):
+    """Times `steps` CPU steps on a bounded sample.  If budget_s is given the sample batch (and, below one
+    image, the image height) is shrunk so that steps+warmup fit the budget; pixels/s is size-independent
+    beyond the caches.  Returns (pixels/s, s/step, threads, sample description)."""
+    import oracle as O
+    O.build()
+    O.set_num_threads(os.cpu_count() or 1)
+    Bs, Hs = min(B, 8), H
+    if budget_s is not None:
+        probe = cpu_step_inputs(K, C, 1, H, W, cin)
+        cpu_step(O, probe, K, C, with_vat)
+        t0 = time.perf_counter()
+        cpu_step(O, probe, K, C, with_vat)
+        t_img = max(time.perf_counter() - t0, 1e-6)
+        per_step = budget_s / max(steps + warmup, 1)
+        Bs = int(max(1, min(B, per_step / t_img)))
+        if per_step < t_img:
+            Hs = int(max(8, (H * per_step / t_img) // 8 * 8))
+    inp = cpu_step_inputs(K, C, Bs, Hs, W, cin)
+    for _ in range(warmup):
+        cpu_step(O, inp, K, C, with_vat)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_step(O, inp, K, C, with_vat)
+    dt = time.perf_counter() - t0
+    sample = (f"same step on {Bs} image(s) of {Hs}x{W} (workload: {B} of {H}x{W}), {steps} steps, "
+              f"C/OpenMP oracle port on all {O.num_threads()} host threads")
+    return Bs * Hs * W * steps / dt, dt / steps, O.num_threads(), sample
+
+
+def run_reference(args, wl):
+    """--impl reference: the path's CPU implementation on the host cores (oracle port; the reference is
+    pure Python/PyTorch and does not exist on the GPU box), bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    K, C, B, H, W, cin, desc = wl
+    val, sec, cores, sample = time_cpu(K, C, B, H, W, cin, args.steps, max(args.warmup, 1),
+                                       with_vat=(args.workload != "c1"), budget_s=150.0)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "K": K, "C": C, "H": H, "W": W, "batch_per_gpu": B},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+
+    import dct_b200
+    from dct_b200.engine import ConsistencyStep, StepBuffers
+
+    K, C, B, H, W, cin, desc = wl
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py --impl ours needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert dct_b200._lib.lib().dct_device_check(local) == 0, "not an sm_100 device"
+    with_vat = args.workload != "c1"
+    n_local = B * H * W
+    step = ConsistencyStep(K, C, B, H, W, cin=cin, jsd_weight=1.0, adv_weight=1.0, n_global=n_local * world,
+                           with_vat=with_vat)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    # R independent buffer sets, rotated every step so that no step finds its inputs in the 126 MB L2
+    per_set = sum(t.numel() * t.element_size() for t in StepBuffers.allocate(K, C, 1, H, W, cin, dev).input_tensors()) * B
+    R = max(2, min(8, int(1.5e9 // max(per_set, 1)) or 2))
+    sets = [StepBuffers.allocate(K, C, B, H, W, cin, dev, gen) for _ in range(R)]
+    dct_b200.set_check_mode("deferred")  # no host sync inside the path; flags are read once at the end
+    graphs = [step.capture(s) for s in sets] if args.graph else None
+    red = torch.zeros(4, dtype=torch.float64, device=dev)
+
+    def one(i):
+        s = sets[i % R]
+        if graphs is not None:
+            graphs[i % R].replay()
+        else:
+            step.run(s)
+        if world > 1:  # the path's only exchange: the loss scalars
+            red.copy_(s.sums)
+            dist.all_reduce(red)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for i in range(args.warmup):
+        one(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        one(i)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = n_local * world * args.steps / (ms_total * 1e-3)
+
+    # ---- roofline of the dominant kernel (fused JSD fwd+bwd): CUDA events around each launch of that
+    # kernel, on the launching stream, over the same rotating buffer sets (inputs never L2-resident)
+    jsd_only = ConsistencyStep(K, C, B, H, W, cin=cin, n_global=n_local * world, with_vat=False, with_dice=False)
+    for i in range(5):
+        jsd_only.run(sets[i % R])
+    reps = min(args.steps, 200)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    torch.cuda.synchronize()
+    for i, (a, b) in enumerate(evs):
+        # keep L2 cold: touch the other sets' step between timed launches
+        step.run(sets[(i + 1) % R])
+        a.record(); jsd_only.run(sets[i % R]); b.record()
+    torch.cuda.synchronize()
+    k_ms = statistics.mean(a.elapsed_time(b) for a, b in evs)
+    alg = jsd_only.algorithmic_bytes()["jsd_fwdbwd"]
+    peak, peak_src = load_peaks()
+    achieved = alg / (k_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "jsd_kernel<K,C,VEC,logits,fwd+bwd> (dct_jsd_fwdbwd_f32)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "frac_of_8TBps_nominal": achieved / 8000.0, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms, "traffic": None,
+                "step_algorithmic_bytes": step.algorithmic_bytes(),
+                "step_achieved_GBps": sum(step.algorithmic_bytes().values()) / (ms_total * 1e-3 / args.steps) / 1e9}
+
+    # ---- e2e: host buffers in pinned memory -> H2D -> the public autograd API -> D2H of losses + Dice rows
+    e2e = run_e2e(args, dct_b200, step, sets[0], dev, world, n_local, K, C, B, H, W, with_vat)
+    dct_b200.raise_if_flagged()
+    clocks = sampler.stop() if rank == 0 else None
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, sec, cores, sample = time_cpu(K, C, B, H, W, cin, steps=10, warmup=1, with_vat=with_vat, budget_s=15.0)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"{args.workload}: {desc}", "K": K, "C": C, "H": H, "W": W, "batch_per_gpu": B,
+                           "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": bool(args.graph),
+                           "l2": f"inputs larger than L2: {R} rotating buffer sets of {per_set / 2**20:.0f} MiB inputs"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": step.launches_per_step * args.steps,
+                "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(args, dct, step, dev_set, dev, world, n_local, K, C, B, H, W, with_vat):
+    """Same step through the PUBLIC API (autograd Functions / meters / generators) with host buffers:
+    every step copies its inputs from pinned host memory (copy stream, double-buffered against the
+    compute of the previous step) and reads the losses and Dice rows back to the host."""
+    import torch
+    import torch.distributed as dist
+    host = [t.cpu().pin_memory() for t in dev_set.input_tensors()]
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    nbuf = 2
+    slots = [[torch.empty_like(t, device=dev) for t in host] for _ in range(nbuf)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready = [torch.cuda.Event() for _ in range(nbuf)]
+    freed = [torch.cuda.Event() for _ in range(nbuf)]
+    out_host = torch.empty(3 + K * B * C, dtype=torch.float32).pin_memory()
+    meters = [dct.DiceMeter(method="2d", C=C) for _ in range(K)]
+    n_glob = n_local * world
+    d2h = out_host.numel() * 4
+
+    def upload(i):
+        j = i % nbuf
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[j])
+            for dst, src in zip(slots[j], host):
+                dst.copy_(src, non_blocking=True)
+            ready[j].record(copy_stream)
+
+    def compute(i):
+        j = i % nbuf
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(ready[j])
+        t = slots[j]
+        logits = [x.requires_grad_() for x in t[:K]]
+        labels, d, d_grad, img, yhat, adv, real = t[K:K + 7]
+        counts = torch.zeros(K, B, C, 3, dtype=torch.int64, device=dev)
+        loss = dct.jsd_consistency_from_logits(logits, weight=1.0, labels=labels, dice_counts=counts, n_global=n_glob)
+        total = loss
+        outs = [loss.detach()]
+        if with_vat:
+            dct.l2_normalize(d)
+            dct.l2_normalize(d, scale=1e-6)
+            yh = yhat.requires_grad_()
+            vkl = dct.kl_div_with_logit(logits[0].detach(), yh).mean()
+            vkl.backward()
+            r_adv, img_adv = dct.l2_normalize(d_grad, scale=10.0, out=torch.empty_like(d_grad), img=img)
+            advl = dct.kl_consistency_from_logits(adv.requires_grad_(), real, weight=1.0, n_global=n_glob)
+            total = total + advl
+            outs += [vkl.detach(), advl.detach()]
+        else:
+            outs += [loss.detach() * 0, loss.detach() * 0]
+        total.backward()
+        rows = []
+        for k in range(K):
+            meters[k].reset()
+            meters[k].add_counts(counts[k])
+            rows.append(meters[k].log.reshape(-1))
+        res = torch.cat([torch.stack(outs)] + rows)
+        if world > 1:
+            dist.all_reduce(res[:3])
+        out_host.copy_(res, non_blocking=True)
+        for x in t:
+            x.requires_grad_(False) if x.is_floating_point() else None
+            x.grad = None
+        freed[j].record(cur)
+
+    steps = max(3, min(args.steps, args.e2e_steps))
+    for j in range(nbuf):
+        freed[j].record(torch.cuda.current_stream(dev))
+    for i in range(3):  # warm-up
+        upload(i); compute(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    upload(0)
+    for i in range(steps):
+        if i + 1 < steps:
+            upload(i + 1)
+        compute(i)
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    dt = float(dt.item())
+    return {"value": n_glob * steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "steps": steps, "ms_per_step": dt / steps * 1e3,
+            "api": "jsd_consistency_from_logits + DiceMeter.add_counts + l2_normalize + kl_div_with_logit + "
+                   "kl_consistency_from_logits (autograd), pinned host inputs, double-buffered H2D",
+            "last_losses": [float(v) for v in out_host[:3]]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--graph", type=int, default=1, help="replay the step as a CUDA graph (1) or launch eagerly (0)")
+    ap.add_argument("--e2e-steps", type=int, default=50)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

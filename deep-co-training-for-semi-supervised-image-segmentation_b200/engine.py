@@ -1,0 +1,150 @@
+"""Allocation-free execution of one unlabeled-branch consistency step.
+
+The autograd drop-ins in :mod:`loss` / :mod:`metrics` allocate their outputs per call, which is
+what a drop-in must do.  A training loop that owns its buffers can instead bind them once and
+replay the whole per-pixel path -- K-view JSD forward+backward with the K Dice counts, the VAT
+power-iteration arithmetic and the adversarial KL -- as a fixed sequence of C-ABI launches on
+one stream, optionally captured in a CUDA graph (the inner loop is launch-bound at ACDC sizes:
+~10 kernels of 5-40 us each).
+
+Where the step sits in the reference iteration (generalframework/trainer/cotraining_totalloss.py):
+  :223-226  unlab_preds -> unlabdiceMeters.add x K -> JSD_2D -> .mean()        [jsd + dice]
+  AEGenerator.py:93-119 (VAT): normalise(d) -> xi*normalise(d) -> net -> kl_div_with_logit.mean().backward()
+                               -> eps*normalise(d.grad) -> clamp(img + r)       [l2 x3, kl_logit]
+  :391-392  KL_Divergence_2D(reduce=True)(softmax(adv_logits), real.detach())   [kl_from_logits]
+The network forward/backward passes between those points stay in PyTorch/cuDNN; here their
+outputs are whatever tensors the caller binds (synthetic ones in bench.py).
+"""
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+
+from . import _lib, _runtime
+
+
+@dataclass
+class StepBuffers:
+    """Device tensors of one consistency step (all float32 NCHW unless noted)."""
+    logits: List[torch.Tensor]          # K x [B,C,H,W]  unlabeled-branch logits of the K views   (in)
+    labels: torch.Tensor                # [B,1,H,W] int64 unlabeled ground truth for the meters    (in)
+    grad_logits: List[torch.Tensor]     # K x [B,C,H,W]  d(w_jsd * mean JSD)/d logits              (out)
+    dice_counts: torch.Tensor           # [K,B,C,3] int64 (I,G,P)                                   (out)
+    d: torch.Tensor                     # [B,Cin,H,W] VAT direction, N(0,1) on entry                (in/out)
+    d_grad: torch.Tensor                # [B,Cin,H,W] dKL/dd coming back from the net               (in)
+    img: torch.Tensor                   # [B,Cin,H,W] unlabeled images in [0,1]                     (in)
+    r_adv: torch.Tensor                 # [B,Cin,H,W]                                               (out)
+    img_adv: torch.Tensor               # [B,Cin,H,W]                                               (out)
+    yhat_logits: torch.Tensor           # [B,C,H,W] net(img + d)                                    (in)
+    grad_yhat: torch.Tensor             # [B,C,H,W] d mean KL_logit / d yhat                        (out)
+    adv_logits: torch.Tensor            # [B,C,H,W] other view on img_adv                           (in)
+    real_probs: torch.Tensor            # [B,C,H,W] detached clean prediction (probabilities)       (in)
+    grad_adv: torch.Tensor              # [B,C,H,W] d(w_adv * KL mean)/d adv_logits                 (out)
+    sums: torch.Tensor                  # [4] float64: sum JSD map, sum VAT KL map, sum adv KL map, -  (out)
+
+    @staticmethod
+    def allocate(K, C, B, H, W, cin, device, generator: Optional[torch.Generator] = None) -> "StepBuffers":
+        """Synthetic, seeded contents: logits 3*randn, labels randint, images rand, d randn."""
+        def rn(*s):
+            return torch.randn(*s, device=device, dtype=torch.float32, generator=generator)
+        logits = [3 * rn(B, C, H, W) for _ in range(K)]
+        e = lambda: torch.empty(B, C, H, W, device=device, dtype=torch.float32)  # noqa: E731
+        ei = lambda: torch.empty(B, cin, H, W, device=device, dtype=torch.float32)  # noqa: E731
+        return StepBuffers(
+            logits=logits,
+            labels=torch.randint(0, C, (B, 1, H, W), device=device, dtype=torch.int64, generator=generator),
+            grad_logits=[e() for _ in range(K)],
+            dice_counts=torch.zeros(K, B, C, 3, dtype=torch.int64, device=device),
+            d=rn(B, cin, H, W), d_grad=rn(B, cin, H, W),
+            img=torch.rand(B, cin, H, W, device=device, dtype=torch.float32, generator=generator),
+            r_adv=ei(), img_adv=ei(),
+            yhat_logits=3 * rn(B, C, H, W), grad_yhat=e(),
+            adv_logits=3 * rn(B, C, H, W), real_probs=torch.softmax(3 * rn(B, C, H, W), 1), grad_adv=e(),
+            sums=torch.zeros(4, dtype=torch.float64, device=device))
+
+    def input_tensors(self):
+        return list(self.logits) + [self.labels, self.d, self.d_grad, self.img, self.yhat_logits, self.adv_logits,
+                                    self.real_probs]
+
+    def result_tensors(self):
+        return [self.sums, self.dice_counts]
+
+
+class ConsistencyStep:
+    """Binds shapes and hyper-parameters; ``run(buffers)`` enqueues the step on the current stream.
+
+    ``jsd_weight`` / ``adv_weight`` are the ramp values the trainer multiplies the two consistency
+    losses with (cotraining_totalloss.py:246); ``n_global`` the pixel count over all ranks.
+    """
+
+    def __init__(self, K, C, B, H, W, cin=1, jsd_weight=1.0, adv_weight=1.0, xi=1e-6, eps=10.0, kl_eps=1e-10,
+                 n_global: Optional[int] = None, with_vat=True, with_dice=True):
+        self.K, self.C, self.B, self.HW, self.M = K, C, B, H * W, cin * H * W
+        self.n = B * H * W if n_global is None else int(n_global)
+        self.jsd_weight, self.adv_weight, self.xi, self.eps, self.kl_eps = jsd_weight, adv_weight, xi, eps, kl_eps
+        self.with_vat, self.with_dice = with_vat, with_dice
+        self._h = _lib.lib()
+        # kernels launched per run(): the fused JSD (+K dice launches until that fusion lands in one kernel)
+        self.launches_per_step = 1 + (K if with_dice else 0) + (5 if with_vat else 0)
+
+    # bytes that MUST move per step (algorithmic, fp32): see DESIGN.md "Algorithmic bytes"
+    def algorithmic_bytes(self):
+        K, C, n = self.K, self.C, self.B * self.HW
+        cin = self.M // self.HW
+        b = {"jsd_fwdbwd": n * (2 * K * C * 4), "dice": (n * K * (C * 4 + 8)) if self.with_dice else 0}
+        if self.with_vat:
+            b.update({"l2_normalize_x3": n * cin * 4 * (2 + 2 + 4), "kl_logit_fwdbwd": n * 3 * C * 4,
+                      "kl_from_logits_fwdbwd": n * 3 * C * 4})
+        return b
+
+    def run(self, bufs: StepBuffers) -> None:
+        h, K, C, B, HW = self._h, self.K, self.C, self.B, self.HW
+        dev = bufs.logits[0].device
+        st = _runtime.state(dev)
+        ws, s = st.workspace.data_ptr(), _runtime.stream_ptr(dev)
+        fl = _runtime.flags_ptr(st)
+        sums = bufs.sums.data_ptr()
+        if self.with_dice:
+            bufs.dice_counts.zero_()
+        _lib.check(h.dct_jsd_fwdbwd_f32(_lib.ptr_array(bufs.logits), K, C, B, HW, _lib.IN_LOGITS,
+                                        self.jsd_weight / self.n, None, sums, _lib.ptr_array(bufs.grad_logits),
+                                        bufs.labels.data_ptr() if self.with_dice else None,
+                                        bufs.dice_counts.data_ptr() if self.with_dice else None, fl, ws, s),
+                   "dct_jsd_fwdbwd_f32")
+        if not self.with_vat:
+            return
+        d = bufs.d.data_ptr()
+        # d <- normalise(N(0,1));  d <- xi * normalise(d)                       (AEGenerator.py:97-98,103)
+        _lib.check(h.dct_l2_normalize_f32(d, d, B, self.M, 1.0, None, None, ws, s), "dct_l2_normalize_f32")
+        _lib.check(h.dct_l2_normalize_f32(d, d, B, self.M, self.xi, None, None, ws, s), "dct_l2_normalize_f32")
+        # delta_kl = kl_div_with_logit(pred.detach(), y_hat); delta_kl.mean().backward()       (:107-108)
+        _lib.check(h.dct_kl_logit_f32(bufs.logits[0].data_ptr(), bufs.yhat_logits.data_ptr(), C, B, HW, None, sums + 8,
+                                      1, None, None, 1.0 / self.n, bufs.grad_yhat.data_ptr(), None, ws, s),
+                   "dct_kl_logit_f32")
+        # r_adv = eps * normalise(d.grad); img_adv = clamp(img + r_adv, 0, 1)                  (:113-117)
+        _lib.check(h.dct_l2_normalize_f32(bufs.d_grad.data_ptr(), bufs.r_adv.data_ptr(), B, self.M, self.eps,
+                                          bufs.img.data_ptr(), bufs.img_adv.data_ptr(), ws, s), "dct_l2_normalize_f32")
+        # adv loss: KL_Divergence_2D(reduce=True)(softmax(adv_logits), real.detach()) + backward (cotraining :391-392)
+        _lib.check(h.dct_kl_from_logits_fwdbwd_f32(bufs.adv_logits.data_ptr(), bufs.real_probs.data_ptr(), C, B, HW,
+                                                   self.kl_eps, self.adv_weight / self.n, None, sums + 16,
+                                                   bufs.grad_adv.data_ptr(), fl, ws, s), "dct_kl_from_logits_fwdbwd_f32")
+
+    def capture(self, bufs: StepBuffers) -> "torch.cuda.CUDAGraph":
+        """Capture ``run(bufs)`` into a CUDA graph (replay with ``graph.replay()``)."""
+        dev = bufs.logits[0].device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            self.run(bufs)  # warm-up on the side stream (allocates the per-stream workspace)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            self.run(bufs)
+        return g
+
+    def losses(self, bufs: StepBuffers):
+        """(jsd_loss, vat_kl_mean, adv_loss) as 0-d float32 tensors on the device (no sync)."""
+        s = bufs.sums
+        return ((s[0] * (self.jsd_weight / self.n)).float(), (s[1] / self.n).float(),
+                (s[2] * (self.adv_weight / self.n)).float())
