@@ -52,15 +52,15 @@ inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_
 template <int VEC>
 struct FVec;
 template <>
-struct FVec<1> {
+struct alignas(4) FVec<1> {
     float v[1];
 };
 template <>
-struct FVec<2> {
+struct alignas(8) FVec<2> {
     float v[2];
 };
 template <>
-struct FVec<4> {
+struct alignas(16) FVec<4> {
     float v[4];
 };
 
@@ -214,8 +214,9 @@ __device__ __forceinline__ int spec_softmax_argmax(const float (&x)[C]) {
     bool near = false;
 #pragma unroll
     for (int c = 0; c < C; ++c) near |= (c != am) & !(__fsub_rn(x[c], m) < -1.52587890625e-05f);
-    // (c != am) is a runtime test, so x[am] itself never trips it; NaN anywhere makes `near` true
-    if (!near && (m == m)) return am;
+    // (c != am) is a runtime test, so x[am] itself never trips it; NaN anywhere makes `near` true.
+    // An infinite maximum gives d = inf - inf = NaN in the pinned arithmetic -> full path (returns 0).
+    if (!near && (fabsf(m) <= 3.4028234664e38f)) return am;
     float S = 0.0f;
     bool any_nan = false;
 #pragma unroll
@@ -300,6 +301,27 @@ __device__ __forceinline__ float fexp(float x) { return __expf(x); }
 __device__ __forceinline__ float flog(float x) { return __logf(x); }
 __device__ __forceinline__ float fdiv(float a, float b) { return __fdividef(a, b); }
 #endif
+
+// base-2 MUFU primitives with flush-to-zero (one SASS instruction each, no denormal fix-up code).
+// Inputs on this path are never denormal where it matters: ex2 arguments are <= 0 (results below
+// 2^-126 flush to 0 = a probability of 0), lg2 arguments are >= 1e-16.
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_ftz(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+constexpr float kLog2e = 1.44269504088896341f;
+constexpr float kLn2 = 0.69314718055994531f;
 
 // the reference's simplex predicate for one pixel: |sum - 1| <= 1e-8 + 1e-5 (utils/utils.py:142-151)
 __device__ __forceinline__ bool simplex_ok(float s) { return fabsf(s - 1.0f) <= (1e-8f + 1e-5f); }

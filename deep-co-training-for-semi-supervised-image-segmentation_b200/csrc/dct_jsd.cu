@@ -57,7 +57,7 @@ using namespace dct;
 
 extern "C" int dct_jsd_fwd_f32(const float* const* views, int K, int C, int64_t B, int64_t HW, int in_kind,
                                float* map, double* sum, int32_t* flags, void* workspace, void* stream) {
-    JsdCall c{views, nullptr, K, C, B, HW, in_kind, kFwd, map, sum, Upstream{nullptr, nullptr, 0.0f}, flags,
+    JsdCall c{nullptr, nullptr, nullptr, views, nullptr, K, C, B, HW, in_kind, kFwd, map, sum, Upstream{nullptr, nullptr, 0.0f}, flags,
               static_cast<Workspace*>(workspace), static_cast<cudaStream_t>(stream)};
     return jsd_dispatch(c);
 }
@@ -65,7 +65,7 @@ extern "C" int dct_jsd_fwd_f32(const float* const* views, int K, int C, int64_t 
 extern "C" int dct_jsd_bwd_f32(const float* const* views, int K, int C, int64_t B, int64_t HW, int in_kind,
                                const float* gmap, const float* gscalar, float gconst, float* const* grad_views,
                                void* stream) {
-    JsdCall c{views, grad_views, K, C, B, HW, in_kind, kBwd, nullptr, nullptr, Upstream{gmap, gscalar, gconst},
+    JsdCall c{nullptr, nullptr, nullptr, views, grad_views, K, C, B, HW, in_kind, kBwd, nullptr, nullptr, Upstream{gmap, gscalar, gconst},
               nullptr, nullptr, static_cast<cudaStream_t>(stream)};
     return jsd_dispatch(c);
 }
@@ -74,15 +74,17 @@ extern "C" int dct_jsd_fwdbwd_f32(const float* const* views, int K, int C, int64
                                   float gconst, float* map, double* sum, float* const* grad_views,
                                   const int64_t* labels, int64_t* counts, int32_t* flags, void* workspace,
                                   void* stream) {
-    JsdCall c{views, grad_views, K, C, B, HW, in_kind, kFwdBwd, map, sum, Upstream{nullptr, nullptr, gconst},
-              flags, static_cast<Workspace*>(workspace), static_cast<cudaStream_t>(stream)};
+    if (labels != nullptr && counts == nullptr) return DCT_ERR_BAD_ARG;
+    bool dice_done = false;
+    JsdCall c{labels, counts, &dice_done, views, grad_views, K, C, B, HW, in_kind, kFwdBwd, map, sum,
+              Upstream{nullptr, nullptr, gconst}, flags, static_cast<Workspace*>(workspace),
+              static_cast<cudaStream_t>(stream)};
     int rc = jsd_dispatch(c);
     if (rc != DCT_OK) return rc;
-    if (labels != nullptr) {
-        if (counts == nullptr) return DCT_ERR_BAD_ARG;
+    if (labels != nullptr && !dice_done) {
         // Dice counting of the K views against the same labels (unlabdiceMeters,
-        // generalframework/trainer/cotraining_totalloss.py:224); the views were just streamed
-        // through L2 by the loss kernel.
+        // generalframework/trainer/cotraining_totalloss.py:224).  C <= 4 with aligned rows is fused
+        // into the loss kernel itself (JsdOp<.., DICEF>); other shapes count in K extra launches.
         for (int k = 0; k < K; ++k) {
             rc = dct_dice_counts_f32(views[k], labels, C, B, HW, counts + (int64_t)k * B * C * 3, 1, flags, stream);
             if (rc != DCT_OK) return rc;

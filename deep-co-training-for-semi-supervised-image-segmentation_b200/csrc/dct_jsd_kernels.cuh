@@ -11,6 +11,7 @@
 // the kernel is an HBM-bound map/reduce ("JSD kernel").
 #pragma once
 #include "dct_common.cuh"
+#include "dct_tile.cuh"
 
 namespace dct {
 
@@ -39,41 +40,46 @@ struct JsdArgsRt {          // runtime-(K,C) fallback
     Workspace* ws;
 };
 
+// s / K.  Powers of two are exact; otherwise one multiply by the rounded reciprocal (<= 1 ulp from the
+// reference's true division, far inside the 1e-5 budget, and ~10 instructions cheaper per call).
 template <int K>
 __device__ __forceinline__ float div_by_K(float s) {
-    if constexpr ((K & (K - 1)) == 0) return s * (1.0f / (float)K);  // exact for powers of two
-    else return s / (float)K;                                        // the reference divides
+    return s * (1.0f / (float)K);
 }
 
-// One pixel.  In: x[k][c] (probs or logits).  Out: returns the JSD value; if GRAD, x[k][c] is
+// One pixel.  In: x[k][c] (probs or logits).  Out: returns the JSD value (nats); if GRAD, x[k][c] is
 // overwritten with gK * d JSD / d x[k][c]  (gK = upstream / K).  `bad` is set when a view fails
 // the reference's simplex predicate (probs mode only).
+//
+// All logarithms are taken in base 2 (one MUFU.LG2 / MUFU.EX2 each, flush-to-zero) and the
+// ln 2 factor is applied once per pixel: H = -ln2 * sum p*lg2(p).
 template <int K, int C, bool LOGITS, bool GRAD>
 __device__ __forceinline__ float jsd_pixel(float (&x)[K][C], float gK, bool& bad) {
     float p[K][C];
-    float hsum = 0.0f;  // sum_k sum_c p*log p   (= -sum_k H_k)
+    float hsum = 0.0f;  // sum_k sum_c p*lg2 p   (= -sum_k H_k / ln2)
     if constexpr (LOGITS) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             float mx = x[k][0];
 #pragma unroll
             for (int c = 1; c < C; ++c) mx = fmaxf(mx, x[k][c]);
+            const float mxl = mx * kLog2e;
             float Z = 0.0f;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                float d = x[k][c] - mx;
-                float e = fexp(d);
-                x[k][c] = d;
+                float t = fmaf(x[k][c], kLog2e, -mxl);  // (x - max) * log2(e), one rounding
+                float e = ex2_ftz(t);
+                x[k][c] = t;
                 p[k][c] = e;
                 Z += e;
             }
-            float inv = fdiv(1.0f, Z);
-            float lZ = flog(Z);
+            const float inv = rcp_ftz(Z);
+            const float lZ = lg2_ftz(Z);
             float hk = 0.0f;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
                 float pv = p[k][c] * inv;
-                float lp = x[k][c] - lZ;  // log-softmax: differs from log(p+1e-16) by < 1e-16/p, and
+                float lp = x[k][c] - lZ;  // lg2 softmax: differs from lg2(p+1e-16) by < 1e-16/p, and
                 p[k][c] = pv;             // only ever multiplied by p  ->  absolute error < 1e-16
                 x[k][c] = lp;
                 hk = fmaf(pv, lp, hk);
@@ -88,7 +94,7 @@ __device__ __forceinline__ float jsd_pixel(float (&x)[K][C], float gK, bool& bad
             for (int c = 0; c < C; ++c) {
                 float pv = x[k][c];
                 s += pv;
-                float lp = flog(pv + kEntEps);
+                float lp = lg2_ftz(pv + kEntEps);
                 p[k][c] = pv;
                 x[k][c] = lp;
                 hk = fmaf(pv, lp, hk);
@@ -97,24 +103,25 @@ __device__ __forceinline__ float jsd_pixel(float (&x)[K][C], float gK, bool& bad
             hsum += hk;
         }
     }
-    float hm = 0.0f;  // sum_c m*log(m+eps)  (= -H(m))
-    float am[C];      // per class: log(m+eps) [+ m/(m+eps) in probs mode]
+    float hm = 0.0f;  // sum_c m*lg2(m+eps)  (= -H(m)/ln2)
+    float am[C];      // per class: lg2(m+eps) [probs mode with GRAD: ln2*lg2(m+eps) + m/(m+eps)]
 #pragma unroll
     for (int c = 0; c < C; ++c) {
         float s = p[0][c];
 #pragma unroll
         for (int k = 1; k < K; ++k) s += p[k][c];
         float m = div_by_K<K>(s);
-        float lm = flog(m + kEntEps);
+        float lm = lg2_ftz(m + kEntEps);
         hm = fmaf(m, lm, hm);
-        if constexpr (GRAD && !LOGITS) lm += fdiv(m, m + kEntEps);
+        if constexpr (GRAD && !LOGITS) lm = fmaf(lm, kLn2, m * rcp_ftz(m + kEntEps));
         am[c] = lm;
     }
-    const float jsd = div_by_K<K>(hsum) - hm;
+    const float jsd = kLn2 * (div_by_K<K>(hsum) - hm);
     if constexpr (GRAD) {
         if constexpr (LOGITS) {
-            // d/dz_kc = gK * p_kc * ((lp_kc - lm_c) - KL(p_k || m));  the +1 terms of
-            // d(p log p)/dp cancel inside the softmax backward.
+            // d/dz_kc = gK * p_kc * ((ln p_kc - ln m_c) - KL(p_k || m));  the +1 terms of
+            // d(p log p)/dp cancel inside the softmax backward.  ln = ln2 * lg2 folded into gK.
+            const float g2 = gK * kLn2;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 float kl = 0.0f;
@@ -125,29 +132,42 @@ __device__ __forceinline__ float jsd_pixel(float (&x)[K][C], float gK, bool& bad
                     kl = fmaf(p[k][c], t, kl);
                 }
 #pragma unroll
-                for (int c = 0; c < C; ++c) x[k][c] = gK * p[k][c] * (x[k][c] - kl);
+                for (int c = 0; c < C; ++c) x[k][c] = (g2 * p[k][c]) * (x[k][c] - kl);
             }
         } else {
-            // d/dp_kc = gK * [(log(p+e) + p/(p+e)) - (log(m+e) + m/(m+e))]
+            // d/dp_kc = gK * [(ln(p+e) + p/(p+e)) - (ln(m+e) + m/(m+e))]
 #pragma unroll
             for (int k = 0; k < K; ++k)
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     float pv = p[k][c];
-                    x[k][c] = gK * ((x[k][c] + fdiv(pv, pv + kEntEps)) - am[c]);
+                    float a = fmaf(x[k][c], kLn2, pv * rcp_ftz(pv + kEntEps));
+                    x[k][c] = gK * (a - am[c]);
                 }
         }
     }
     return jsd;
 }
 
+// JSD as a tile-pipeline Op (dct_tile.cuh): NIN = K views; gradients overwrite the views' rows.
+template <int K, bool LOGITS, int MODE, bool DICEF>
+struct JsdOp {
+    static constexpr int NIN = K, NOUT = (MODE != kFwd) ? K : 0;
+    static constexpr bool HAS_MAP = (MODE != kBwd), USES_UP = (MODE != kFwd), CHECKS_SIMPLEX = !LOGITS;
+    static constexpr int NDICE = DICEF ? K : 0;
+    template <int CM>
+    static __device__ __forceinline__ float apply(float (&x)[K][CM], int, float g, float, bool& bad) {
+        return jsd_pixel<K, CM, LOGITS, MODE != kFwd>(x, div_by_K<K>(g), bad);
+    }
+};
+
 template <int K, int C>
 constexpr int jsd_vec() {
     return K * C <= 16 ? 4 : (K * C <= 40 ? 2 : 1);
 }
 
-template <int K, int C, int VEC, bool LOGITS, int MODE>
-__global__ void __launch_bounds__(256) jsd_kernel(const JsdArgs<K> a) {
+template <int K, int C, int VEC, bool LOGITS, int MODE, int MINB = 1>
+__global__ void __launch_bounds__(256, MINB) jsd_kernel(const JsdArgs<K> a) {
     const int64_t HW = a.HW;
     const int64_t gpi = HW / VEC;  // pixel groups per image (host guarantees HW % VEC == 0)
     const int b = blockIdx.y;
@@ -325,6 +345,9 @@ __global__ void __launch_bounds__(256) jsd_kernel_rt(const JsdArgsRt a) {
 // host-side launch of one (K,C) instantiation; defined per K in dct_jsd_k*.cu
 // ---------------------------------------------------------------------------------------------
 struct JsdCall {
+    const int64_t* labels;      // fused Dice (kFwdBwd / kFwd with logits): nullable
+    int64_t* counts;            // [K][B][C][3]
+    bool* dice_done;            // set to true when the launch also produced the Dice counts
     const float* const* views;
     float* const* grads;
     int K, C;
@@ -344,7 +367,47 @@ int jsd_launch_k3(const JsdCall& c);
 int jsd_launch_k4(const JsdCall& c);
 
 template <int K, int C>
+int jsd_launch_tile(const JsdCall& c) {
+    TileArgs a{};
+    for (int k = 0; k < K; ++k) {
+        a.in[k] = c.views[k];
+        a.out[k] = c.grads ? c.grads[k] : nullptr;
+    }
+    a.HW = c.HW; a.map = c.map; a.sum = c.sum; a.up = c.up; a.eps = 0.0f; a.flags = c.flags; a.ws = c.ws;
+    a.labels = nullptr; a.counts = nullptr; a.count_view_stride = c.B * C * 3;
+    const bool lg = c.in_kind == DCT_IN_LOGITS;
+    if (c.mode == kFwdBwd) {
+        if constexpr (C <= 4) {
+            if (lg && c.labels != nullptr && aligned(c.labels, 16)) {
+                a.labels = c.labels;
+                a.counts = reinterpret_cast<unsigned long long*>(c.counts);
+                if (!tile_eligible<JsdOp<K, true, kFwdBwd, true>>(a, c.B)) return DCT_ERR_UNSUPPORTED;
+                int rc = tile_launch_ct<JsdOp<K, true, kFwdBwd, true>, C>(a, c.B, c.stream);
+                if (rc == DCT_OK && c.dice_done) *c.dice_done = true;
+                return rc;
+            }
+        }
+        if (!tile_eligible<JsdOp<K, true, kFwdBwd, false>>(a, c.B)) return DCT_ERR_UNSUPPORTED;
+        return lg ? tile_launch_ct<JsdOp<K, true, kFwdBwd, false>, C>(a, c.B, c.stream)
+                  : tile_launch_ct<JsdOp<K, false, kFwdBwd, false>, C>(a, c.B, c.stream);
+    }
+    if (c.mode == kBwd) {
+        if (!tile_eligible<JsdOp<K, true, kBwd, false>>(a, c.B)) return DCT_ERR_UNSUPPORTED;
+        return lg ? tile_launch_ct<JsdOp<K, true, kBwd, false>, C>(a, c.B, c.stream)
+                  : tile_launch_ct<JsdOp<K, false, kBwd, false>, C>(a, c.B, c.stream);
+    }
+    if (!tile_eligible<JsdOp<K, true, kFwd, false>>(a, c.B)) return DCT_ERR_UNSUPPORTED;
+    return lg ? tile_launch_ct<JsdOp<K, true, kFwd, false>, C>(a, c.B, c.stream)
+              : tile_launch_ct<JsdOp<K, false, kFwd, false>, C>(a, c.B, c.stream);
+}
+
+template <int K, int C>
 int jsd_launch_kc(const JsdCall& c) {
+    if constexpr (K * C <= 16) {
+        // ACDC / spleen-sized class counts: TMA tile pipeline (falls through when rows are not 16-byte aligned)
+        int rc = jsd_launch_tile<K, C>(c);
+        if (rc != DCT_ERR_UNSUPPORTED) return rc;
+    }
     constexpr int VEC = jsd_vec<K, C>();
     JsdArgs<K> a;
     bool al = (c.HW % VEC) == 0 && (c.map == nullptr || aligned(c.map, 4 * VEC)) &&
@@ -359,7 +422,7 @@ int jsd_launch_kc(const JsdCall& c) {
     auto go = [&](auto vec_tag) -> int {
         constexpr int V = decltype(vec_tag)::value;
         dim3 grid = image_grid(c.B, c.HW / V, threads);
-#define DCT_JSD_GO(LG, MD) jsd_kernel<K, C, V, LG, MD><<<grid, threads, 0, c.stream>>>(a)
+#define DCT_JSD_GO(LG, MD) jsd_kernel<K, C, V, LG, MD, (V == 4 ? 3 : 2)><<<grid, threads, 0, c.stream>>>(a)
         if (c.in_kind == DCT_IN_LOGITS) {
             if (c.mode == kFwd) DCT_JSD_GO(true, kFwd);
             else if (c.mode == kBwd) DCT_JSD_GO(true, kBwd);

@@ -28,6 +28,7 @@ __device__ __forceinline__ void softmax_stats(float (&x)[CM], float (&e)[CM], in
 // KL_Divergence_2D.forward -- generalframework/loss/loss.py:117-134
 struct KlProbFwd {
     static constexpr int NIN = 2, NOUT = 0;
+    static constexpr int NDICE = 0;
     static constexpr bool HAS_MAP = true, USES_UP = false, CHECKS_SIMPLEX = true;
     template <int CM>
     static __device__ __forceinline__ float apply(float (&x)[2][CM], int C, float, float eps, bool& bad) {
@@ -49,6 +50,7 @@ struct KlProbFwd {
 template <bool WANT_Y>
 struct KlProbBwd {
     static constexpr int NIN = 2, NOUT = 2;
+    static constexpr int NDICE = 0;
     static constexpr bool HAS_MAP = false, USES_UP = true, CHECKS_SIMPLEX = false;
     template <int CM>
     static __device__ __forceinline__ float apply(float (&x)[2][CM], int C, float g, float eps, bool&) {
@@ -69,6 +71,7 @@ struct KlProbBwd {
 template <bool GRAD>
 struct KlLogit {
     static constexpr int NIN = 2, NOUT = GRAD ? 2 : 0;
+    static constexpr int NDICE = 0;
     static constexpr bool HAS_MAP = true, USES_UP = GRAD, CHECKS_SIMPLEX = false;
     template <int CM>
     static __device__ __forceinline__ float apply(float (&x)[2][CM], int C, float g, float, bool&) {
@@ -103,6 +106,7 @@ struct KlLogit {
 // (generalframework/trainer/cotraining_totalloss.py:391-392).  in[0] = p_logit, in[1] = y_prob; out[0] = grad p_logit.
 struct KlFromLogits {
     static constexpr int NIN = 2, NOUT = 1;
+    static constexpr int NDICE = 0;
     static constexpr bool HAS_MAP = true, USES_UP = true, CHECKS_SIMPLEX = true;
     template <int CM>
     static __device__ __forceinline__ float apply(float (&x)[2][CM], int C, float g, float eps, bool& bad) {
@@ -134,6 +138,7 @@ struct KlFromLogits {
 // KL_div.forward -- loss.py:99-107: sum_c -p*log(q/p + eps)
 struct KlDivFwd {
     static constexpr int NIN = 2, NOUT = 0;
+    static constexpr int NDICE = 0;
     static constexpr bool HAS_MAP = true, USES_UP = false, CHECKS_SIMPLEX = true;
     template <int CM>
     static __device__ __forceinline__ float apply(float (&x)[2][CM], int C, float, float eps, bool& bad) {
@@ -153,6 +158,7 @@ struct KlDivFwd {
 // Entropy_2D / Entropy forward -- loss.py:53-84
 struct EntropyFwd {
     static constexpr int NIN = 1, NOUT = 0;
+    static constexpr int NDICE = 0;
     static constexpr bool HAS_MAP = true, USES_UP = false, CHECKS_SIMPLEX = true;
     template <int CM>
     static __device__ __forceinline__ float apply(float (&x)[1][CM], int C, float, float, bool& bad) {
@@ -170,6 +176,7 @@ struct EntropyFwd {
 };
 struct EntropyBwd {
     static constexpr int NIN = 1, NOUT = 1;
+    static constexpr int NDICE = 0;
     static constexpr bool HAS_MAP = false, USES_UP = true, CHECKS_SIMPLEX = false;
     template <int CM>
     static __device__ __forceinline__ float apply(float (&x)[1][CM], int C, float g, float, bool&) {
@@ -186,6 +193,7 @@ struct EntropyBwd {
 // F.softmax(x, 1) as a standalone product op uses the accurate libdevice expf and IEEE division
 struct SoftmaxFwd {
     static constexpr int NIN = 1, NOUT = 1;
+    static constexpr int NDICE = 0;
     static constexpr bool HAS_MAP = false, USES_UP = false, CHECKS_SIMPLEX = false;
     template <int CM>
     static __device__ __forceinline__ float apply(float (&x)[1][CM], int C, float, float, bool&) {
@@ -205,6 +213,7 @@ struct SoftmaxFwd {
 };
 struct SoftmaxBwd {  // in[0] = p, in[1] = gp ; out[0] = gx
     static constexpr int NIN = 2, NOUT = 1;
+    static constexpr int NDICE = 0;
     static constexpr bool HAS_MAP = false, USES_UP = false, CHECKS_SIMPLEX = false;
     template <int CM>
     static __device__ __forceinline__ float apply(float (&x)[2][CM], int C, float, float, bool&) {

@@ -12,6 +12,7 @@
 // integers: per-thread packed counters (C <= 4) or a per-CTA shared-memory histogram (C > 4) are
 // merged into global int64 counters with atomics.
 #include "dct_common.cuh"
+#include "dct_tile.cuh"
 
 namespace dct {
 
@@ -237,8 +238,22 @@ __global__ void dice_from_counts_kernel(const int64_t* counts, int64_t B, int C,
     }
 }
 
+// Dice counting as a tile-pipeline Op (C <= 4): no outputs, one counted tensor
+struct DiceOp {
+    static constexpr int NIN = 1, NOUT = 0, NDICE = 1;
+    static constexpr bool HAS_MAP = false, USES_UP = false, CHECKS_SIMPLEX = false;
+    template <int CM>
+    static __device__ __forceinline__ float apply(float (&)[1][CM], int, float, float, bool&) { return 0.0f; }
+};
+
 template <int CT>
 static int dice_launch_ct(const MetricArgs& a, int64_t B, cudaStream_t s) {
+    if constexpr (CT > 0 && CT <= 4) {
+        TileArgs t{};
+        t.in[0] = a.x; t.HW = a.HW; t.flags = a.flags; t.labels = a.labels;
+        t.counts = reinterpret_cast<unsigned long long*>(a.out); t.count_view_stride = B * CT * 3;
+        if (tile_eligible<DiceOp>(t, B)) return tile_launch_ct<DiceOp, CT>(t, B, s);
+    }
     constexpr int VEC = metric_vec<CT>();
     if ((a.HW % VEC) != 0 || !aligned(a.x, 4 * VEC) || !aligned(a.labels, VEC >= 2 ? 16 : 8)) return DCT_ERR_UNSUPPORTED;
     const int C = CT ? CT : a.C;

@@ -6,6 +6,7 @@
 // per-thread arrays in local memory) so every C <= DCT_MAX_CLASSES is served.
 #pragma once
 #include "dct_common.cuh"
+#include "dct_tile.cuh"
 
 namespace dct {
 
@@ -100,6 +101,13 @@ __global__ void __launch_bounds__(256) pix_kernel(const PixArgs a) {
 
 template <class Op, int CT>
 int pix_launch_ct(const PixArgs& a, int64_t B, cudaStream_t stream) {
+    if constexpr (CT > 0 && Op::NIN * CT <= 16) {
+        TileArgs t{};
+        for (int n = 0; n < Op::NIN; ++n) t.in[n] = a.in[n];
+        for (int n = 0; n < Op::NOUT; ++n) t.out[n] = a.out[n];
+        t.HW = a.HW; t.map = a.map; t.sum = a.sum; t.up = a.up; t.eps = a.eps; t.flags = a.flags; t.ws = a.ws;
+        if (tile_eligible<Op>(t, B)) return tile_launch_ct<Op, CT>(t, B, stream);
+    }
     constexpr int VEC = pix_vec<Op::NIN, CT>();
     bool al = (a.HW % VEC) == 0 && (a.map == nullptr || aligned(a.map, 4 * VEC)) &&
               (a.up.gmap == nullptr || aligned(a.up.gmap, 4 * VEC));

@@ -243,7 +243,9 @@ def test_dice_meter_statistics_vs_reference(C, dct, dev):
     for j in range(3):
         m.add(T(GOLDEN[f"{key}/x{j}"], dev), T(GOLDEN[f"{key}/gt{j}"], dev))
     (rm, rs), (ms, ss) = m.value()
-    assert np.array_equal(N(ms), GOLDEN[key + "/ref_means"])
+    # the rows are bit-exact (test_dice_vs_reference_bit_exact); their mean/std are float reductions
+    # whose order differs between ATen CPU (the fixture) and ATen CUDA
+    assert_close(N(ms), GOLDEN[key + "/ref_means"], rtol=1e-6)
     assert_close(N(ss), GOLDEN[key + "/ref_stds"], rtol=1e-6)
     assert_close(np.array([rm.item(), rs.item()]), GOLDEN[key + "/ref_report"], rtol=1e-6)
     assert set(m.summary()) == {"mDSC", "mVars"} and set(m.detailed_summary()) == {f"DSC{i}" for i in range(C)}
