@@ -39,7 +39,7 @@ _SIGNATURES = {
     "dct_entropy_bwd_f32": [_p, _i, _i64, _i64, _p, _p, _f, _p, _p],
     "dct_softmax_fwd_f32": [_p, _i, _i64, _i64, _p, _p],
     "dct_softmax_bwd_f32": [_p, _p, _i, _i64, _i64, _p, _p],
-    "dct_l2_normalize_f32": [_p, _p, _i64, _i64, _f, _p, _p, _p, _p],
+    "dct_l2_normalize_f32": [_p, _p, _i64, _i64, _i, _f, _p, _p, _p, _p],
     "dct_fgsm_f32": [_p, _p, _f, _p, _p, _i64, _p],
     "dct_dice_counts_f32": [_p, _p, _i, _i64, _i64, _p, _i, _p, _p],
     "dct_dice_from_counts_f32": [_p, _i64, _i, _i, _p, _p],

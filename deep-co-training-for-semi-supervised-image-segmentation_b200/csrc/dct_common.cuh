@@ -200,23 +200,13 @@ __device__ __forceinline__ float spec_expf(float d) {
     return __fmul_rn(y, scale);
 }
 
-// pred = argmax_c softmax_spec(x)_c.  Fast path: if every other class is more than 2^-16 below the
-// maximum its spec probability is strictly smaller (spec_expf(d) <= 1 - 2^-22 for d < -2^-16, and
-// IEEE division by the common sum keeps the order strict), so the raw arg-max IS the answer; only
-// near-ties / NaNs run the full pinned arithmetic.
+// The full pinned arithmetic (slow path of the arg-max below; the test-side CPU checker restates it operation for operation).
 template <int C>
-__device__ __forceinline__ int spec_softmax_argmax(const float (&x)[C]) {
+__device__ __forceinline__ int spec_softmax_argmax_full(const float (&x)[C]) {
     float m = x[0];
-    int am = 0;
 #pragma unroll
     for (int c = 1; c < C; ++c)
-        if (x[c] > m) { m = x[c]; am = c; }
-    bool near = false;
-#pragma unroll
-    for (int c = 0; c < C; ++c) near |= (c != am) & !(__fsub_rn(x[c], m) < -1.52587890625e-05f);
-    // (c != am) is a runtime test, so x[am] itself never trips it; NaN anywhere makes `near` true.
-    // An infinite maximum gives d = inf - inf = NaN in the pinned arithmetic -> full path (returns 0).
-    if (!near && (fabsf(m) <= 3.4028234664e38f)) return am;
+        if (x[c] > m) m = x[c];
     float S = 0.0f;
     bool any_nan = false;
 #pragma unroll
@@ -235,6 +225,71 @@ __device__ __forceinline__ int spec_softmax_argmax(const float (&x)[C]) {
         if (q > qb) { qb = q; best = c; }
     }
     return best;
+}
+
+static __device__ __noinline__ int spec_full_upto4(float x0, float x1, float x2, float x3, int C) {
+    float x[4] = {x0, x1, x2, x3};
+    float m = x[0];
+    for (int c = 1; c < C; ++c)
+        if (x[c] > m) m = x[c];
+    float S = 0.0f;
+    bool any_nan = false;
+    for (int c = 0; c < C; ++c) {
+        float d = __fsub_rn(x[c], m);
+        any_nan |= (d != d);
+        float e = spec_expf(d);
+        S = (c == 0) ? e : __fadd_rn(S, e);
+    }
+    if (any_nan) return 0;
+    int best = 0;
+    float qb = __fdiv_rn(spec_expf(__fsub_rn(x[0], m)), S);
+    for (int c = 1; c < C; ++c) {
+        float q = __fdiv_rn(spec_expf(__fsub_rn(x[c], m)), S);
+        if (q > qb) { qb = q; best = c; }
+    }
+    return best;
+}
+
+// pred = argmax_c softmax_spec(x)_c, returned as a one-hot BYTE mask (1 << 8*pred) for C <= 4
+// (what the packed Dice counters add), or as the index for larger C.
+//
+// Fast path.  Let t = fl(max - 2^-15).  If exactly one class satisfies x_c >= t and all inputs are
+// finite, every other class has fl(x_c - max) <= -2^-17, so spec_expf(d_c) <= 1 - 2^-18 < 1 = spec_expf(0)
+// and IEEE division by the common sum keeps q_c < q_max strictly: the raw arg-max IS the pinned
+// answer.  Near-ties, exact ties, NaN and +-inf (detected through the finiteness of the class sum)
+// run the full pinned arithmetic.  One-hot masks make "exactly one" a power-of-two test.
+template <int C>
+__device__ __forceinline__ unsigned int spec_softmax_argmax_onehot4(const float (&x)[C]) {
+    static_assert(C <= 4, "one-hot byte mask needs C <= 4");
+    float m = x[0], s = x[0];
+#pragma unroll
+    for (int c = 1; c < C; ++c) { m = fmaxf(m, x[c]); s += x[c]; }
+    const float t = m - 3.0517578125e-05f;
+    unsigned int hot = 0u;
+#pragma unroll
+    for (int c = 0; c < C; ++c) hot += (x[c] >= t) ? (1u << (8 * c)) : 0u;
+    const bool fast = ((hot & (hot - 1u)) == 0u) & (hot != 0u) & (fabsf(s) <= 3.4028234664e38f);
+    if (fast) return hot;
+    // rare: scalars by value into an out-of-line call, so x[] never becomes address-taken
+    return 1u << (8 * spec_full_upto4(x[0], C > 1 ? x[C > 1 ? 1 : 0] : 0.0f, C > 2 ? x[C > 2 ? 2 : 0] : 0.0f,
+                                      C > 3 ? x[C > 3 ? 3 : 0] : 0.0f, C));
+}
+
+template <int C>
+__device__ __forceinline__ int spec_softmax_argmax(const float (&x)[C]) {
+    float m = x[0], s = x[0];
+    int am = 0;
+#pragma unroll
+    for (int c = 1; c < C; ++c) {
+        s += x[c];
+        if (x[c] > m) { m = x[c]; am = c; }
+    }
+    const float t = m - 3.0517578125e-05f;
+    int n_ge = 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) n_ge += (x[c] >= t) ? 1 : 0;
+    if ((n_ge == 1) & (fabsf(s) <= 3.4028234664e38f)) return am;
+    return spec_softmax_argmax_full<C>(x);
 }
 
 // runtime-C variant reading a strided column (generic fallback kernels)

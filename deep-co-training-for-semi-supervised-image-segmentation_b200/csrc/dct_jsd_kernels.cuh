@@ -155,6 +155,7 @@ struct JsdOp {
     static constexpr int NIN = K, NOUT = (MODE != kFwd) ? K : 0;
     static constexpr bool HAS_MAP = (MODE != kBwd), USES_UP = (MODE != kFwd), CHECKS_SIMPLEX = !LOGITS;
     static constexpr int NDICE = DICEF ? K : 0;
+    static constexpr bool GMAP = (MODE == kBwd);
     template <int CM>
     static __device__ __forceinline__ float apply(float (&x)[K][CM], int, float g, float, bool& bad) {
         return jsd_pixel<K, CM, LOGITS, MODE != kFwd>(x, div_by_K<K>(g), bad);

@@ -29,6 +29,7 @@ __device__ __forceinline__ void softmax_stats(float (&x)[CM], float (&e)[CM], in
 struct KlProbFwd {
     static constexpr int NIN = 2, NOUT = 0;
     static constexpr int NDICE = 0;
+    static constexpr bool GMAP = false;
     static constexpr bool HAS_MAP = true, USES_UP = false, CHECKS_SIMPLEX = true;
     template <int CM>
     static __device__ __forceinline__ float apply(float (&x)[2][CM], int C, float, float eps, bool& bad) {
@@ -51,6 +52,7 @@ template <bool WANT_Y>
 struct KlProbBwd {
     static constexpr int NIN = 2, NOUT = 2;
     static constexpr int NDICE = 0;
+    static constexpr bool GMAP = true;
     static constexpr bool HAS_MAP = false, USES_UP = true, CHECKS_SIMPLEX = false;
     template <int CM>
     static __device__ __forceinline__ float apply(float (&x)[2][CM], int C, float g, float eps, bool&) {
@@ -72,6 +74,7 @@ template <bool GRAD>
 struct KlLogit {
     static constexpr int NIN = 2, NOUT = GRAD ? 2 : 0;
     static constexpr int NDICE = 0;
+    static constexpr bool GMAP = GRAD;
     static constexpr bool HAS_MAP = true, USES_UP = GRAD, CHECKS_SIMPLEX = false;
     template <int CM>
     static __device__ __forceinline__ float apply(float (&x)[2][CM], int C, float g, float, bool&) {
@@ -107,6 +110,7 @@ struct KlLogit {
 struct KlFromLogits {
     static constexpr int NIN = 2, NOUT = 1;
     static constexpr int NDICE = 0;
+    static constexpr bool GMAP = false;
     static constexpr bool HAS_MAP = true, USES_UP = true, CHECKS_SIMPLEX = true;
     template <int CM>
     static __device__ __forceinline__ float apply(float (&x)[2][CM], int C, float g, float eps, bool& bad) {
@@ -139,6 +143,7 @@ struct KlFromLogits {
 struct KlDivFwd {
     static constexpr int NIN = 2, NOUT = 0;
     static constexpr int NDICE = 0;
+    static constexpr bool GMAP = false;
     static constexpr bool HAS_MAP = true, USES_UP = false, CHECKS_SIMPLEX = true;
     template <int CM>
     static __device__ __forceinline__ float apply(float (&x)[2][CM], int C, float, float eps, bool& bad) {
@@ -159,6 +164,7 @@ struct KlDivFwd {
 struct EntropyFwd {
     static constexpr int NIN = 1, NOUT = 0;
     static constexpr int NDICE = 0;
+    static constexpr bool GMAP = false;
     static constexpr bool HAS_MAP = true, USES_UP = false, CHECKS_SIMPLEX = true;
     template <int CM>
     static __device__ __forceinline__ float apply(float (&x)[1][CM], int C, float, float, bool& bad) {
@@ -177,6 +183,7 @@ struct EntropyFwd {
 struct EntropyBwd {
     static constexpr int NIN = 1, NOUT = 1;
     static constexpr int NDICE = 0;
+    static constexpr bool GMAP = true;
     static constexpr bool HAS_MAP = false, USES_UP = true, CHECKS_SIMPLEX = false;
     template <int CM>
     static __device__ __forceinline__ float apply(float (&x)[1][CM], int C, float g, float, bool&) {
@@ -194,6 +201,7 @@ struct EntropyBwd {
 struct SoftmaxFwd {
     static constexpr int NIN = 1, NOUT = 1;
     static constexpr int NDICE = 0;
+    static constexpr bool GMAP = false;
     static constexpr bool HAS_MAP = false, USES_UP = false, CHECKS_SIMPLEX = false;
     template <int CM>
     static __device__ __forceinline__ float apply(float (&x)[1][CM], int C, float, float, bool&) {
@@ -214,6 +222,7 @@ struct SoftmaxFwd {
 struct SoftmaxBwd {  // in[0] = p, in[1] = gp ; out[0] = gx
     static constexpr int NIN = 2, NOUT = 1;
     static constexpr int NDICE = 0;
+    static constexpr bool GMAP = false;
     static constexpr bool HAS_MAP = false, USES_UP = false, CHECKS_SIMPLEX = false;
     template <int CM>
     static __device__ __forceinline__ float apply(float (&x)[2][CM], int C, float, float, bool&) {

@@ -16,7 +16,8 @@
 // register-tiled fallback):
 //   NIN, NOUT        number of [B,C,HW] input / output tensors (output n reuses input n's rows)
 //   HAS_MAP          produces a per-pixel scalar (map store and/or deterministic grid sum)
-//   USES_UP          consumes an upstream gradient (gconst * *gscalar * gmap[pixel])
+//   USES_UP          consumes an upstream gradient (gconst * *gscalar [* gmap[pixel] if GMAP])
+//   GMAP             the upstream may carry a per-pixel map (reserves one side row per stage)
 //   CHECKS_SIMPLEX   sets the simplex flag through `bad`
 //   NDICE            number of leading input tensors whose Dice counts are accumulated (0 = none)
 //   apply<CM>(x[NIN][CM], C, g, eps, bad) -> map value; outputs left in x[0..NOUT)
@@ -45,26 +46,36 @@ struct TileArgs {
     int num_tiles;
 };
 
-template <int ROWS, int PPT, int THREADS>
+// float rows + optional side rows: int64 labels (Dice ops) and the upstream-gradient map (backward ops)
+template <class Op, int CT>
+constexpr int tile_row_words() {
+    return Op::NIN * CT + (Op::NDICE > 0 ? 2 : 0) + (Op::GMAP ? 1 : 0);
+}
+
+template <int WORDS, int PPT, int THREADS, int MINB>
 constexpr int tile_stages() {
-    // as many stages as fit in ~200 KB, between 2 and 8
-    constexpr size_t stage = (size_t)ROWS * PPT * THREADS * 4;
-    constexpr size_t n = (200 * 1024) / stage;
+    // as many stages as fit in this CTA's share of shared memory, between 2 and 8
+    constexpr size_t stage = (size_t)WORDS * PPT * THREADS * 4;
+    // 228 KB per SM, 1 KB reserved per CTA, ~0.7 KB of static shared memory + barriers in the kernel
+    constexpr size_t n = (233472 / MINB - 1024 - 672) / stage;
     return n < 2 ? 2 : (n > 8 ? 8 : (int)n);
 }
 
 template <class Op, int CT, int PPT, int THREADS, int STAGES>
 struct TileCfg {
     static constexpr int TP = THREADS * PPT;
-    static constexpr int ROWS = Op::NIN * CT;
-    static constexpr size_t kStageBytes = (size_t)ROWS * TP * 4;
+    static constexpr int ROWS = Op::NIN * CT;                       // float data rows
+    static constexpr int WORDS = tile_row_words<Op, CT>();          // 4-byte words per pixel incl. side rows
+    static constexpr size_t kStageBytes = (size_t)WORDS * TP * 4;
+    static constexpr int kLabelOff = ROWS * TP;                     // in floats; labels are 8-byte, TP*8 bytes
+    static constexpr int kGmapOff = (ROWS + (Op::NDICE > 0 ? 2 : 0)) * TP;  // valid when Op::GMAP
     static constexpr size_t kSmemBytes = kStageBytes * STAGES + 8 * STAGES + 128;
 };
 
-template <class Op, int CT, int PPT, int THREADS, int STAGES>
-__global__ void __launch_bounds__(THREADS, 1) tile_kernel(const TileArgs a) {
+template <class Op, int CT, int PPT, int THREADS, int STAGES, int MINB = 1>
+__global__ void __launch_bounds__(THREADS, MINB) tile_kernel(const TileArgs a) {
     using Cfg = TileCfg<Op, CT, PPT, THREADS, STAGES>;
-    constexpr int TP = Cfg::TP, ROWS = Cfg::ROWS, NIN = Op::NIN, NOUT = Op::NOUT, C = CT;
+    constexpr int TP = Cfg::TP, ROWS = Cfg::ROWS, WORDS = Cfg::WORDS, NIN = Op::NIN, NOUT = Op::NOUT, C = CT;
     constexpr bool DICE = Op::NDICE > 0;
     static_assert(!DICE || CT <= 4, "fused Dice counters are packed 8-bit fields: C <= 4");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -74,6 +85,8 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const TileArgs a) {
     const int tid = threadIdx.x;
     const int64_t HW = a.HW;
     const int tpi = a.tiles_per_image;
+    const bool do_dice = DICE && a.labels != nullptr;
+    const bool has_gmap = Op::GMAP && a.up.gmap != nullptr;
 
     // contiguous tile range of this CTA
     const int per = a.num_tiles / gridDim.x, extra = a.num_tiles % gridDim.x;
@@ -95,13 +108,22 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const TileArgs a) {
         const int64_t off = (int64_t)(tile - b * tpi) * TP;
         const int64_t rem = HW - off;
         const uint32_t bytes = (uint32_t)((rem < TP ? rem : TP) * 4);
-        float* dst = stages + (size_t)stage * ROWS * TP;
-        tma::mbar_expect_tx(&full[stage], bytes * ROWS);
+        float* dst = stages + (size_t)stage * WORDS * TP;
+        uint32_t total = bytes * ROWS;
+        if constexpr (DICE) total += do_dice ? 2u * bytes : 0u;
+        if constexpr (Op::GMAP) total += has_gmap ? bytes : 0u;
+        tma::mbar_expect_tx(&full[stage], total);
 #pragma unroll
         for (int n = 0; n < NIN; ++n)
 #pragma unroll
             for (int c = 0; c < C; ++c)
                 tma::bulk_load(dst + (n * C + c) * TP, a.in[n] + ((int64_t)b * C + c) * HW + off, bytes, &full[stage]);
+        if constexpr (DICE) {
+            if (do_dice) tma::bulk_load(dst + Cfg::kLabelOff, a.labels + (int64_t)b * HW + off, 2u * bytes, &full[stage]);
+        }
+        if constexpr (Op::GMAP) {
+            if (has_gmap) tma::bulk_load(dst + Cfg::kGmapOff, a.up.gmap + (int64_t)b * HW + off, bytes, &full[stage]);
+        }
     };
 
     if (tid == 0) {
@@ -115,29 +137,37 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const TileArgs a) {
     double acc = 0.0;
     bool bad = false;
     int nbad_label = 0;
-    unsigned int pk[DICE ? Op::NDICE : 1][3];  // packed 8-bit per-class counters: [view][I,G,P]
+    unsigned int pk[DICE ? Op::NDICE : 1][2];  // packed 8-bit per-class counters: [view][I,P]
+    unsigned int pkG = 0u;                     // |gt == c| is the same for every view
     if constexpr (DICE) {
 #pragma unroll
-        for (int n = 0; n < Op::NDICE; ++n) pk[n][0] = pk[n][1] = pk[n][2] = 0u;
+        for (int n = 0; n < Op::NDICE; ++n) pk[n][0] = pk[n][1] = 0u;
     }
     int cur_b = -1, since_flush = 0;
-    const bool do_dice = DICE && a.labels != nullptr;
 
     // flush this thread's packed counters into the CTA's shared counters, then (all threads) to global
     auto flush_counts = [&](int b) {
         if constexpr (DICE) {
 #pragma unroll
-            for (int n = 0; n < Op::NDICE; ++n)
+            for (int c = 0; c < C; ++c) {
+                int g = (int)((pkG >> (8 * c)) & 0xffu);
+                g = __reduce_add_sync(0xffffffffu, g);
 #pragma unroll
-                for (int q = 0; q < 3; ++q)
-#pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        int v = (int)((pk[n][q] >> (8 * c)) & 0xffu);
-                        v = __reduce_add_sync(0xffffffffu, v);
-                        if ((tid & 31) == 0 && v) atomicAdd(&s_cnt[(n * C + c) * 3 + q], v);
+                for (int n = 0; n < Op::NDICE; ++n) {
+                    int vi = (int)((pk[n][0] >> (8 * c)) & 0xffu);
+                    int vp = (int)((pk[n][1] >> (8 * c)) & 0xffu);
+                    vi = __reduce_add_sync(0xffffffffu, vi);
+                    vp = __reduce_add_sync(0xffffffffu, vp);
+                    if ((tid & 31) == 0) {
+                        if (vi) atomicAdd(&s_cnt[(n * C + c) * 3 + 0], vi);
+                        if (g) atomicAdd(&s_cnt[(n * C + c) * 3 + 1], g);
+                        if (vp) atomicAdd(&s_cnt[(n * C + c) * 3 + 2], vp);
                     }
+                }
+            }
+            pkG = 0u;
 #pragma unroll
-            for (int n = 0; n < Op::NDICE; ++n) pk[n][0] = pk[n][1] = pk[n][2] = 0u;
+            for (int n = 0; n < Op::NDICE; ++n) pk[n][0] = pk[n][1] = 0u;
             __syncthreads();
             for (int j = tid; j < Op::NDICE * C * 3; j += THREADS) {
                 const int v = s_cnt[j];
@@ -159,7 +189,7 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const TileArgs a) {
         const int64_t off = (int64_t)(tile - b * tpi) * TP;
         const int64_t rem = HW - off;
         const int len = (int)(rem < TP ? rem : TP);
-        float* st = stages + (size_t)stage * ROWS * TP;
+        float* st = stages + (size_t)stage * WORDS * TP;
         const int p0 = tid * PPT;
         const bool active = p0 < len;
         if constexpr (DICE) {
@@ -169,19 +199,21 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const TileArgs a) {
                 since_flush = 0;
             }
         }
-        // small per-pixel side inputs come straight from global memory, requested before the wait
-        FVec<PPT> gm;
-#pragma unroll
-        for (int v = 0; v < PPT; ++v) gm.v[v] = 1.0f;
-        if constexpr (Op::USES_UP) {
-            if (a.up.gmap != nullptr && active) gm = ld_stream<PPT>(a.up.gmap + (int64_t)b * HW + off + p0);
-        }
-        long long lab[PPT];
-        if constexpr (DICE) {
-            if (do_dice && active) ld_labels<PPT>(a.labels + (int64_t)b * HW + off + p0, lab);
-        }
         tma::mbar_wait(&full[stage], parity);
         if (active) {
+            FVec<PPT> gm;
+#pragma unroll
+            for (int v = 0; v < PPT; ++v) gm.v[v] = 1.0f;
+            if constexpr (Op::GMAP) {
+                if (has_gmap) gm = *reinterpret_cast<const FVec<PPT>*>(st + Cfg::kGmapOff + p0);
+            }
+            uint2 lab[PPT];  // int64 labels as (lo, hi) words
+            if constexpr (DICE) {
+                if (do_dice) {
+#pragma unroll
+                    for (int v = 0; v < PPT; ++v) lab[v] = reinterpret_cast<const uint2*>(st + Cfg::kLabelOff)[p0 + v];
+                }
+            }
             FVec<PPT> xin[NIN][C];
 #pragma unroll
             for (int n = 0; n < NIN; ++n)
@@ -198,18 +230,16 @@ __global__ void __launch_bounds__(THREADS, 1) tile_kernel(const TileArgs a) {
                     for (int c = 0; c < C; ++c) x[n][c] = xin[n][c].v[v];
                 if constexpr (DICE) {
                     if (do_dice) {
-                        const long long gl = lab[v];
-                        const bool valid = (gl >= 0) & (gl < C);
+                        const unsigned int gl = lab[v].x;
+                        const bool valid = (lab[v].y == 0u) & (gl < (unsigned int)C);  // 0 <= int64 label < C
                         nbad_label += !valid;
+                        const unsigned int gmask = valid ? (1u << (8u * (gl & 3u))) : 0u;  // one-hot byte of the label
+                        pkG += gmask;
 #pragma unroll
                         for (int n = 0; n < Op::NDICE; ++n) {
-                            const int pred = spec_softmax_argmax<C>(x[n]);
-                            const unsigned int sh = 8u * (unsigned int)pred;
-                            pk[n][2] += 1u << sh;
-                            if (valid) {
-                                pk[n][1] += 1u << (8u * (unsigned int)gl);
-                                pk[n][0] += (unsigned int)(gl == pred) << sh;
-                            }
+                            const unsigned int hot = spec_softmax_argmax_onehot4<C>(x[n]);  // one-hot byte of the prediction
+                            pk[n][1] += hot;
+                            pk[n][0] += hot & gmask;
                         }
                     }
                 }
@@ -291,10 +321,13 @@ template <class Op, int CT>
 int tile_launch_ct(TileArgs a, int64_t B, cudaStream_t stream) {
     constexpr int ROWS = Op::NIN * CT;
     static_assert(ROWS <= 16, "tile pipeline instantiations are for NIN*C <= 16 (larger: register-tiled kernels)");
-    constexpr int PPT = 4, THREADS = 256;
-    constexpr int STAGES = tile_stages<ROWS, PPT, THREADS>();
+    // measured on B200 (tools/kbench_tile.cu): two 256-thread CTAs per SM beat one larger CTA for every op
+    // (the per-tile CTA barrier of one overlaps the math of the other); math-heavy ops take 2 pixels/thread.
+    constexpr int THREADS = 256, MINB = 2;
+    constexpr int PPT = ROWS > 8 ? 2 : 4;
+    constexpr int STAGES = tile_stages<tile_row_words<Op, CT>(), PPT, THREADS, MINB>();
     using Cfg = TileCfg<Op, CT, PPT, THREADS, STAGES>;
-    auto kern = tile_kernel<Op, CT, PPT, THREADS, STAGES>;
+    auto kern = tile_kernel<Op, CT, PPT, THREADS, STAGES, MINB>;
     static bool configured[64] = {};  // per instantiation and device (the attribute is per device function)
     int devid = 0;
     cudaGetDevice(&devid);
@@ -305,7 +338,7 @@ int tile_launch_ct(TileArgs a, int64_t B, cudaStream_t stream) {
     }
     a.tiles_per_image = (int)((a.HW + Cfg::TP - 1) / Cfg::TP);
     a.num_tiles = (int)(a.tiles_per_image * B);
-    int grid = kSMs;
+    int grid = kSMs * MINB;
     if (grid > a.num_tiles) grid = a.num_tiles;
     kern<<<grid, THREADS, Cfg::kSmemBytes, stream>>>(a);
     return check_launch();

@@ -27,6 +27,7 @@ struct L2Args {
     const float* d;
     float* out;
     int64_t M;
+    int passes;        // 1, or 2 = normalise(normalise(d)) (AEGenerator.py:98 followed by :103)
     float scale;
     const float* img;  // nullable
     float* adv;        // nullable
@@ -50,10 +51,10 @@ __device__ __forceinline__ float block_sum_f(float v, float* s_warp) {
     return t;
 }
 
-__device__ __forceinline__ void l2_emit(const L2Args& a, int64_t off, const FVec<4>& v, float nrm) {
+__device__ __forceinline__ void l2_emit(const L2Args& a, int64_t off, const FVec<4>& v) {
     FVec<4> o;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) o.v[j] = a.scale * __fdiv_rn(v.v[j], nrm);  // d /= norm ; then scale * d
+    for (int j = 0; j < 4; ++j) o.v[j] = a.scale * v.v[j];  // (d / norm) was formed in registers; then scale * d
     st_stream<4>(a.out + off, o);
     if (a.img != nullptr) {
         FVec<4> im = ld_stream<4>(a.img + off), ad;
@@ -84,18 +85,32 @@ l2_cluster_kernel(const L2Args a) {
             ss += v[j].v[0] * v[j].v[0] + v[j].v[1] * v[j].v[1] + v[j].v[2] * v[j].v[2] + v[j].v[3] * v[j].v[3];
         }
     }
-    float cta = block_sum_f(ss, s_warp);
-    if (threadIdx.x == 0) s_part = cta;
-    cluster.sync();
-    float tot = 0.0f;
+    for (int pass = 0; pass < a.passes; ++pass) {
+        float cta = block_sum_f(ss, s_warp);
+        if (threadIdx.x == 0) s_part = cta;
+        cluster.sync();
+        float tot = 0.0f;
 #pragma unroll
-    for (int r = 0; r < kL2Cluster; ++r) tot += *cluster.map_shared_rank(&s_part, r);  // DSMEM, fixed order
-    cluster.sync();  // peers may not exit (and free s_part) before everyone has read it
-    const float nrm = sqrtf(tot) + 1e-16f;
+        for (int r = 0; r < kL2Cluster; ++r) tot += *cluster.map_shared_rank(&s_part, r);  // DSMEM, fixed order
+        cluster.sync();  // nobody may overwrite / free s_part before every peer has read it
+        const float nrm = sqrtf(tot) + 1e-16f;
+        ss = 0.0f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int64_t q = ((int64_t)j * kL2Cluster + rank) * kL2Threads + threadIdx.x;
+            if (q < nvec) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    v[j].v[e] = __fdiv_rn(v[j].v[e], nrm);  // d /= norm (IEEE divide, as the reference)
+                    ss += v[j].v[e] * v[j].v[e];
+                }
+            }
+        }
+    }
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
         const int64_t q = ((int64_t)j * kL2Cluster + rank) * kL2Threads + threadIdx.x;
-        if (q < nvec) l2_emit(a, base + q * 4, v[j], nrm);
+        if (q < nvec) l2_emit(a, base + q * 4, v[j]);
     }
 }
 
@@ -131,7 +146,7 @@ __global__ void __launch_bounds__(256) l2_scale_kernel(const L2Args a, int npart
     __syncthreads();
     const float nrm = s_nrm;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.M; i += (int64_t)gridDim.x * blockDim.x) {
-        float o = a.scale * __fdiv_rn(a.d[base + i], nrm);
+        float o = a.scale * __fdiv_rn(a.d[base + i], nrm);  // scale == 1 on all but the last pass
         a.out[base + i] = o;
         if (a.img != nullptr) a.adv[base + i] = fminf(fmaxf(a.img[base + i] + o, 0.0f), 1.0f);
     }
@@ -176,13 +191,13 @@ static inline unsigned ew_blocks(int64_t n, int vec) {
 
 using namespace dct;
 
-extern "C" int dct_l2_normalize_f32(const float* d, float* out, int64_t B, int64_t M, float scale, const float* img,
-                                    float* adv, void* workspace, void* stream) {
-    if (d == nullptr || out == nullptr || B < 1 || M < 1) return DCT_ERR_BAD_ARG;
+extern "C" int dct_l2_normalize_f32(const float* d, float* out, int64_t B, int64_t M, int passes, float scale,
+                                    const float* img, float* adv, void* workspace, void* stream) {
+    if (d == nullptr || out == nullptr || B < 1 || M < 1 || passes < 1 || passes > 2) return DCT_ERR_BAD_ARG;
     if ((img == nullptr) != (adv == nullptr)) return DCT_ERR_BAD_ARG;
     if (!aligned(d, 4) || !aligned(out, 4) || !aligned(img, 4) || !aligned(adv, 4)) return DCT_ERR_MISALIGNED;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    L2Args a{d, out, M, scale, img, adv, static_cast<Workspace*>(workspace)};
+    L2Args a{d, out, M, passes, scale, img, adv, static_cast<Workspace*>(workspace)};
     const bool vec_ok = (M % 4) == 0 && aligned(d, 16) && aligned(out, 16) && aligned(img, 16) && aligned(adv, 16);
     const int64_t per_wave = (int64_t)kL2Cluster * kL2Threads * 4;  // floats covered by one float4 per thread
     const int64_t nv = (M + per_wave - 1) / per_wave;
@@ -202,11 +217,22 @@ extern "C" int dct_l2_normalize_f32(const float* d, float* out, int64_t B, int64
     if (cap < 1) return DCT_ERR_UNSUPPORTED;
     if (gx > cap) gx = cap;
     if (gx > 1024) gx = 1024;
-    l2_sumsq_kernel<<<dim3((unsigned)gx, (unsigned)B), 256, 0, s>>>(d, M, a.ws);
-    int rc = check_launch();
-    if (rc != DCT_OK) return rc;
-    l2_scale_kernel<<<dim3((unsigned)gx, (unsigned)B), 256, 0, s>>>(a, (int)gx);
-    return check_launch();
+    for (int pass = 0; pass < passes; ++pass) {
+        // two launches per pass; intermediate passes write the unscaled result to `out` and continue from there
+        const bool last = (pass == passes - 1);
+        L2Args p = a;
+        p.d = (pass == 0) ? d : out;
+        p.scale = last ? scale : 1.0f;
+        p.img = last ? img : nullptr;
+        p.adv = last ? adv : nullptr;
+        l2_sumsq_kernel<<<dim3((unsigned)gx, (unsigned)B), 256, 0, s>>>(p.d, M, a.ws);
+        int rc = check_launch();
+        if (rc != DCT_OK) return rc;
+        l2_scale_kernel<<<dim3((unsigned)gx, (unsigned)B), 256, 0, s>>>(p, (int)gx);
+        rc = check_launch();
+        if (rc != DCT_OK) return rc;
+    }
+    return DCT_OK;
 }
 
 extern "C" int dct_fgsm_f32(const float* img, const float* grad, float eps, float* adv, float* noise, int64_t n,

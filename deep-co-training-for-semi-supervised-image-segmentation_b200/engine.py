@@ -84,28 +84,30 @@ class ConsistencyStep:
         self.jsd_weight, self.adv_weight, self.xi, self.eps, self.kl_eps = jsd_weight, adv_weight, xi, eps, kl_eps
         self.with_vat, self.with_dice = with_vat, with_dice
         self._h = _lib.lib()
-        # kernels launched per run(): the fused JSD (+K dice launches until that fusion lands in one kernel)
-        self.launches_per_step = 1 + (K if with_dice else 0) + (5 if with_vat else 0)
+        # kernels launched per run(): the JSD kernel (Dice fused for C <= 4, else K counting launches) + 4 VAT/KL
+        self.launches_per_step = 1 + (0 if (not with_dice or (C <= 4 and K * C <= 16)) else K) + (4 if with_vat else 0)
 
     # bytes that MUST move per step (algorithmic, fp32): see DESIGN.md "Algorithmic bytes"
     def algorithmic_bytes(self):
         K, C, n = self.K, self.C, self.B * self.HW
         cin = self.M // self.HW
-        b = {"jsd_fwdbwd": n * (2 * K * C * 4), "dice": (n * K * (C * 4 + 8)) if self.with_dice else 0}
+        fused = self.with_dice and C <= 4 and K * C <= 16   # Dice counted inside the JSD kernel: + labels only
+        b = {"jsd_fwdbwd": n * (2 * K * C * 4) + (n * 8 if fused else 0),
+             "dice": (n * K * (C * 4 + 8)) if (self.with_dice and not fused) else 0}
         if self.with_vat:
             b.update({"l2_normalize_x3": n * cin * 4 * (2 + 2 + 4), "kl_logit_fwdbwd": n * 3 * C * 4,
                       "kl_from_logits_fwdbwd": n * 3 * C * 4})
         return b
 
-    def run(self, bufs: StepBuffers) -> None:
+    def run(self, bufs: StepBuffers, zero_counts: bool = True) -> None:
         h, K, C, B, HW = self._h, self.K, self.C, self.B, self.HW
         dev = bufs.logits[0].device
         st = _runtime.state(dev)
         ws, s = st.workspace.data_ptr(), _runtime.stream_ptr(dev)
         fl = _runtime.flags_ptr(st)
         sums = bufs.sums.data_ptr()
-        if self.with_dice:
-            bufs.dice_counts.zero_()
+        if self.with_dice and zero_counts:
+            bufs.dice_counts.zero_()  # the kernels accumulate into the counters
         _lib.check(h.dct_jsd_fwdbwd_f32(_lib.ptr_array(bufs.logits), K, C, B, HW, _lib.IN_LOGITS,
                                         self.jsd_weight / self.n, None, sums, _lib.ptr_array(bufs.grad_logits),
                                         bufs.labels.data_ptr() if self.with_dice else None,
@@ -115,14 +117,13 @@ class ConsistencyStep:
             return
         d = bufs.d.data_ptr()
         # d <- normalise(N(0,1));  d <- xi * normalise(d)                       (AEGenerator.py:97-98,103)
-        _lib.check(h.dct_l2_normalize_f32(d, d, B, self.M, 1.0, None, None, ws, s), "dct_l2_normalize_f32")
-        _lib.check(h.dct_l2_normalize_f32(d, d, B, self.M, self.xi, None, None, ws, s), "dct_l2_normalize_f32")
+        _lib.check(h.dct_l2_normalize_f32(d, d, B, self.M, 2, self.xi, None, None, ws, s), "dct_l2_normalize_f32")
         # delta_kl = kl_div_with_logit(pred.detach(), y_hat); delta_kl.mean().backward()       (:107-108)
         _lib.check(h.dct_kl_logit_f32(bufs.logits[0].data_ptr(), bufs.yhat_logits.data_ptr(), C, B, HW, None, sums + 8,
                                       1, None, None, 1.0 / self.n, bufs.grad_yhat.data_ptr(), None, ws, s),
                    "dct_kl_logit_f32")
         # r_adv = eps * normalise(d.grad); img_adv = clamp(img + r_adv, 0, 1)                  (:113-117)
-        _lib.check(h.dct_l2_normalize_f32(bufs.d_grad.data_ptr(), bufs.r_adv.data_ptr(), B, self.M, self.eps,
+        _lib.check(h.dct_l2_normalize_f32(bufs.d_grad.data_ptr(), bufs.r_adv.data_ptr(), B, self.M, 1, self.eps,
                                           bufs.img.data_ptr(), bufs.img_adv.data_ptr(), ws, s), "dct_l2_normalize_f32")
         # adv loss: KL_Divergence_2D(reduce=True)(softmax(adv_logits), real.detach()) + backward (cotraining :391-392)
         _lib.check(h.dct_kl_from_logits_fwdbwd_f32(bufs.adv_logits.data_ptr(), bufs.real_probs.data_ptr(), C, B, HW,

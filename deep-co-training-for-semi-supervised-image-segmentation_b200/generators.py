@@ -21,8 +21,9 @@ from . import _lib, _runtime
 from .loss import kl_div_with_logit as _kl_div_with_logit
 
 
-def l2_normalize(d: Tensor, scale: float = 1.0, out: Tensor = None, img: Tensor = None) -> Tensor:
+def l2_normalize(d: Tensor, scale: float = 1.0, out: Tensor = None, img: Tensor = None, passes: int = 1) -> Tensor:
     """``scale * d / (||d_b||_2 + 1e-16)`` per sample.  ``out`` defaults to ``d`` itself (in place).
+    ``passes=2`` normalises twice before scaling (``xi * _l2_normalize(_l2_normalize(d))``) in one launch.
 
     With ``img`` returns ``(out, clamp(img + out, 0, 1))`` from the same launch.
     """
@@ -41,7 +42,7 @@ def l2_normalize(d: Tensor, scale: float = 1.0, out: Tensor = None, img: Tensor 
         img = img.contiguous()
         assert img.shape == d.shape and img.dtype == torch.float32
         adv = torch.empty_like(img)
-    _lib.check(_lib.lib().dct_l2_normalize_f32(d.data_ptr(), out.data_ptr(), b, m, float(scale),
+    _lib.check(_lib.lib().dct_l2_normalize_f32(d.data_ptr(), out.data_ptr(), b, m, int(passes), float(scale),
                                                None if img is None else img.data_ptr(),
                                                None if adv is None else adv.data_ptr(),
                                                st.workspace.data_ptr(), _runtime.stream_ptr(d.device)),
@@ -118,10 +119,10 @@ class VATGenerator(object):
         with torch.no_grad():
             pred = self.net(img)
         d = torch.randn(img.shape, dtype=torch.float32, device=img.device)
-        d = l2_normalize(d)
         self.net.zero_grad()
-        for _ in range(self.ip):
-            d = l2_normalize(d, scale=self.xi)              # xi * _l2_normalize(d)
+        for it in range(self.ip):
+            # first iteration: d = _l2_normalize(d) (:98) and xi * _l2_normalize(d) (:103) in one launch
+            d = l2_normalize(d, scale=self.xi, passes=2 if it == 0 else 1)
             d.requires_grad = True
             y_hat = self.net(img + d)
             delta_kl = _kl_div_with_logit(pred.detach(), y_hat)  # [B,H,W]

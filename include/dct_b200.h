@@ -160,8 +160,10 @@ DCT_API int dct_softmax_bwd_f32(const float* p, const float* gp, int C, int64_t 
 /* VATGenerator._l2_normalize (AEGenerator.py:68-76): out_b = scale * (d_b / (||d_b||_2 + 1e-16)).
  * `out` may alias `d` (the reference normalises in place); scale = 1 for the bare function,
  * xi / eps for `xi * _l2_normalize(d)` (:103) and `eps * d` (:113-114).
+ * passes = 2 applies the normalisation twice before scaling -- the reference's
+ * `d = _l2_normalize(d)` (:98) immediately followed by `xi * _l2_normalize(d)` (:103) -- in one launch.
  * If img != NULL also writes adv = clamp(img + out, 0, 1) (:116-117). */
-DCT_API int dct_l2_normalize_f32(const float* d, float* out, int64_t B, int64_t M, float scale,
+DCT_API int dct_l2_normalize_f32(const float* d, float* out, int64_t B, int64_t M, int passes, float scale,
                          const float* img, float* adv, void* workspace, void* stream);
 
 /* FSGMGenerator.adversarial_fgsm (AEGenerator.py:35-51): noise = eps*sign(grad); adv = img + noise */

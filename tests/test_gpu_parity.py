@@ -196,6 +196,9 @@ def test_l2_normalize_paths_vs_oracle(dct, dev, oracle):
         wadv, wr = oracle.vat_apply(img.numpy(), want, 10.0)
         assert_close(N(r), wr, what=f"r_adv {shape}")
         assert_close(N(adv), wadv, floor=1.0, what=f"img_adv {shape}")
+        # passes=2: normalise(normalise(d)) then scale, one launch (AEGenerator.py:98 + :103)
+        twice = dct.l2_normalize(d.to(dev).clone(), scale=1e-6, passes=2)
+        assert_close(N(twice), oracle.l2_normalize(want) * np.float32(1e-6), what=f"l2 x2 {shape}")
         nrm = N(got).reshape(shape[0], -1).astype(np.float64)
         assert np.allclose(np.sqrt((nrm ** 2).sum(1)), 1.0, rtol=1e-3)  # the reference's own assert (:75)
 
@@ -391,7 +394,9 @@ def test_flags_and_errors_through_c_abi(dct, dev):
     assert h.dct_jsd_fwd_f32(arr, 2, 65, 1, 64, 1, None, None, None, None, None) == -2     # C > 64
     assert h.dct_jsd_fwd_f32(None, 2, 4, 1, 64, 1, None, None, None, None, None) == -1
     assert h.dct_dice_counts_f32(x.data_ptr() + 2, x.data_ptr(), 4, 1, 64, x.data_ptr(), 0, None, None) == -3
-    assert h.dct_l2_normalize_f32(None, None, 1, 1, 1.0, None, None, None, None) == -1
+    assert h.dct_l2_normalize_f32(None, None, 1, 1, 1, 1.0, None, None, None, None) == -1
+    d = torch.randn(2, 1, 8, 8, device=dev)
+    assert h.dct_l2_normalize_f32(d.data_ptr(), d.data_ptr(), 2, 64, 3, 1.0, None, None, None, None) == -1  # passes in {1,2}
     assert b"misaligned" in h.dct_error_string(-3)
     torch.cuda.synchronize()
 

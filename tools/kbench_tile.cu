@@ -1,0 +1,143 @@
+// kbench_tile.cu -- developer micro-benchmark: tile_kernel<Op,...> configurations (PPT, THREADS, STAGES, CTAs/SM)
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "dct_jsd_kernels.cuh"
+#include "dct_pixelwise.cuh"
+
+namespace dct {
+#define DCT_KBENCH 1
+}
+// pull in the KL ops (defined in dct_kl.cu) without its extern "C" part clashing: include the TU
+#include "dct_kl.cu"
+
+using namespace dct;
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
+
+__global__ void fillf(float* p, size_t n, unsigned seed, float scale) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        unsigned h = (unsigned)i * 2654435761u + seed; h ^= h >> 13; h *= 0x5bd1e995u; h ^= h >> 15;
+        p[i] = ((h & 0xffff) / 65535.0f - 0.5f) * scale;
+    }
+}
+__global__ void filll(long long* p, size_t n, int C) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        unsigned h = (unsigned)i * 2654435761u; h ^= h >> 13; h *= 0x5bd1e995u; h ^= h >> 15;
+        p[i] = h % C;
+    }
+}
+
+struct DiceOpB {
+    static constexpr int NIN = 1, NOUT = 0, NDICE = 1;
+    static constexpr bool HAS_MAP = false, USES_UP = false, CHECKS_SIMPLEX = false, GMAP = false;
+    template <int CM>
+    static __device__ __forceinline__ float apply(float (&)[1][CM], int, float, float, bool&) { return 0.0f; }
+};
+
+template <class Op, int CT, int PPT, int THREADS, int STAGES, int MINB>
+void run(const char* tag, int64_t B, int64_t HW, int reps, double bytes_per_px, bool labels) {
+    using Cfg = TileCfg<Op, CT, PPT, THREADS, STAGES>;
+    auto kern = tile_kernel<Op, CT, PPT, THREADS, STAGES, MINB>;
+    if (Cfg::kSmemBytes * MINB > 227 * 1024) { printf("%-14s skip (smem)\n", tag); return; }
+    const int R = 4;
+    size_t n = (size_t)B * CT * HW;
+    std::vector<TileArgs> sets(R);
+    Workspace* ws; CK(cudaMalloc(&ws, sizeof(Workspace))); CK(cudaMemset(ws, 0, sizeof(Workspace)));
+    double* sum; CK(cudaMalloc(&sum, 8));
+    unsigned long long* counts; CK(cudaMalloc(&counts, 8 * 8 * B * CT * 3)); CK(cudaMemset(counts, 0, 8 * 8 * B * CT * 3));
+    std::vector<void*> allocs;
+    for (int r = 0; r < R; ++r) {
+        TileArgs a{};
+        for (int k = 0; k < Op::NIN; ++k) {
+            float* in; CK(cudaMalloc(&in, n * 4)); allocs.push_back(in);
+            fillf<<<1024, 256>>>(in, n, 17u * r + k, 12.0f);
+            a.in[k] = in;
+        }
+        for (int k = 0; k < Op::NOUT; ++k) { float* g; CK(cudaMalloc(&g, n * 4)); allocs.push_back(g); a.out[k] = g; }
+        if (labels) { long long* l; CK(cudaMalloc(&l, (size_t)B * HW * 8)); allocs.push_back(l); filll<<<1024, 256>>>(l, (size_t)B * HW, CT); a.labels = (const int64_t*)l; }
+        a.counts = counts; a.count_view_stride = B * CT * 3;
+        a.HW = HW; a.map = nullptr; a.sum = Op::HAS_MAP ? sum : nullptr; a.up = Upstream{nullptr, nullptr, 1e-6f};
+        a.eps = 1e-10f; a.flags = nullptr; a.ws = ws;
+        a.tiles_per_image = (int)((HW + Cfg::TP - 1) / Cfg::TP); a.num_tiles = (int)(a.tiles_per_image * B);
+        sets[r] = a;
+    }
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
+    int grid = 148 * MINB; if (grid > sets[0].num_tiles) grid = sets[0].num_tiles;
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 5; ++i) kern<<<grid, THREADS, Cfg::kSmemBytes>>>(sets[i % R]);
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < reps; ++i) kern<<<grid, THREADS, Cfg::kSmemBytes>>>(sets[i % R]);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    double us = ms * 1e3 / reps;
+    cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
+    printf("%-14s C=%d PPT=%d thr=%4d stages=%d minb=%d regs=%3d smem=%3zuKB grid=%3d  %8.2f us  %7.1f GB/s  %6.2f Gpix/s\n", tag, CT, PPT,
+           THREADS, STAGES, MINB, fa.numRegs, Cfg::kSmemBytes / 1024, grid, us, bytes_per_px * B * HW / us / 1e3, B * HW / us / 1e3);
+    for (void* p : allocs) cudaFree(p);
+    cudaFree(ws); cudaFree(sum); cudaFree(counts);
+}
+
+static int g_only = -1, g_idx = 0;
+#define RUN(...) do { if (g_only < 0 || g_only == g_idx) run<__VA_ARGS__>; ++g_idx; } while (0)
+int main(int argc, char** argv) {
+    int reps = argc > 1 ? atoi(argv[1]) : 40;
+    if (argc > 2) g_only = atoi(argv[2]);
+    const int64_t B = 32, HW = 65536;
+    using JD = JsdOp<3, true, kFwdBwd, true>;
+    using JN = JsdOp<3, true, kFwdBwd, false>;
+    if (g_only < 0 || g_only == g_idx) run<JN, 4, 4, 256, 4, 1>("jsd", B, HW, reps, 96, false);
+    ++g_idx;
+    if (g_only < 0 || g_only == g_idx) run<JD, 4, 4, 256, 3, 1>("jsd+dice", B, HW, reps, 104, true);
+    ++g_idx;
+    if (g_only < 0 || g_only == g_idx) run<JD, 4, 2, 512, 3, 1>("jsd+dice", B, HW, reps, 104, true);
+    ++g_idx;
+    if (g_only < 0 || g_only == g_idx) run<JD, 4, 1, 1024, 3, 1>("jsd+dice", B, HW, reps, 104, true);
+    ++g_idx;
+    if (g_only < 0 || g_only == g_idx) run<JD, 4, 2, 256, 4, 2>("jsd+dice", B, HW, reps, 104, true);
+    ++g_idx;
+    if (g_only < 0 || g_only == g_idx) run<JD, 4, 1, 512, 4, 2>("jsd+dice", B, HW, reps, 104, true);
+    ++g_idx;
+    if (g_only < 0 || g_only == g_idx) run<JD, 4, 4, 512, 2, 1>("jsd+dice", B, HW, reps, 104, true);
+    ++g_idx;
+    if (g_only < 0 || g_only == g_idx) run<JD, 4, 2, 1024, 2, 1>("jsd+dice", B, HW, reps, 104, true);
+    ++g_idx;
+    if (g_only < 0 || g_only == g_idx) run<JD, 4, 1, 512, 3, 3>("jsd+dice", B, HW, reps, 104, true);
+    ++g_idx;
+    if (g_only < 0 || g_only == g_idx) run<KlFromLogits, 4, 4, 256, 6, 1>("klfromlogits", B, HW, reps, 48, false);
+    ++g_idx;
+    if (g_only < 0 || g_only == g_idx) run<KlFromLogits, 4, 2, 512, 6, 1>("klfromlogits", B, HW, reps, 48, false);
+    ++g_idx;
+    if (g_only < 0 || g_only == g_idx) run<KlFromLogits, 4, 1, 1024, 6, 1>("klfromlogits", B, HW, reps, 48, false);
+    ++g_idx;
+    if (g_only < 0 || g_only == g_idx) run<KlFromLogits, 4, 4, 256, 3, 2>("klfromlogits", B, HW, reps, 48, false);
+    ++g_idx;
+    if (g_only < 0 || g_only == g_idx) run<KlFromLogits, 4, 2, 512, 3, 2>("klfromlogits", B, HW, reps, 48, false);
+    ++g_idx;
+    if (g_only < 0 || g_only == g_idx) run<KlFromLogits, 4, 4, 512, 3, 1>("klfromlogits", B, HW, reps, 48, false);
+    ++g_idx;
+    if (g_only < 0 || g_only == g_idx) run<KlLogit<true>, 4, 4, 256, 6, 1>("kllogit", B, HW, reps, 64, false);
+    ++g_idx;
+    if (g_only < 0 || g_only == g_idx) run<KlLogit<true>, 4, 2, 512, 6, 1>("kllogit", B, HW, reps, 64, false);
+    ++g_idx;
+    if (g_only < 0 || g_only == g_idx) run<KlLogit<true>, 4, 1, 1024, 6, 1>("kllogit", B, HW, reps, 64, false);
+    ++g_idx;
+    if (g_only < 0 || g_only == g_idx) run<DiceOpB, 4, 4, 256, 8, 1>("dice", B, HW, reps, 24, true);
+    ++g_idx;
+    if (g_only < 0 || g_only == g_idx) run<DiceOpB, 4, 2, 512, 8, 1>("dice", B, HW, reps, 24, true);
+    ++g_idx;
+    if (g_only < 0 || g_only == g_idx) run<DiceOpB, 4, 1, 1024, 8, 1>("dice", B, HW, reps, 24, true);
+    ++g_idx;
+    if (g_only < 0 || g_only == g_idx) run<DiceOpB, 4, 4, 256, 4, 2>("dice", B, HW, reps, 24, true);
+    ++g_idx;
+    // spleen-like: K=2, C=2, 512x512, B=8
+    if (g_only < 0 || g_only == g_idx) run<JsdOp<2, true, kFwdBwd, true>, 2, 4, 256, 8, 1>("jsd+dice c3", 8, 262144, reps, 40, true);
+    ++g_idx;
+    if (g_only < 0 || g_only == g_idx) run<JsdOp<2, true, kFwdBwd, true>, 2, 2, 512, 8, 1>("jsd+dice c3", 8, 262144, reps, 40, true);
+    ++g_idx;
+    if (g_only < 0 || g_only == g_idx) run<JsdOp<2, true, kFwdBwd, true>, 2, 1, 1024, 8, 1>("jsd+dice c3", 8, 262144, reps, 40, true);
+    ++g_idx;
+    return 0;
+}
