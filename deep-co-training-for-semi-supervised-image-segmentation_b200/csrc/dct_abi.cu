@@ -1,6 +1,19 @@
 // dct_abi.cu -- library-level entry points of include/dct_b200.h
 #include "dct_common.cuh"
 
+#include <cstdlib>
+#include <cstring>
+
+namespace dct {
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = std::getenv("DCT_B200_PDL");
+        return !(e != nullptr && std::strcmp(e, "0") == 0);
+    }();
+    return on;
+}
+}  // namespace dct
+
 using namespace dct;
 
 extern "C" int dct_abi_version(void) { return DCT_ABI_VERSION; }

@@ -43,6 +43,30 @@ inline int check_launch() {
     return DCT_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (sm_90+): the kernels of one consistency step are 15-45 us each,
+// so the ~2 us launch latency + prologue of kernel N+1 is overlapped with the tail of kernel N.
+// Every kernel launched through launch_pdl() executes pdl_wait() before its first global-memory
+// access (full completion + visibility of the previous grid), so no data dependency is relaxed.
+// DCT_B200_PDL=0 in the environment falls back to plain stream-ordered launches.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();  // dct_abi.cu
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 // ---------------------------------------------------------------------------------------------
@@ -380,6 +404,66 @@ constexpr float kLn2 = 0.69314718055994531f;
 
 // the reference's simplex predicate for one pixel: |sum - 1| <= 1e-8 + 1e-5 (utils/utils.py:142-151)
 __device__ __forceinline__ bool simplex_ok(float s) { return fabsf(s - 1.0f) <= (1e-8f + 1e-5f); }
+
+// ---------------------------------------------------------------------------------------------
+// Lane types of the per-pixel math.  Every Op body is written once against the v*() helpers below
+// and instantiated for T = float (one pixel) and T = f2 (TWO pixels in a 64-bit register pair).
+// On sm_100 the f2 adds / multiplies / FMAs are single packed instructions (SASS FADD2 / FMUL2 /
+// FFMA2 via __fadd2_rn / __fmul2_rn / __ffma2_rn): the tile kernels are issue-slot bound at their
+// low occupancy, and packing halves the FP32 instruction count.  Per component the packed ops
+// round exactly like their scalar twins, so both instantiations give bit-identical results.
+// MUFU (ex2/lg2/rcp), min/max and compares stay per component.
+// ---------------------------------------------------------------------------------------------
+struct f2 {
+    float2 v;
+};
+__device__ __forceinline__ f2 mk2(float a, float b) { return f2{make_float2(a, b)}; }
+
+template <class T> __device__ __forceinline__ T vset(float s);
+template <> __device__ __forceinline__ float vset<float>(float s) { return s; }
+template <> __device__ __forceinline__ f2 vset<f2>(float s) { return mk2(s, s); }
+
+__device__ __forceinline__ float vadd(float a, float b) { return a + b; }
+__device__ __forceinline__ float vsub(float a, float b) { return a - b; }
+__device__ __forceinline__ float vmul(float a, float b) { return a * b; }
+__device__ __forceinline__ float vfma(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ float vmax(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ float vneg(float a) { return -a; }
+__device__ __forceinline__ float vex2(float a) { return ex2_ftz(a); }
+__device__ __forceinline__ float vlg2(float a) { return lg2_ftz(a); }
+__device__ __forceinline__ float vrcp(float a) { return rcp_ftz(a); }
+__device__ __forceinline__ float vlog(float a) { return flog(a); }
+__device__ __forceinline__ float vexp(float a) { return fexp(a); }
+__device__ __forceinline__ float vdiv(float a, float b) { return fdiv(a, b); }
+__device__ __forceinline__ float vhsum(float a) { return a; }
+__device__ __forceinline__ bool vsimplex_bad(float s) { return !simplex_ok(s); }
+
+__device__ __forceinline__ f2 vadd(f2 a, f2 b) { return f2{__fadd2_rn(a.v, b.v)}; }
+__device__ __forceinline__ f2 vmul(f2 a, f2 b) { return f2{__fmul2_rn(a.v, b.v)}; }
+__device__ __forceinline__ f2 vfma(f2 a, f2 b, f2 c) { return f2{__ffma2_rn(a.v, b.v, c.v)}; }
+// a - b as fma(b, -1, a): one rounding of the exact difference, identical to a subtraction
+__device__ __forceinline__ f2 vsub(f2 a, f2 b) { return f2{__ffma2_rn(b.v, make_float2(-1.0f, -1.0f), a.v)}; }
+__device__ __forceinline__ f2 vmax(f2 a, f2 b) { return mk2(fmaxf(a.v.x, b.v.x), fmaxf(a.v.y, b.v.y)); }
+__device__ __forceinline__ f2 vneg(f2 a) { return mk2(-a.v.x, -a.v.y); }
+__device__ __forceinline__ f2 vex2(f2 a) { return mk2(ex2_ftz(a.v.x), ex2_ftz(a.v.y)); }
+__device__ __forceinline__ f2 vlg2(f2 a) { return mk2(lg2_ftz(a.v.x), lg2_ftz(a.v.y)); }
+__device__ __forceinline__ f2 vrcp(f2 a) { return mk2(rcp_ftz(a.v.x), rcp_ftz(a.v.y)); }
+__device__ __forceinline__ f2 vlog(f2 a) { return mk2(flog(a.v.x), flog(a.v.y)); }
+__device__ __forceinline__ f2 vexp(f2 a) { return mk2(fexp(a.v.x), fexp(a.v.y)); }
+__device__ __forceinline__ f2 vdiv(f2 a, f2 b) { return mk2(fdiv(a.v.x, b.v.x), fdiv(a.v.y, b.v.y)); }
+__device__ __forceinline__ float vhsum(f2 a) { return a.v.x + a.v.y; }
+__device__ __forceinline__ float vget(float a, int) { return a; }
+__device__ __forceinline__ float vget(f2 a, int j) { return j == 0 ? a.v.x : a.v.y; }
+__device__ __forceinline__ bool vsimplex_bad(f2 s) { return !simplex_ok(s.v.x) | !simplex_ok(s.v.y); }
+
+// scalar-operand forms (the scalar is broadcast for f2)
+template <class T> __device__ __forceinline__ T vadds(T a, float s) { return vadd(a, vset<T>(s)); }
+template <class T> __device__ __forceinline__ T vmuls(T a, float s) { return vmul(a, vset<T>(s)); }
+template <class T> __device__ __forceinline__ T vfmas(T a, float s, T c) { return vfma(a, vset<T>(s), c); }
+
+// apply a scalar function per component (for the rare exact-arithmetic ops)
+template <class F> __device__ __forceinline__ float vmap(F f, float a, float b) { return f(a, b); }
+template <class F> __device__ __forceinline__ f2 vmap(F f, f2 a, f2 b) { return mk2(f(a.v.x, b.v.x), f(a.v.y, b.v.y)); }
 
 __device__ __forceinline__ float upstream_scalar(const Upstream& u) {
     float g = u.gconst;

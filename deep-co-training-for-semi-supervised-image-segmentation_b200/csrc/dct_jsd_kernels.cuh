@@ -47,92 +47,95 @@ __device__ __forceinline__ float div_by_K(float s) {
     return s * (1.0f / (float)K);
 }
 
-// One pixel.  In: x[k][c] (probs or logits).  Out: returns the JSD value (nats); if GRAD, x[k][c] is
+// One pixel (T = float) or one pixel PAIR (T = f2, packed FP32x2 math -- see dct_common.cuh).
+// In: x[k][c] (probs or logits).  Out: returns the JSD value (nats); if GRAD, x[k][c] is
 // overwritten with gK * d JSD / d x[k][c]  (gK = upstream / K).  `bad` is set when a view fails
 // the reference's simplex predicate (probs mode only).
 //
 // All logarithms are taken in base 2 (one MUFU.LG2 / MUFU.EX2 each, flush-to-zero) and the
 // ln 2 factor is applied once per pixel: H = -ln2 * sum p*lg2(p).
-template <int K, int C, bool LOGITS, bool GRAD>
-__device__ __forceinline__ float jsd_pixel(float (&x)[K][C], float gK, bool& bad) {
-    float p[K][C];
-    float hsum = 0.0f;  // sum_k sum_c p*lg2 p   (= -sum_k H_k / ln2)
+template <int K, int C, bool LOGITS, bool GRAD, class T>
+__device__ __forceinline__ T jsd_pixel(T (&x)[K][C], T gK, bool& bad) {
+    constexpr float invK = 1.0f / (float)K;  // exact for powers of two; else <= 1 ulp from the true division
+    T p[K][C];
+    T hsum = vset<T>(0.0f);  // sum_k sum_c p*lg2 p   (= -sum_k H_k / ln2)
     if constexpr (LOGITS) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            float mx = x[k][0];
+            T mx = x[k][0];
 #pragma unroll
-            for (int c = 1; c < C; ++c) mx = fmaxf(mx, x[k][c]);
-            const float mxl = mx * kLog2e;
-            float Z = 0.0f;
+            for (int c = 1; c < C; ++c) mx = vmax(mx, x[k][c]);
+            const T nmxl = vmuls(mx, -kLog2e);
+            T Z;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                float t = fmaf(x[k][c], kLog2e, -mxl);  // (x - max) * log2(e), one rounding
-                float e = ex2_ftz(t);
+                T t = vfmas(x[k][c], kLog2e, nmxl);  // (x - max) * log2(e), one rounding
+                T e = vex2(t);
                 x[k][c] = t;
                 p[k][c] = e;
-                Z += e;
+                Z = (c == 0) ? e : vadd(Z, e);
             }
-            const float inv = rcp_ftz(Z);
-            const float lZ = lg2_ftz(Z);
-            float hk = 0.0f;
+            const T inv = vrcp(Z);
+            const T lZ = vlg2(Z);
+            T hk = vset<T>(0.0f);
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                float pv = p[k][c] * inv;
-                float lp = x[k][c] - lZ;  // lg2 softmax: differs from lg2(p+1e-16) by < 1e-16/p, and
-                p[k][c] = pv;             // only ever multiplied by p  ->  absolute error < 1e-16
+                T pv = vmul(p[k][c], inv);
+                T lp = vsub(x[k][c], lZ);  // lg2 softmax: differs from lg2(p+1e-16) by < 1e-16/p, and
+                p[k][c] = pv;              // only ever multiplied by p  ->  absolute error < 1e-16
                 x[k][c] = lp;
-                hk = fmaf(pv, lp, hk);
+                hk = vfma(pv, lp, hk);
             }
-            hsum += hk;
+            hsum = vadd(hsum, hk);
         }
     } else {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            float s = 0.0f, hk = 0.0f;
+            T s = vset<T>(0.0f), hk = vset<T>(0.0f);
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                float pv = x[k][c];
-                s += pv;
-                float lp = lg2_ftz(pv + kEntEps);
+                T pv = x[k][c];
+                s = vadd(s, pv);
+                T lp = vlg2(vadds(pv, kEntEps));
                 p[k][c] = pv;
                 x[k][c] = lp;
-                hk = fmaf(pv, lp, hk);
+                hk = vfma(pv, lp, hk);
             }
-            bad |= !simplex_ok(s);
-            hsum += hk;
+            bad |= vsimplex_bad(s);
+            hsum = vadd(hsum, hk);
         }
     }
-    float hm = 0.0f;  // sum_c m*lg2(m+eps)  (= -H(m)/ln2)
-    float am[C];      // per class: lg2(m+eps) [probs mode with GRAD: ln2*lg2(m+eps) + m/(m+eps)]
+    T hm = vset<T>(0.0f);  // sum_c m*lg2(m+eps)  (= -H(m)/ln2)
+    T am[C];               // per class: lg2(m+eps) [probs mode with GRAD: ln2*lg2(m+eps) + m/(m+eps)]
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        float s = p[0][c];
+        T s = p[0][c];
 #pragma unroll
-        for (int k = 1; k < K; ++k) s += p[k][c];
-        float m = div_by_K<K>(s);
-        float lm = lg2_ftz(m + kEntEps);
-        hm = fmaf(m, lm, hm);
-        if constexpr (GRAD && !LOGITS) lm = fmaf(lm, kLn2, m * rcp_ftz(m + kEntEps));
+        for (int k = 1; k < K; ++k) s = vadd(s, p[k][c]);
+        T m = vmuls(s, invK);
+        T me = vadds(m, kEntEps);
+        T lm = vlg2(me);
+        hm = vfma(m, lm, hm);
+        if constexpr (GRAD && !LOGITS) lm = vfmas(lm, kLn2, vmul(m, vrcp(me)));
         am[c] = lm;
     }
-    const float jsd = kLn2 * (div_by_K<K>(hsum) - hm);
+    const T jsd = vmuls(vsub(vmuls(hsum, invK), hm), kLn2);
     if constexpr (GRAD) {
         if constexpr (LOGITS) {
             // d/dz_kc = gK * p_kc * ((ln p_kc - ln m_c) - KL(p_k || m));  the +1 terms of
             // d(p log p)/dp cancel inside the softmax backward.  ln = ln2 * lg2 folded into gK.
-            const float g2 = gK * kLn2;
+            const T g2 = vmuls(gK, kLn2);
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                float kl = 0.0f;
+                T kl = vset<T>(0.0f);
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
-                    float t = x[k][c] - am[c];
+                    T t = vsub(x[k][c], am[c]);
                     x[k][c] = t;
-                    kl = fmaf(p[k][c], t, kl);
+                    kl = vfma(p[k][c], t, kl);
                 }
 #pragma unroll
-                for (int c = 0; c < C; ++c) x[k][c] = (g2 * p[k][c]) * (x[k][c] - kl);
+                for (int c = 0; c < C; ++c) x[k][c] = vmul(vmul(g2, p[k][c]), vsub(x[k][c], kl));
             }
         } else {
             // d/dp_kc = gK * [(ln(p+e) + p/(p+e)) - (ln(m+e) + m/(m+e))]
@@ -140,9 +143,9 @@ __device__ __forceinline__ float jsd_pixel(float (&x)[K][C], float gK, bool& bad
             for (int k = 0; k < K; ++k)
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
-                    float pv = p[k][c];
-                    float a = fmaf(x[k][c], kLn2, pv * rcp_ftz(pv + kEntEps));
-                    x[k][c] = gK * (a - am[c]);
+                    T pv = p[k][c];
+                    T a = vfmas(x[k][c], kLn2, vmul(pv, vrcp(vadds(pv, kEntEps))));
+                    x[k][c] = vmul(gK, vsub(a, am[c]));
                 }
         }
     }
@@ -156,9 +159,9 @@ struct JsdOp {
     static constexpr bool HAS_MAP = (MODE != kBwd), USES_UP = (MODE != kFwd), CHECKS_SIMPLEX = !LOGITS;
     static constexpr int NDICE = DICEF ? K : 0;
     static constexpr bool GMAP = (MODE == kBwd);
-    template <int CM>
-    static __device__ __forceinline__ float apply(float (&x)[K][CM], int, float g, float, bool& bad) {
-        return jsd_pixel<K, CM, LOGITS, MODE != kFwd>(x, div_by_K<K>(g), bad);
+    template <int CM, class T>
+    static __device__ __forceinline__ T apply(T (&x)[K][CM], int, T g, float, bool& bad) {
+        return jsd_pixel<K, CM, LOGITS, MODE != kFwd, T>(x, vmuls(g, 1.0f / (float)K), bad);
     }
 };
 
@@ -205,7 +208,7 @@ __global__ void __launch_bounds__(256, MINB) jsd_kernel(const JsdArgs<K> a) {
                 for (int c = 0; c < C; ++c) x[k][c] = xin[k][c].v[v];
             float gK = gs;
             if constexpr (MODE == kBwd) gK *= gm.v[v];
-            float j = jsd_pixel<K, C, LOGITS, MODE != kFwd>(x, gK, bad);
+            float j = jsd_pixel<K, C, LOGITS, MODE != kFwd, float>(x, gK, bad);
             mapv.v[v] = j;
             part += j;
             if constexpr (MODE != kFwd) {

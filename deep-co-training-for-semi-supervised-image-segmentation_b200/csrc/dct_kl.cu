@@ -4,25 +4,25 @@
 
 namespace dct {
 
-// softmax statistics of one pixel: on return x[c] = x[c] - max, returns {1/Z, log Z}
-template <int CM>
-__device__ __forceinline__ void softmax_stats(float (&x)[CM], float (&e)[CM], int C, float& inv, float& lZ) {
-    float mx = x[0];
+// softmax statistics of one pixel (pair): on return x[c] = x[c] - max, e[c] = exp(x[c] - max); gives {1/Z, log Z}
+template <int CM, class T>
+__device__ __forceinline__ void softmax_stats(T (&x)[CM], T (&e)[CM], int C, T& inv, T& lZ) {
+    T mx = x[0];
 #pragma unroll
     for (int c = 1; c < CM; ++c)
-        if (c < C) mx = fmaxf(mx, x[c]);
-    float Z = 0.0f;
+        if (c < C) mx = vmax(mx, x[c]);
+    T Z = vset<T>(0.0f);
 #pragma unroll
     for (int c = 0; c < CM; ++c)
         if (c < C) {
-            float d = x[c] - mx;
-            float ev = fexp(d);
+            T d = vsub(x[c], mx);
+            T ev = vexp(d);
             x[c] = d;
             e[c] = ev;
-            Z += ev;
+            Z = vadd(Z, ev);
         }
-    inv = fdiv(1.0f, Z);
-    lZ = flog(Z);
+    inv = vdiv(vset<T>(1.0f), Z);
+    lZ = vlog(Z);
 }
 
 // KL_Divergence_2D.forward -- generalframework/loss/loss.py:117-134
@@ -31,19 +31,19 @@ struct KlProbFwd {
     static constexpr int NDICE = 0;
     static constexpr bool GMAP = false;
     static constexpr bool HAS_MAP = true, USES_UP = false, CHECKS_SIMPLEX = true;
-    template <int CM>
-    static __device__ __forceinline__ float apply(float (&x)[2][CM], int C, float, float eps, bool& bad) {
-        float yy = 0.0f, yp = 0.0f, sp = 0.0f, sy = 0.0f;
+    template <int CM, class T>
+    static __device__ __forceinline__ T apply(T (&x)[2][CM], int C, T, float eps, bool& bad) {
+        T yy = vset<T>(0.0f), yp = vset<T>(0.0f), sp = vset<T>(0.0f), sy = vset<T>(0.0f);
 #pragma unroll
         for (int c = 0; c < CM; ++c)
             if (c < C) {
-                float pv = x[0][c], yv = x[1][c];
-                sp += pv; sy += yv;
-                yy = fmaf(yv, flog(yv + eps), yy);
-                yp = fmaf(yv, flog(pv + eps), yp);
+                T pv = x[0][c], yv = x[1][c];
+                sp = vadd(sp, pv); sy = vadd(sy, yv);
+                yy = vfma(yv, vlog(vadds(yv, eps)), yy);
+                yp = vfma(yv, vlog(vadds(pv, eps)), yp);
             }
-        bad |= !simplex_ok(sp) | !simplex_ok(sy);
-        return yy - yp;
+        bad |= vsimplex_bad(sp) | vsimplex_bad(sy);
+        return vsub(yy, yp);
     }
 };
 
@@ -54,16 +54,21 @@ struct KlProbBwd {
     static constexpr int NDICE = 0;
     static constexpr bool GMAP = true;
     static constexpr bool HAS_MAP = false, USES_UP = true, CHECKS_SIMPLEX = false;
-    template <int CM>
-    static __device__ __forceinline__ float apply(float (&x)[2][CM], int C, float g, float eps, bool&) {
+    template <int CM, class T>
+    static __device__ __forceinline__ T apply(T (&x)[2][CM], int C, T g, float eps, bool&) {
+        const T ng = vneg(g);
 #pragma unroll
         for (int c = 0; c < CM; ++c)
             if (c < C) {
-                float pv = x[0][c], yv = x[1][c];
-                x[0][c] = -g * fdiv(yv, pv + eps);
-                if constexpr (WANT_Y) x[1][c] = g * ((flog(yv + eps) + fdiv(yv, yv + eps)) - flog(pv + eps));
+                T pv = x[0][c], yv = x[1][c];
+                T pe = vadds(pv, eps);
+                x[0][c] = vmul(ng, vdiv(yv, pe));
+                if constexpr (WANT_Y) {
+                    T ye = vadds(yv, eps);
+                    x[1][c] = vmul(g, vsub(vadd(vlog(ye), vdiv(yv, ye)), vlog(pe)));
+                }
             }
-        return 0.0f;
+        return vset<T>(0.0f);
     }
 };
 
@@ -76,29 +81,30 @@ struct KlLogit {
     static constexpr int NDICE = 0;
     static constexpr bool GMAP = GRAD;
     static constexpr bool HAS_MAP = true, USES_UP = GRAD, CHECKS_SIMPLEX = false;
-    template <int CM>
-    static __device__ __forceinline__ float apply(float (&x)[2][CM], int C, float g, float, bool&) {
-        float eq[CM], ep[CM];
-        float invq, lZq, invp, lZp;
-        softmax_stats<CM>(x[0], eq, C, invq, lZq);
-        softmax_stats<CM>(x[1], ep, C, invp, lZp);
-        float out = 0.0f;
+    template <int CM, class T>
+    static __device__ __forceinline__ T apply(T (&x)[2][CM], int C, T g, float, bool&) {
+        T eq[CM], ep[CM];
+        T invq, lZq, invp, lZp;
+        softmax_stats<CM, T>(x[0], eq, C, invq, lZq);
+        softmax_stats<CM, T>(x[1], ep, C, invp, lZp);
+        const T dl = vsub(lZp, lZq);
+        T out = vset<T>(0.0f);
 #pragma unroll
         for (int c = 0; c < CM; ++c)
             if (c < C) {
-                float q = eq[c] * invq;
-                float t = (x[0][c] - lZq) - (x[1][c] - lZp);  // log q - log p
+                T q = vmul(eq[c], invq);
+                T t = vadd(vsub(x[0][c], x[1][c]), dl);  // log q - log p = (dq - dp) + (lZp - lZq)
                 eq[c] = q;
                 x[0][c] = t;
-                out = fmaf(q, t, out);
+                out = vfma(q, t, out);
             }
         if constexpr (GRAD) {
 #pragma unroll
             for (int c = 0; c < CM; ++c)
                 if (c < C) {
-                    float q = eq[c];
-                    x[0][c] = g * q * (x[0][c] - out);
-                    x[1][c] = g * (ep[c] * invp - q);
+                    T q = eq[c];
+                    x[0][c] = vmul(vmul(g, q), vsub(x[0][c], out));
+                    x[1][c] = vmul(g, vsub(vmul(ep[c], invp), q));
                 }
         }
         return out;
@@ -112,30 +118,31 @@ struct KlFromLogits {
     static constexpr int NDICE = 0;
     static constexpr bool GMAP = false;
     static constexpr bool HAS_MAP = true, USES_UP = true, CHECKS_SIMPLEX = true;
-    template <int CM>
-    static __device__ __forceinline__ float apply(float (&x)[2][CM], int C, float g, float eps, bool& bad) {
-        float e[CM];
-        float inv, lZ;
-        softmax_stats<CM>(x[0], e, C, inv, lZ);
-        float yy = 0.0f, yp = 0.0f, sy = 0.0f, dot = 0.0f;
+    template <int CM, class T>
+    static __device__ __forceinline__ T apply(T (&x)[2][CM], int C, T g, float eps, bool& bad) {
+        T e[CM];
+        T inv, lZ;
+        softmax_stats<CM, T>(x[0], e, C, inv, lZ);
+        const T ng = vneg(g);
+        T yy = vset<T>(0.0f), yp = vset<T>(0.0f), sy = vset<T>(0.0f), dot = vset<T>(0.0f);
 #pragma unroll
         for (int c = 0; c < CM; ++c)
             if (c < C) {
-                float pv = e[c] * inv, yv = x[1][c];
-                sy += yv;
-                float pe = pv + eps;
-                yy = fmaf(yv, flog(yv + eps), yy);
-                yp = fmaf(yv, flog(pe), yp);
-                float gp = -g * fdiv(yv, pe);
+                T pv = vmul(e[c], inv), yv = x[1][c];
+                sy = vadd(sy, yv);
+                T pe = vadds(pv, eps);
+                yy = vfma(yv, vlog(vadds(yv, eps)), yy);
+                yp = vfma(yv, vlog(pe), yp);
+                T gp = vmul(ng, vdiv(yv, pe));
                 e[c] = pv;
                 x[0][c] = gp;
-                dot = fmaf(pv, gp, dot);
+                dot = vfma(pv, gp, dot);
             }
-        bad |= !simplex_ok(sy);
+        bad |= vsimplex_bad(sy);
 #pragma unroll
         for (int c = 0; c < CM; ++c)
-            if (c < C) x[0][c] = e[c] * (x[0][c] - dot);
-        return yy - yp;
+            if (c < C) x[0][c] = vmul(e[c], vsub(x[0][c], dot));
+        return vsub(yy, yp);
     }
 };
 
@@ -145,17 +152,19 @@ struct KlDivFwd {
     static constexpr int NDICE = 0;
     static constexpr bool GMAP = false;
     static constexpr bool HAS_MAP = true, USES_UP = false, CHECKS_SIMPLEX = true;
-    template <int CM>
-    static __device__ __forceinline__ float apply(float (&x)[2][CM], int C, float, float eps, bool& bad) {
-        float s = 0.0f, sp = 0.0f, sq = 0.0f;
+    template <int CM, class T>
+    static __device__ __forceinline__ T apply(T (&x)[2][CM], int C, T, float eps, bool& bad) {
+        T s = vset<T>(0.0f), sp = vset<T>(0.0f), sq = vset<T>(0.0f);
 #pragma unroll
         for (int c = 0; c < CM; ++c)
             if (c < C) {
-                float pv = x[0][c], qv = x[1][c];
-                sp += pv; sq += qv;
-                s = fmaf(-pv, logf(qv / pv + eps), s);  // IEEE divide: 0/0 -> NaN exactly like the reference
+                T pv = x[0][c], qv = x[1][c];
+                sp = vadd(sp, pv); sq = vadd(sq, qv);
+                // IEEE divide and libdevice logf: 0/0 -> NaN exactly like the reference
+                T l = vmap([eps](float q, float p) { return logf(q / p + eps); }, qv, pv);
+                s = vfma(vneg(pv), l, s);
             }
-        bad |= !simplex_ok(sp) | !simplex_ok(sq);
+        bad |= vsimplex_bad(sp) | vsimplex_bad(sq);
         return s;
     }
 };
@@ -166,18 +175,18 @@ struct EntropyFwd {
     static constexpr int NDICE = 0;
     static constexpr bool GMAP = false;
     static constexpr bool HAS_MAP = true, USES_UP = false, CHECKS_SIMPLEX = true;
-    template <int CM>
-    static __device__ __forceinline__ float apply(float (&x)[1][CM], int C, float, float, bool& bad) {
-        float h = 0.0f, s = 0.0f;
+    template <int CM, class T>
+    static __device__ __forceinline__ T apply(T (&x)[1][CM], int C, T, float, bool& bad) {
+        T h = vset<T>(0.0f), s = vset<T>(0.0f);
 #pragma unroll
         for (int c = 0; c < CM; ++c)
             if (c < C) {
-                float pv = x[0][c];
-                s += pv;
-                h = fmaf(pv, flog(pv + kEntEps), h);
+                T pv = x[0][c];
+                s = vadd(s, pv);
+                h = vfma(pv, vlog(vadds(pv, kEntEps)), h);
             }
-        bad |= !simplex_ok(s);
-        return -h;
+        bad |= vsimplex_bad(s);
+        return vneg(h);
     }
 };
 struct EntropyBwd {
@@ -185,15 +194,17 @@ struct EntropyBwd {
     static constexpr int NDICE = 0;
     static constexpr bool GMAP = true;
     static constexpr bool HAS_MAP = false, USES_UP = true, CHECKS_SIMPLEX = false;
-    template <int CM>
-    static __device__ __forceinline__ float apply(float (&x)[1][CM], int C, float g, float, bool&) {
+    template <int CM, class T>
+    static __device__ __forceinline__ T apply(T (&x)[1][CM], int C, T g, float, bool&) {
+        const T ng = vneg(g);
 #pragma unroll
         for (int c = 0; c < CM; ++c)
             if (c < C) {
-                float pv = x[0][c];
-                x[0][c] = -g * (flog(pv + kEntEps) + fdiv(pv, pv + kEntEps));
+                T pv = x[0][c];
+                T pe = vadds(pv, kEntEps);
+                x[0][c] = vmul(ng, vadd(vlog(pe), vdiv(pv, pe)));
             }
-        return 0.0f;
+        return vset<T>(0.0f);
     }
 };
 
@@ -203,20 +214,23 @@ struct SoftmaxFwd {
     static constexpr int NDICE = 0;
     static constexpr bool GMAP = false;
     static constexpr bool HAS_MAP = false, USES_UP = false, CHECKS_SIMPLEX = false;
-    template <int CM>
-    static __device__ __forceinline__ float apply(float (&x)[1][CM], int C, float, float, bool&) {
-        float mx = x[0][0];
+    template <int CM, class T>
+    static __device__ __forceinline__ T apply(T (&x)[1][CM], int C, T, float, bool&) {
+        T mx = x[0][0];
 #pragma unroll
         for (int c = 1; c < CM; ++c)
-            if (c < C) mx = fmaxf(mx, x[0][c]);
-        float Z = 0.0f;
+            if (c < C) mx = vmax(mx, x[0][c]);
+        T Z = vset<T>(0.0f);
 #pragma unroll
         for (int c = 0; c < CM; ++c)
-            if (c < C) { x[0][c] = expf(x[0][c] - mx); Z += x[0][c]; }
+            if (c < C) {
+                x[0][c] = vmap([](float a, float m) { return expf(a - m); }, x[0][c], mx);
+                Z = vadd(Z, x[0][c]);
+            }
 #pragma unroll
         for (int c = 0; c < CM; ++c)
-            if (c < C) x[0][c] = x[0][c] / Z;
-        return 0.0f;
+            if (c < C) x[0][c] = vmap([](float a, float z) { return a / z; }, x[0][c], Z);
+        return vset<T>(0.0f);
     }
 };
 struct SoftmaxBwd {  // in[0] = p, in[1] = gp ; out[0] = gx
@@ -224,16 +238,16 @@ struct SoftmaxBwd {  // in[0] = p, in[1] = gp ; out[0] = gx
     static constexpr int NDICE = 0;
     static constexpr bool GMAP = false;
     static constexpr bool HAS_MAP = false, USES_UP = false, CHECKS_SIMPLEX = false;
-    template <int CM>
-    static __device__ __forceinline__ float apply(float (&x)[2][CM], int C, float, float, bool&) {
-        float dot = 0.0f;
+    template <int CM, class T>
+    static __device__ __forceinline__ T apply(T (&x)[2][CM], int C, T, float, bool&) {
+        T dot = vset<T>(0.0f);
 #pragma unroll
         for (int c = 0; c < CM; ++c)
-            if (c < C) dot = fmaf(x[0][c], x[1][c], dot);
+            if (c < C) dot = vfma(x[0][c], x[1][c], dot);
 #pragma unroll
         for (int c = 0; c < CM; ++c)
-            if (c < C) x[0][c] = x[0][c] * (x[1][c] - dot);
-        return 0.0f;
+            if (c < C) x[0][c] = vmul(x[0][c], vsub(x[1][c], dot));
+        return vset<T>(0.0f);
     }
 };
 

@@ -242,8 +242,8 @@ __global__ void dice_from_counts_kernel(const int64_t* counts, int64_t B, int C,
 struct DiceOp {
     static constexpr int NIN = 1, NOUT = 0, NDICE = 1;
     static constexpr bool HAS_MAP = false, USES_UP = false, CHECKS_SIMPLEX = false, GMAP = false;
-    template <int CM>
-    static __device__ __forceinline__ float apply(float (&)[1][CM], int, float, float, bool&) { return 0.0f; }
+    template <int CM, class T>
+    static __device__ __forceinline__ T apply(T (&)[1][CM], int, T, float, bool&) { return vset<T>(0.0f); }
 };
 
 template <int CT>

@@ -31,7 +31,7 @@ constexpr int pix_vec() {
 // Op interface:
 //   static constexpr int NIN, NOUT (NOUT <= NIN: outputs reuse the input registers);
 //   static constexpr bool HAS_MAP  (produces a per-pixel scalar), USES_UP (consumes an upstream);
-//   template <int CM> static float apply(float (&x)[NIN][CM], int C, float g, float eps, bool& bad)
+//   template <int CM, class T> static T apply(T (&x)[NIN][CM], int C, T g, float eps, bool& bad)   (T = float | f2)
 //       in: x = inputs; out: x[0..NOUT) = outputs; returns the map value.
 template <class Op, int CT, int VEC>
 __global__ void __launch_bounds__(256) pix_kernel(const PixArgs a) {
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) pix_kernel(const PixArgs a) {
 #pragma unroll
                 for (int c = 0; c < CM; ++c)
                     if (c < C) x[n][c] = xin[n][c].v[v];
-            float mv = Op::template apply<CM>(x, C, gs * gm.v[v], a.eps, bad);
+            float mv = Op::template apply<CM, float>(x, C, gs * gm.v[v], a.eps, bad);
             mapv.v[v] = mv;
             part += mv;
 #pragma unroll

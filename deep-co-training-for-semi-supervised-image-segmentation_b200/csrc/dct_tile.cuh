@@ -52,37 +52,50 @@ constexpr int tile_row_words() {
     return Op::NIN * CT + (Op::NDICE > 0 ? 2 : 0) + (Op::GMAP ? 1 : 0);
 }
 
-template <int WORDS, int PPT, int THREADS, int MINB>
+template <int WORDS, int PPT, int CTHREADS, int MINB>
 constexpr int tile_stages() {
     // as many stages as fit in this CTA's share of shared memory, between 2 and 8
-    constexpr size_t stage = (size_t)WORDS * PPT * THREADS * 4;
-    // 228 KB per SM, 1 KB reserved per CTA, ~0.7 KB of static shared memory + barriers in the kernel
-    constexpr size_t n = (233472 / MINB - 1024 - 672) / stage;
+    constexpr size_t stage = (size_t)WORDS * PPT * CTHREADS * 4;
+    // 228 KB per SM, 1 KB reserved per CTA, < 1 KB of static shared memory + barriers + alignment slack
+    constexpr size_t n = (233472 / MINB - 2048) / stage;
     return n < 2 ? 2 : (n > 8 ? 8 : (int)n);
 }
 
-template <class Op, int CT, int PPT, int THREADS, int STAGES>
+template <class Op, int CT, int PPT, int CTHREADS, int STAGES>
 struct TileCfg {
-    static constexpr int TP = THREADS * PPT;
+    static constexpr int TP = CTHREADS * PPT;                       // pixels per tile
     static constexpr int ROWS = Op::NIN * CT;                       // float data rows
     static constexpr int WORDS = tile_row_words<Op, CT>();          // 4-byte words per pixel incl. side rows
     static constexpr size_t kStageBytes = (size_t)WORDS * TP * 4;
     static constexpr int kLabelOff = ROWS * TP;                     // in floats; labels are 8-byte, TP*8 bytes
     static constexpr int kGmapOff = (ROWS + (Op::NDICE > 0 ? 2 : 0)) * TP;  // valid when Op::GMAP
-    static constexpr size_t kSmemBytes = kStageBytes * STAGES + 8 * STAGES + 128;
+    static constexpr size_t kSmemBytes = kStageBytes * STAGES + 16 * STAGES + 128;
 };
 
-template <class Op, int CT, int PPT, int THREADS, int STAGES, int MINB = 1>
-__global__ void __launch_bounds__(THREADS, MINB) tile_kernel(const TileArgs a) {
-    using Cfg = TileCfg<Op, CT, PPT, THREADS, STAGES>;
+// Warp-specialised persistent kernel: NCW consumer warps + 1 producer warp per CTA.
+//   producer (one elected lane): issues every bulk load / store; recycles a stage when its `done`
+//       mbarrier (NCW arrivals) has completed and, for ops with outputs, when the bulk store group
+//       that drains it has finished reading shared memory;
+//   consumers: wait on the stage's `full` mbarrier (transaction bytes), compute in registers, write
+//       results back in place, fence to the async proxy, arrive on `done`.  No CTA-wide barrier in
+//       the tile loop: a fast warp runs ahead by up to STAGES-1 tiles.
+template <class Op, int CT, int PPT, int NCW, int STAGES, int MINB = 1>
+__global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArgs a) {
+    constexpr int CTHREADS = NCW * 32;
+    using Cfg = TileCfg<Op, CT, PPT, CTHREADS, STAGES>;
     constexpr int TP = Cfg::TP, ROWS = Cfg::ROWS, WORDS = Cfg::WORDS, NIN = Op::NIN, NOUT = Op::NOUT, C = CT;
     constexpr bool DICE = Op::NDICE > 0;
+    constexpr int LW = (PPT % 2 == 0) ? 2 : 1;   // pixels per math lane group: pairs use packed FP32x2
+    constexpr int NG = PPT / LW;
+    using T = typename std::conditional<LW == 2, f2, float>::type;
     static_assert(!DICE || CT <= 4, "fused Dice counters are packed 8-bit fields: C <= 4");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stages = reinterpret_cast<float*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + Cfg::kStageBytes * STAGES);
+    uint64_t* done = full + STAGES;
     __shared__ int s_cnt[DICE ? Op::NDICE * CT * 3 : 1];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const bool is_producer = tid >= CTHREADS;
     const int64_t HW = a.HW;
     const int tpi = a.tiles_per_image;
     const bool do_dice = DICE && a.labels != nullptr;
@@ -91,208 +104,247 @@ __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(const TileArgs a) {
     // contiguous tile range of this CTA
     const int per = a.num_tiles / gridDim.x, extra = a.num_tiles % gridDim.x;
     const int t_begin = blockIdx.x * per + min((int)blockIdx.x, extra);
-    const int t_end = t_begin + per + ((int)blockIdx.x < extra ? 1 : 0);
+    const int n_tiles = per + ((int)blockIdx.x < extra ? 1 : 0);
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) tma::mbar_init(&full[s], 1);
+        for (int s = 0; s < STAGES; ++s) {
+            tma::mbar_init(&full[s], 1);
+            tma::mbar_init(&done[s], NCW);
+        }
         tma::fence_barrier_init();
     }
     if constexpr (DICE) {
-        for (int j = tid; j < Op::NDICE * CT * 3; j += THREADS) s_cnt[j] = 0;
+        for (int j = tid; j < Op::NDICE * CT * 3; j += blockDim.x) s_cnt[j] = 0;
     }
+    pdl_launch_dependents();  // the next kernel may start its own prologue; it waits for our completion below
     __syncthreads();
+    pdl_wait();               // the previous grid has completed and its writes are visible (no-op without PDL)
 
-    auto issue_load = [&](int tile, int stage) {  // thread 0 only
-        const int b = tile / tpi;
-        const int64_t off = (int64_t)(tile - b * tpi) * TP;
-        const int64_t rem = HW - off;
-        const uint32_t bytes = (uint32_t)((rem < TP ? rem : TP) * 4);
-        float* dst = stages + (size_t)stage * WORDS * TP;
-        uint32_t total = bytes * ROWS;
-        if constexpr (DICE) total += do_dice ? 2u * bytes : 0u;
-        if constexpr (Op::GMAP) total += has_gmap ? bytes : 0u;
-        tma::mbar_expect_tx(&full[stage], total);
-#pragma unroll
-        for (int n = 0; n < NIN; ++n)
-#pragma unroll
-            for (int c = 0; c < C; ++c)
-                tma::bulk_load(dst + (n * C + c) * TP, a.in[n] + ((int64_t)b * C + c) * HW + off, bytes, &full[stage]);
-        if constexpr (DICE) {
-            if (do_dice) tma::bulk_load(dst + Cfg::kLabelOff, a.labels + (int64_t)b * HW + off, 2u * bytes, &full[stage]);
-        }
-        if constexpr (Op::GMAP) {
-            if (has_gmap) tma::bulk_load(dst + Cfg::kGmapOff, a.up.gmap + (int64_t)b * HW + off, bytes, &full[stage]);
-        }
-    };
-
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < STAGES - 1; ++s)
-            if (t_begin + s < t_end) issue_load(t_begin + s, s);
-    }
-
-    float gs = 1.0f;
-    if constexpr (Op::USES_UP) gs = upstream_scalar(a.up);
     double acc = 0.0;
     bool bad = false;
-    int nbad_label = 0;
-    unsigned int pk[DICE ? Op::NDICE : 1][2];  // packed 8-bit per-class counters: [view][I,P]
-    unsigned int pkG = 0u;                     // |gt == c| is the same for every view
-    if constexpr (DICE) {
-#pragma unroll
-        for (int n = 0; n < Op::NDICE; ++n) pk[n][0] = pk[n][1] = 0u;
-    }
-    int cur_b = -1, since_flush = 0;
 
-    // flush this thread's packed counters into the CTA's shared counters, then (all threads) to global
-    auto flush_counts = [&](int b) {
-        if constexpr (DICE) {
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                int g = (int)((pkG >> (8 * c)) & 0xffu);
-                g = __reduce_add_sync(0xffffffffu, g);
-#pragma unroll
-                for (int n = 0; n < Op::NDICE; ++n) {
-                    int vi = (int)((pk[n][0] >> (8 * c)) & 0xffu);
-                    int vp = (int)((pk[n][1] >> (8 * c)) & 0xffu);
-                    vi = __reduce_add_sync(0xffffffffu, vi);
-                    vp = __reduce_add_sync(0xffffffffu, vp);
-                    if ((tid & 31) == 0) {
-                        if (vi) atomicAdd(&s_cnt[(n * C + c) * 3 + 0], vi);
-                        if (g) atomicAdd(&s_cnt[(n * C + c) * 3 + 1], g);
-                        if (vp) atomicAdd(&s_cnt[(n * C + c) * 3 + 2], vp);
-                    }
-                }
-            }
-            pkG = 0u;
-#pragma unroll
-            for (int n = 0; n < Op::NDICE; ++n) pk[n][0] = pk[n][1] = 0u;
-            __syncthreads();
-            for (int j = tid; j < Op::NDICE * C * 3; j += THREADS) {
-                const int v = s_cnt[j];
-                if (v) {
-                    const int n = j / (C * 3), r = j - n * C * 3;
-                    atomicAdd(&a.counts[(int64_t)n * a.count_view_stride + (int64_t)b * C * 3 + r], (unsigned long long)v);
-                    s_cnt[j] = 0;
-                }
-            }
-            __syncthreads();
-        }
-    };
-
-    int it = 0;
-    for (int tile = t_begin; tile < t_end; ++tile, ++it) {
-        const int stage = it % STAGES;
-        const uint32_t parity = (uint32_t)(it / STAGES) & 1u;
-        const int b = tile / tpi;
-        const int64_t off = (int64_t)(tile - b * tpi) * TP;
-        const int64_t rem = HW - off;
-        const int len = (int)(rem < TP ? rem : TP);
-        float* st = stages + (size_t)stage * WORDS * TP;
-        const int p0 = tid * PPT;
-        const bool active = p0 < len;
-        if constexpr (DICE) {
-            if (do_dice && (b != cur_b || since_flush > 255 - PPT)) {  // uniform across the CTA
-                if (cur_b >= 0) flush_counts(cur_b);
-                cur_b = b;
-                since_flush = 0;
-            }
-        }
-        tma::mbar_wait(&full[stage], parity);
-        if (active) {
-            FVec<PPT> gm;
-#pragma unroll
-            for (int v = 0; v < PPT; ++v) gm.v[v] = 1.0f;
-            if constexpr (Op::GMAP) {
-                if (has_gmap) gm = *reinterpret_cast<const FVec<PPT>*>(st + Cfg::kGmapOff + p0);
-            }
-            uint2 lab[PPT];  // int64 labels as (lo, hi) words
-            if constexpr (DICE) {
-                if (do_dice) {
-#pragma unroll
-                    for (int v = 0; v < PPT; ++v) lab[v] = reinterpret_cast<const uint2*>(st + Cfg::kLabelOff)[p0 + v];
-                }
-            }
-            FVec<PPT> xin[NIN][C];
-#pragma unroll
-            for (int n = 0; n < NIN; ++n)
-#pragma unroll
-                for (int c = 0; c < C; ++c) xin[n][c] = *reinterpret_cast<const FVec<PPT>*>(st + (n * C + c) * TP + p0);
-            FVec<PPT> mapv;
-            float part = 0.0f;
-#pragma unroll
-            for (int v = 0; v < PPT; ++v) {
-                float x[NIN][C];
+    if (is_producer) {
+        if (lane == 0) {
+            auto issue_load = [&](int i) {  // i-th tile of this CTA into stage i % STAGES
+                const int tile = t_begin + i, stage = i % STAGES;
+                const int b = tile / tpi;
+                const int64_t off = (int64_t)(tile - b * tpi) * TP;
+                const int64_t rem = HW - off;
+                const uint32_t bytes = (uint32_t)((rem < TP ? rem : TP) * 4);
+                float* dst = stages + (size_t)stage * WORDS * TP;
+                uint32_t total = bytes * ROWS;
+                if constexpr (DICE) total += do_dice ? 2u * bytes : 0u;
+                if constexpr (Op::GMAP) total += has_gmap ? bytes : 0u;
+                tma::mbar_expect_tx(&full[stage], total);
 #pragma unroll
                 for (int n = 0; n < NIN; ++n)
 #pragma unroll
-                    for (int c = 0; c < C; ++c) x[n][c] = xin[n][c].v[v];
+                    for (int c = 0; c < C; ++c)
+                        tma::bulk_load(dst + (n * C + c) * TP, a.in[n] + ((int64_t)b * C + c) * HW + off, bytes, &full[stage]);
                 if constexpr (DICE) {
-                    if (do_dice) {
-                        const unsigned int gl = lab[v].x;
-                        const bool valid = (lab[v].y == 0u) & (gl < (unsigned int)C);  // 0 <= int64 label < C
-                        nbad_label += !valid;
-                        const unsigned int gmask = valid ? (1u << (8u * (gl & 3u))) : 0u;  // one-hot byte of the label
-                        pkG += gmask;
+                    if (do_dice) tma::bulk_load(dst + Cfg::kLabelOff, a.labels + (int64_t)b * HW + off, 2u * bytes, &full[stage]);
+                }
+                if constexpr (Op::GMAP) {
+                    if (has_gmap) tma::bulk_load(dst + Cfg::kGmapOff, a.up.gmap + (int64_t)b * HW + off, bytes, &full[stage]);
+                }
+            };
+            for (int i = 0; i < STAGES && i < n_tiles; ++i) issue_load(i);
+            for (int i = 0; i < n_tiles; ++i) {
+                const int stage = i % STAGES;
+                tma::mbar_wait(&done[stage], (uint32_t)(i / STAGES) & 1u);  // every consumer warp is through with tile i
+                if constexpr (NOUT > 0) {
+                    const int tile = t_begin + i;
+                    const int b = tile / tpi;
+                    const int64_t off = (int64_t)(tile - b * tpi) * TP;
+                    const int64_t rem = HW - off;
+                    const uint32_t bytes = (uint32_t)((rem < TP ? rem : TP) * 4);
+                    const float* st = stages + (size_t)stage * WORDS * TP;
 #pragma unroll
-                        for (int n = 0; n < Op::NDICE; ++n) {
-                            const unsigned int hot = spec_softmax_argmax_onehot4<C>(x[n]);  // one-hot byte of the prediction
-                            pk[n][1] += hot;
-                            pk[n][0] += hot & gmask;
+                    for (int n = 0; n < NOUT; ++n)
+                        if (a.out[n] != nullptr) {
+#pragma unroll
+                            for (int c = 0; c < C; ++c)
+                                tma::bulk_store(a.out[n] + ((int64_t)b * C + c) * HW + off, st + (n * C + c) * TP, bytes);
+                        }
+                    tma::bulk_commit();
+                    // tile i-1's store group has drained its stage once at most one group is still reading
+                    if (i >= 1 && i - 1 + STAGES < n_tiles) {
+                        tma::bulk_wait_read<1>();
+                        issue_load(i - 1 + STAGES);
+                    }
+                } else {
+                    if (i + STAGES < n_tiles) issue_load(i + STAGES);
+                }
+            }
+            if constexpr (NOUT > 0) tma::bulk_wait_all<0>();
+        }
+        __syncwarp();
+    } else {
+        float gs = 1.0f;
+        if constexpr (Op::USES_UP) gs = upstream_scalar(a.up);
+        int nbad_label = 0;
+        unsigned int pk[DICE ? Op::NDICE : 1][2];  // packed 8-bit per-class counters: [view][I,P]
+        unsigned int pkG = 0u;                     // |gt == c| is the same for every view
+        if constexpr (DICE) {
+#pragma unroll
+            for (int n = 0; n < Op::NDICE; ++n) pk[n][0] = pk[n][1] = 0u;
+        }
+        int cur_b = -1, since_flush = 0;
+        auto consumer_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(CTHREADS) : "memory"); };
+
+        // flush this thread's packed counters into the CTA's shared counters, then (all consumers) to global
+        auto flush_counts = [&](int b) {
+            if constexpr (DICE) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    int g = (int)((pkG >> (8 * c)) & 0xffu);
+                    g = __reduce_add_sync(0xffffffffu, g);
+#pragma unroll
+                    for (int n = 0; n < Op::NDICE; ++n) {
+                        int vi = (int)((pk[n][0] >> (8 * c)) & 0xffu);
+                        int vp = (int)((pk[n][1] >> (8 * c)) & 0xffu);
+                        vi = __reduce_add_sync(0xffffffffu, vi);
+                        vp = __reduce_add_sync(0xffffffffu, vp);
+                        if (lane == 0) {
+                            if (vi) atomicAdd(&s_cnt[(n * C + c) * 3 + 0], vi);
+                            if (g) atomicAdd(&s_cnt[(n * C + c) * 3 + 1], g);
+                            if (vp) atomicAdd(&s_cnt[(n * C + c) * 3 + 2], vp);
                         }
                     }
                 }
-                const float mv = Op::template apply<C>(x, C, gs * gm.v[v], a.eps, bad);
-                mapv.v[v] = mv;
-                part += mv;
+                pkG = 0u;
 #pragma unroll
-                for (int n = 0; n < NOUT; ++n)
-#pragma unroll
-                    for (int c = 0; c < C; ++c) xin[n][c].v[v] = x[n][c];
-            }
-            acc += (double)part;
-            if constexpr (Op::HAS_MAP) {
-                if (a.map != nullptr) st_stream<PPT>(a.map + (int64_t)b * HW + off + p0, mapv);
-            }
-#pragma unroll
-            for (int n = 0; n < NOUT; ++n)
-                if (a.out[n] != nullptr) {
-#pragma unroll
-                    for (int c = 0; c < C; ++c) *reinterpret_cast<FVec<PPT>*>(st + (n * C + c) * TP + p0) = xin[n][c];
+                for (int n = 0; n < Op::NDICE; ++n) pk[n][0] = pk[n][1] = 0u;
+                consumer_sync();
+                for (int j = tid; j < Op::NDICE * C * 3; j += CTHREADS) {
+                    const int v = s_cnt[j];
+                    if (v) {
+                        const int n = j / (C * 3), r = j - n * C * 3;
+                        atomicAdd(&a.counts[(int64_t)n * a.count_view_stride + (int64_t)b * C * 3 + r], (unsigned long long)v);
+                        s_cnt[j] = 0;
+                    }
                 }
-        }
-        since_flush += PPT;
-        if constexpr (NOUT > 0) tma::fence_proxy_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-            if constexpr (NOUT > 0) {
-                const uint32_t bytes = (uint32_t)len * 4u;
+                consumer_sync();
+            }
+        };
+
+        for (int i = 0; i < n_tiles; ++i) {
+            const int tile = t_begin + i;
+            const int stage = i % STAGES;
+            const int b = tile / tpi;
+            const int64_t off = (int64_t)(tile - b * tpi) * TP;
+            const int64_t rem = HW - off;
+            const int len = (int)(rem < TP ? rem : TP);
+            float* st = stages + (size_t)stage * WORDS * TP;
+            const int p0 = tid * PPT;
+            const bool active = p0 < len;
+            if constexpr (DICE) {
+                if (do_dice && (b != cur_b || since_flush > 255 - PPT)) {  // uniform across the consumers
+                    if (cur_b >= 0) flush_counts(cur_b);
+                    cur_b = b;
+                    since_flush = 0;
+                }
+            }
+            tma::mbar_wait(&full[stage], (uint32_t)(i / STAGES) & 1u);
+            if (active) {
+                FVec<PPT> gm;
+#pragma unroll
+                for (int v = 0; v < PPT; ++v) gm.v[v] = 1.0f;
+                if constexpr (Op::GMAP) {
+                    if (has_gmap) gm = *reinterpret_cast<const FVec<PPT>*>(st + Cfg::kGmapOff + p0);
+                }
+                uint2 lab[PPT];  // int64 labels as (lo, hi) words
+                if constexpr (DICE) {
+                    if (do_dice) {
+                        if constexpr (PPT % 2 == 0) {
+#pragma unroll
+                            for (int v = 0; v < PPT / 2; ++v) {  // two labels per 128-bit shared load
+                                const uint4 q = reinterpret_cast<const uint4*>(st + Cfg::kLabelOff)[(p0 >> 1) + v];
+                                lab[2 * v] = make_uint2(q.x, q.y);
+                                lab[2 * v + 1] = make_uint2(q.z, q.w);
+                            }
+                        } else {
+#pragma unroll
+                            for (int v = 0; v < PPT; ++v) lab[v] = reinterpret_cast<const uint2*>(st + Cfg::kLabelOff)[p0 + v];
+                        }
+                    }
+                }
+                FVec<PPT> xin[NIN][C];
+#pragma unroll
+                for (int n = 0; n < NIN; ++n)
+#pragma unroll
+                    for (int c = 0; c < C; ++c) xin[n][c] = *reinterpret_cast<const FVec<PPT>*>(st + (n * C + c) * TP + p0);
+                FVec<PPT> mapv;
+                float part = 0.0f;
+#pragma unroll
+                for (int gi = 0; gi < NG; ++gi) {
+                    T x[NIN][C];
+#pragma unroll
+                    for (int n = 0; n < NIN; ++n)
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            if constexpr (LW == 2) x[n][c] = mk2(xin[n][c].v[2 * gi], xin[n][c].v[2 * gi + 1]);
+                            else x[n][c] = xin[n][c].v[gi];
+                        }
+                    if constexpr (DICE) {
+                        if (do_dice) {
+#pragma unroll
+                            for (int j = 0; j < LW; ++j) {
+                                const uint2 lb = lab[gi * LW + j];
+                                const bool valid = (lb.y == 0u) & (lb.x < (unsigned int)C);  // 0 <= int64 label < C
+                                nbad_label += !valid;
+                                const unsigned int gmask = valid ? (1u << (8u * (lb.x & 3u))) : 0u;  // one-hot byte of the label
+                                pkG += gmask;
+#pragma unroll
+                                for (int n = 0; n < Op::NDICE; ++n) {
+                                    float xs[C];
+#pragma unroll
+                                    for (int c = 0; c < C; ++c) xs[c] = vget(x[n][c], j);
+                                    const unsigned int hot = spec_softmax_argmax_onehot4<C>(xs);  // one-hot byte of the prediction
+                                    pk[n][1] += hot;
+                                    pk[n][0] += hot & gmask;
+                                }
+                            }
+                        }
+                    }
+                    T gv;
+                    if constexpr (LW == 2) gv = mk2(gs * gm.v[2 * gi], gs * gm.v[2 * gi + 1]);
+                    else gv = gs * gm.v[gi];
+                    const T mv = Op::template apply<C, T>(x, C, gv, a.eps, bad);
+                    if constexpr (LW == 2) { mapv.v[2 * gi] = vget(mv, 0); mapv.v[2 * gi + 1] = vget(mv, 1); }
+                    else mapv.v[gi] = vget(mv, 0);
+                    part += vhsum(mv);
+#pragma unroll
+                    for (int n = 0; n < NOUT; ++n)
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            if constexpr (LW == 2) { xin[n][c].v[2 * gi] = vget(x[n][c], 0); xin[n][c].v[2 * gi + 1] = vget(x[n][c], 1); }
+                            else xin[n][c].v[gi] = vget(x[n][c], 0);
+                        }
+                }
+                acc += (double)part;
+                if constexpr (Op::HAS_MAP) {
+                    if (a.map != nullptr) st_stream<PPT>(a.map + (int64_t)b * HW + off + p0, mapv);
+                }
 #pragma unroll
                 for (int n = 0; n < NOUT; ++n)
                     if (a.out[n] != nullptr) {
 #pragma unroll
-                        for (int c = 0; c < C; ++c)
-                            tma::bulk_store(a.out[n] + ((int64_t)b * C + c) * HW + off, st + (n * C + c) * TP, bytes);
+                        for (int c = 0; c < C; ++c) *reinterpret_cast<FVec<PPT>*>(st + (n * C + c) * TP + p0) = xin[n][c];
                     }
-                tma::bulk_commit();
             }
-            const int next = tile + (STAGES - 1);
-            if (next < t_end) {
-                // the stage being refilled was drained by the store group committed one iteration ago
-                if constexpr (NOUT > 0) tma::bulk_wait_read<1>();
-                issue_load(next, (it + STAGES - 1) % STAGES);
-            }
+            since_flush += PPT;
+            if constexpr (NOUT > 0) tma::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) tma::mbar_arrive(&done[stage]);
         }
-    }
-    if constexpr (NOUT > 0) {
-        if (tid == 0) tma::bulk_wait_all<0>();
-    }
-    if constexpr (DICE) {
-        if (do_dice) {
-            if (cur_b >= 0) flush_counts(cur_b);
-            nbad_label = __reduce_add_sync(0xffffffffu, nbad_label);
-            if ((tid & 31) == 0 && nbad_label != 0 && a.flags != nullptr) atomicAdd(&a.flags[DCT_FLAG_LABEL], nbad_label);
+        if constexpr (DICE) {
+            if (do_dice) {
+                if (cur_b >= 0) flush_counts(cur_b);
+                nbad_label = __reduce_add_sync(0xffffffffu, nbad_label);
+                if (lane == 0 && nbad_label != 0 && a.flags != nullptr) atomicAdd(&a.flags[DCT_FLAG_LABEL], nbad_label);
+            }
         }
     }
     if constexpr (Op::CHECKS_SIMPLEX) {
@@ -321,13 +373,12 @@ template <class Op, int CT>
 int tile_launch_ct(TileArgs a, int64_t B, cudaStream_t stream) {
     constexpr int ROWS = Op::NIN * CT;
     static_assert(ROWS <= 16, "tile pipeline instantiations are for NIN*C <= 16 (larger: register-tiled kernels)");
-    // measured on B200 (tools/kbench_tile.cu): two 256-thread CTAs per SM beat one larger CTA for every op
-    // (the per-tile CTA barrier of one overlaps the math of the other); math-heavy ops take 2 pixels/thread.
-    constexpr int THREADS = 256, MINB = 2;
+    // measured on B200 (tools/kbench_tile.cu): two CTAs of 8 consumer warps per SM; math-heavy ops take 2 pixels/thread
+    constexpr int NCW = 8, MINB = 2;
     constexpr int PPT = ROWS > 8 ? 2 : 4;
-    constexpr int STAGES = tile_stages<tile_row_words<Op, CT>(), PPT, THREADS, MINB>();
-    using Cfg = TileCfg<Op, CT, PPT, THREADS, STAGES>;
-    auto kern = tile_kernel<Op, CT, PPT, THREADS, STAGES, MINB>;
+    constexpr int STAGES = tile_stages<tile_row_words<Op, CT>(), PPT, NCW * 32, MINB>();
+    using Cfg = TileCfg<Op, CT, PPT, NCW * 32, STAGES>;
+    auto kern = tile_kernel<Op, CT, PPT, NCW, STAGES, MINB>;
     static bool configured[64] = {};  // per instantiation and device (the attribute is per device function)
     int devid = 0;
     cudaGetDevice(&devid);
@@ -340,7 +391,8 @@ int tile_launch_ct(TileArgs a, int64_t B, cudaStream_t stream) {
     a.num_tiles = (int)(a.tiles_per_image * B);
     int grid = kSMs * MINB;
     if (grid > a.num_tiles) grid = a.num_tiles;
-    kern<<<grid, THREADS, Cfg::kSmemBytes, stream>>>(a);
+    cudaError_t e = launch_pdl(kern, dim3(grid), dim3(NCW * 32 + 32), Cfg::kSmemBytes, stream, a);
+    if (e != cudaSuccess) { g_last_cuda_error = e; return DCT_ERR_CUDA; }
     return check_launch();
 }
 

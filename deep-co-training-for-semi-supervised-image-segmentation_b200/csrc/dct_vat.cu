@@ -77,6 +77,8 @@ l2_cluster_kernel(const L2Args a) {
     const int64_t nvec = a.M / 4;
     FVec<4> v[NV];
     float ss = 0.0f;
+    pdl_launch_dependents();
+    pdl_wait();
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
         const int64_t q = ((int64_t)j * kL2Cluster + rank) * kL2Threads + threadIdx.x;  // float4 index in sample
@@ -203,11 +205,13 @@ extern "C" int dct_l2_normalize_f32(const float* d, float* out, int64_t B, int64
     const int64_t nv = (M + per_wave - 1) / per_wave;
     if (vec_ok && nv <= kL2MaxVecPerThread && B * kL2Cluster <= 0x7fffffff) {
         dim3 grid((unsigned)(B * kL2Cluster));
-        if (nv <= 1) l2_cluster_kernel<1><<<grid, kL2Threads, 0, s>>>(a);
-        else if (nv <= 2) l2_cluster_kernel<2><<<grid, kL2Threads, 0, s>>>(a);
-        else if (nv <= 4) l2_cluster_kernel<4><<<grid, kL2Threads, 0, s>>>(a);
-        else if (nv <= 8) l2_cluster_kernel<8><<<grid, kL2Threads, 0, s>>>(a);
-        else l2_cluster_kernel<16><<<grid, kL2Threads, 0, s>>>(a);
+        cudaError_t e;
+        if (nv <= 1) e = launch_pdl(l2_cluster_kernel<1>, grid, dim3(kL2Threads), 0, s, a);
+        else if (nv <= 2) e = launch_pdl(l2_cluster_kernel<2>, grid, dim3(kL2Threads), 0, s, a);
+        else if (nv <= 4) e = launch_pdl(l2_cluster_kernel<4>, grid, dim3(kL2Threads), 0, s, a);
+        else if (nv <= 8) e = launch_pdl(l2_cluster_kernel<8>, grid, dim3(kL2Threads), 0, s, a);
+        else e = launch_pdl(l2_cluster_kernel<16>, grid, dim3(kL2Threads), 0, s, a);
+        if (e != cudaSuccess) { g_last_cuda_error = e; return DCT_ERR_CUDA; }
         return check_launch();
     }
     if (workspace == nullptr) return DCT_ERR_BAD_ARG;

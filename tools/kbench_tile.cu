@@ -11,6 +11,8 @@ namespace dct {
 }
 // pull in the KL ops (defined in dct_kl.cu) without its extern "C" part clashing: include the TU
 #include "dct_kl.cu"
+static bool g_pdl = true;
+namespace dct { bool pdl_enabled() { return g_pdl; } }
 
 using namespace dct;
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
@@ -31,14 +33,24 @@ __global__ void filll(long long* p, size_t n, int C) {
 struct DiceOpB {
     static constexpr int NIN = 1, NOUT = 0, NDICE = 1;
     static constexpr bool HAS_MAP = false, USES_UP = false, CHECKS_SIMPLEX = false, GMAP = false;
-    template <int CM>
-    static __device__ __forceinline__ float apply(float (&)[1][CM], int, float, float, bool&) { return 0.0f; }
+    template <int CM, class T>
+    static __device__ __forceinline__ T apply(T (&)[1][CM], int, T, float, bool&) { return vset<T>(0.0f); }
 };
 
-template <class Op, int CT, int PPT, int THREADS, int STAGES, int MINB>
+// pure copy through the pipeline (NIN*C planes in, same planes out): the skeleton's own ceiling
+template <int N>
+struct CopyOp {
+    static constexpr int NIN = N, NOUT = N, NDICE = 0;
+    static constexpr bool HAS_MAP = false, USES_UP = false, CHECKS_SIMPLEX = false, GMAP = false;
+    template <int CM, class T>
+    static __device__ __forceinline__ T apply(T (&)[N][CM], int, T, float, bool&) { return vset<T>(0.0f); }
+};
+
+template <class Op, int CT, int PPT, int NCW, int STAGES, int MINB>
 void run(const char* tag, int64_t B, int64_t HW, int reps, double bytes_per_px, bool labels) {
-    using Cfg = TileCfg<Op, CT, PPT, THREADS, STAGES>;
-    auto kern = tile_kernel<Op, CT, PPT, THREADS, STAGES, MINB>;
+    constexpr int THREADS = NCW * 32 + 32;
+    using Cfg = TileCfg<Op, CT, PPT, NCW * 32, STAGES>;
+    auto kern = tile_kernel<Op, CT, PPT, NCW, STAGES, MINB>;
     if (Cfg::kSmemBytes * MINB > 227 * 1024) { printf("%-14s skip (smem)\n", tag); return; }
     const int R = 4;
     size_t n = (size_t)B * CT * HW;
@@ -65,10 +77,10 @@ void run(const char* tag, int64_t B, int64_t HW, int reps, double bytes_per_px, 
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
     int grid = 148 * MINB; if (grid > sets[0].num_tiles) grid = sets[0].num_tiles;
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    for (int i = 0; i < 5; ++i) kern<<<grid, THREADS, Cfg::kSmemBytes>>>(sets[i % R]);
+    for (int i = 0; i < 5; ++i) launch_pdl(kern, dim3(grid), dim3(THREADS), Cfg::kSmemBytes, (cudaStream_t)0, sets[i % R]);
     CK(cudaDeviceSynchronize());
     CK(cudaEventRecord(e0));
-    for (int i = 0; i < reps; ++i) kern<<<grid, THREADS, Cfg::kSmemBytes>>>(sets[i % R]);
+    for (int i = 0; i < reps; ++i) launch_pdl(kern, dim3(grid), dim3(THREADS), Cfg::kSmemBytes, (cudaStream_t)0, sets[i % R]);
     CK(cudaEventRecord(e1));
     CK(cudaDeviceSynchronize());
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
@@ -81,63 +93,38 @@ void run(const char* tag, int64_t B, int64_t HW, int reps, double bytes_per_px, 
 }
 
 static int g_only = -1, g_idx = 0;
-#define RUN(...) do { if (g_only < 0 || g_only == g_idx) run<__VA_ARGS__>; ++g_idx; } while (0)
+// STAGES = 0: as many as fit
+template <class Op, int CT, int PPT, int NCW, int MINB>
+void run_auto(const char* tag, int64_t B, int64_t HW, int reps, double bpp, bool labels) {
+    constexpr int S = tile_stages<tile_row_words<Op, CT>(), PPT, NCW * 32, MINB>();
+    if (g_only < 0 || g_only == g_idx) run<Op, CT, PPT, NCW, S, MINB>(tag, B, HW, reps, bpp, labels);
+    ++g_idx;
+}
+template <class Op, int CT>
+void sweep(const char* tag, int64_t B, int64_t HW, int reps, double bpp, bool labels) {
+    run_auto<Op, CT, 2, 8, 2>(tag, B, HW, reps, bpp, labels);
+    run_auto<Op, CT, 4, 8, 2>(tag, B, HW, reps, bpp, labels);
+    run_auto<Op, CT, 2, 8, 1>(tag, B, HW, reps, bpp, labels);
+    run_auto<Op, CT, 2, 16, 1>(tag, B, HW, reps, bpp, labels);
+    run_auto<Op, CT, 4, 16, 1>(tag, B, HW, reps, bpp, labels);
+    run_auto<Op, CT, 2, 4, 3>(tag, B, HW, reps, bpp, labels);
+    run_auto<Op, CT, 2, 6, 3>(tag, B, HW, reps, bpp, labels);
+    run_auto<Op, CT, 2, 12, 1>(tag, B, HW, reps, bpp, labels);
+}
 int main(int argc, char** argv) {
     int reps = argc > 1 ? atoi(argv[1]) : 40;
     if (argc > 2) g_only = atoi(argv[2]);
-    const int64_t B = 32, HW = 65536;
-    using JD = JsdOp<3, true, kFwdBwd, true>;
-    using JN = JsdOp<3, true, kFwdBwd, false>;
-    if (g_only < 0 || g_only == g_idx) run<JN, 4, 4, 256, 4, 1>("jsd", B, HW, reps, 96, false);
-    ++g_idx;
-    if (g_only < 0 || g_only == g_idx) run<JD, 4, 4, 256, 3, 1>("jsd+dice", B, HW, reps, 104, true);
-    ++g_idx;
-    if (g_only < 0 || g_only == g_idx) run<JD, 4, 2, 512, 3, 1>("jsd+dice", B, HW, reps, 104, true);
-    ++g_idx;
-    if (g_only < 0 || g_only == g_idx) run<JD, 4, 1, 1024, 3, 1>("jsd+dice", B, HW, reps, 104, true);
-    ++g_idx;
-    if (g_only < 0 || g_only == g_idx) run<JD, 4, 2, 256, 4, 2>("jsd+dice", B, HW, reps, 104, true);
-    ++g_idx;
-    if (g_only < 0 || g_only == g_idx) run<JD, 4, 1, 512, 4, 2>("jsd+dice", B, HW, reps, 104, true);
-    ++g_idx;
-    if (g_only < 0 || g_only == g_idx) run<JD, 4, 4, 512, 2, 1>("jsd+dice", B, HW, reps, 104, true);
-    ++g_idx;
-    if (g_only < 0 || g_only == g_idx) run<JD, 4, 2, 1024, 2, 1>("jsd+dice", B, HW, reps, 104, true);
-    ++g_idx;
-    if (g_only < 0 || g_only == g_idx) run<JD, 4, 1, 512, 3, 3>("jsd+dice", B, HW, reps, 104, true);
-    ++g_idx;
-    if (g_only < 0 || g_only == g_idx) run<KlFromLogits, 4, 4, 256, 6, 1>("klfromlogits", B, HW, reps, 48, false);
-    ++g_idx;
-    if (g_only < 0 || g_only == g_idx) run<KlFromLogits, 4, 2, 512, 6, 1>("klfromlogits", B, HW, reps, 48, false);
-    ++g_idx;
-    if (g_only < 0 || g_only == g_idx) run<KlFromLogits, 4, 1, 1024, 6, 1>("klfromlogits", B, HW, reps, 48, false);
-    ++g_idx;
-    if (g_only < 0 || g_only == g_idx) run<KlFromLogits, 4, 4, 256, 3, 2>("klfromlogits", B, HW, reps, 48, false);
-    ++g_idx;
-    if (g_only < 0 || g_only == g_idx) run<KlFromLogits, 4, 2, 512, 3, 2>("klfromlogits", B, HW, reps, 48, false);
-    ++g_idx;
-    if (g_only < 0 || g_only == g_idx) run<KlFromLogits, 4, 4, 512, 3, 1>("klfromlogits", B, HW, reps, 48, false);
-    ++g_idx;
-    if (g_only < 0 || g_only == g_idx) run<KlLogit<true>, 4, 4, 256, 6, 1>("kllogit", B, HW, reps, 64, false);
-    ++g_idx;
-    if (g_only < 0 || g_only == g_idx) run<KlLogit<true>, 4, 2, 512, 6, 1>("kllogit", B, HW, reps, 64, false);
-    ++g_idx;
-    if (g_only < 0 || g_only == g_idx) run<KlLogit<true>, 4, 1, 1024, 6, 1>("kllogit", B, HW, reps, 64, false);
-    ++g_idx;
-    if (g_only < 0 || g_only == g_idx) run<DiceOpB, 4, 4, 256, 8, 1>("dice", B, HW, reps, 24, true);
-    ++g_idx;
-    if (g_only < 0 || g_only == g_idx) run<DiceOpB, 4, 2, 512, 8, 1>("dice", B, HW, reps, 24, true);
-    ++g_idx;
-    if (g_only < 0 || g_only == g_idx) run<DiceOpB, 4, 1, 1024, 8, 1>("dice", B, HW, reps, 24, true);
-    ++g_idx;
-    if (g_only < 0 || g_only == g_idx) run<DiceOpB, 4, 4, 256, 4, 2>("dice", B, HW, reps, 24, true);
-    ++g_idx;
-    // spleen-like: K=2, C=2, 512x512, B=8
-    if (g_only < 0 || g_only == g_idx) run<JsdOp<2, true, kFwdBwd, true>, 2, 4, 256, 8, 1>("jsd+dice c3", 8, 262144, reps, 40, true);
-    ++g_idx;
-    if (g_only < 0 || g_only == g_idx) run<JsdOp<2, true, kFwdBwd, true>, 2, 2, 512, 8, 1>("jsd+dice c3", 8, 262144, reps, 40, true);
-    ++g_idx;
-    if (g_only < 0 || g_only == g_idx) run<JsdOp<2, true, kFwdBwd, true>, 2, 1, 1024, 8, 1>("jsd+dice c3", 8, 262144, reps, 40, true);
-    ++g_idx;
+    int64_t B = argc > 3 ? atoi(argv[3]) : 32;
+    if (argc > 4) g_pdl = atoi(argv[4]) != 0;
+    const int64_t HW = 65536;
+    sweep<JsdOp<3, true, kFwdBwd, true>, 4>("jsd+dice c2", B, HW, reps, 104, true);
+    sweep<JsdOp<3, true, kFwdBwd, false>, 4>("jsd c2", B, HW, reps, 96, false);
+    sweep<CopyOp<3>, 4>("copy3x4", B, HW, reps, 96, false);
+    sweep<CopyOp<1>, 4>("copy1x4", B, HW, reps, 32, false);
+    sweep<KlFromLogits, 4>("klfromlogits", B, HW, reps, 48, false);
+    sweep<KlLogit<true>, 4>("kllogit", B, HW, reps, 64, false);
+    sweep<DiceOpB, 4>("dice", B, HW, reps, 24, true);
+    sweep<JsdOp<2, true, kFwdBwd, true>, 2>("jsd+dice c3", B / 4, 262144, reps, 40, true);
+    sweep<JsdOp<2, true, kFwdBwd, true>, 4>("jsd+dice c1x8", B, 65536, reps, 72, true);
     return 0;
 }
