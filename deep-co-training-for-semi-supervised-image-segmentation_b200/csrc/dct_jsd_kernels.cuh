@@ -407,8 +407,8 @@ int jsd_launch_tile(const JsdCall& c) {
 
 template <int K, int C>
 int jsd_launch_kc(const JsdCall& c) {
-    if constexpr (K * C <= 16) {
-        // ACDC / spleen-sized class counts: TMA tile pipeline (falls through when rows are not 16-byte aligned)
+    if constexpr (K * C <= kTileMaxRows) {
+        // TMA tile pipeline (falls through to the register-tiled kernel when rows are not 16-byte aligned)
         int rc = jsd_launch_tile<K, C>(c);
         if (rc != DCT_ERR_UNSUPPORTED) return rc;
     }

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) pix_kernel(const PixArgs a) {
 
 template <class Op, int CT>
 int pix_launch_ct(const PixArgs& a, int64_t B, cudaStream_t stream) {
-    if constexpr (CT > 0 && Op::NIN * CT <= 16) {
+    if constexpr (CT > 0 && Op::NIN * CT <= kTileMaxRows) {
         TileArgs t{};
         for (int n = 0; n < Op::NIN; ++n) t.in[n] = a.in[n];
         for (int n = 0; n < Op::NOUT; ++n) t.out[n] = a.out[n];

@@ -28,6 +28,7 @@
 namespace dct {
 
 constexpr int kTileMaxTensors = 8;
+constexpr int kTileMaxRows = 80;   // NIN*C rows per stage
 
 struct TileArgs {
     const float* in[kTileMaxTensors];
@@ -117,7 +118,6 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
     if constexpr (DICE) {
         for (int j = tid; j < Op::NDICE * CT * 3; j += blockDim.x) s_cnt[j] = 0;
     }
-    pdl_launch_dependents();  // the next kernel may start its own prologue; it waits for our completion below
     __syncthreads();
     pdl_wait();               // the previous grid has completed and its writes are visible (no-op without PDL)
 
@@ -347,6 +347,9 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
             }
         }
     }
+    // this CTA's tiles are done: the next kernel in the stream may be scheduled onto the SMs that drain first and run
+    // its prologue; its pdl_wait() still holds it until this whole grid (epilogue below included) has completed
+    pdl_launch_dependents();
     if constexpr (Op::CHECKS_SIMPLEX) {
         if (a.flags != nullptr && __syncthreads_or(bad)) {
             if (bad) atomicAdd(&a.flags[DCT_FLAG_SIMPLEX], 1);
@@ -372,10 +375,16 @@ inline bool tile_eligible(const TileArgs& a, int64_t B) {
 template <class Op, int CT>
 int tile_launch_ct(TileArgs a, int64_t B, cudaStream_t stream) {
     constexpr int ROWS = Op::NIN * CT;
-    static_assert(ROWS <= 16, "tile pipeline instantiations are for NIN*C <= 16 (larger: register-tiled kernels)");
-    // measured on B200 (tools/kbench_tile.cu): two CTAs of 8 consumer warps per SM; math-heavy ops take 2 pixels/thread
-    constexpr int NCW = 8, MINB = 2;
-    constexpr int PPT = ROWS > 8 ? 2 : 4;
+    static_assert(ROWS <= kTileMaxRows, "tile pipeline instantiations are for NIN*C <= 80");
+    // Launch shapes measured on B200 (tools/kbench_tile.cu, profiles/):
+    //   rows <= 8        4 pixels/thread, 8 consumer warps, 2 CTAs/SM
+    //   rows <= 16       2 pixels/thread (math-heavy: ACDC K*C = 12..16), 8 warps, 2 CTAs/SM
+    //   rows <= 40       Cityscapes C = 19 with 2 tensors: 2 pixels/thread keeps the packed FP32x2 math; one CTA per SM
+    //                    of 4 warps (8 for read-only ops) so that a [rows][TP] stage leaves room for >= 2..5 stages
+    //   rows <= 80       one pixel/thread (a pixel pair would need > 255 registers), 4 warps
+    constexpr int PPT = ROWS <= 8 ? 4 : (ROWS <= 40 ? 2 : 1);
+    constexpr int NCW = ROWS <= 16 ? 8 : (ROWS <= 40 ? (Op::NOUT == 0 ? 8 : 4) : 4);
+    constexpr int MINB = ROWS <= 16 ? 2 : (ROWS <= 40 ? 1 : (ROWS <= 60 ? 2 : 1));
     constexpr int STAGES = tile_stages<tile_row_words<Op, CT>(), PPT, NCW * 32, MINB>();
     using Cfg = TileCfg<Op, CT, PPT, NCW * 32, STAGES>;
     auto kern = tile_kernel<Op, CT, PPT, NCW, STAGES, MINB>;

@@ -51,51 +51,48 @@ __device__ __forceinline__ float block_sum_f(float v, float* s_warp) {
     return t;
 }
 
-__device__ __forceinline__ void l2_emit(const L2Args& a, int64_t off, const FVec<4>& v) {
-    FVec<4> o;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) o.v[j] = a.scale * v.v[j];  // (d / norm) was formed in registers; then scale * d
-    st_stream<4>(a.out + off, o);
-    if (a.img != nullptr) {
-        FVec<4> im = ld_stream<4>(a.img + off), ad;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) ad.v[j] = fminf(fmaxf(im.v[j] + o.v[j], 0.0f), 1.0f);
-        st_stream<4>(a.adv + off, ad);
-    }
-}
-
 // One cluster per sample; NV float4 per thread (compile-time so the slice lives in registers).
-template <int NV>
+// Critical path per normalisation pass: warp shuffle tree -> one shared-memory word per warp -> ONE
+// cluster barrier -> every warp gathers the 8 CTAs x 8 warps partials through distributed shared
+// memory (2 per lane) and reduces them with the same shuffle tree (so all 2048 threads of the
+// cluster hold bit-identical norms).  Per-pass slots make a second barrier per pass unnecessary;
+// the image (for the clamp(img + r) tail) is prefetched before the first barrier.
+template <int NV, bool IMG>
 __global__ void __cluster_dims__(kL2Cluster, 1, 1) __launch_bounds__(kL2Threads)
 l2_cluster_kernel(const L2Args a) {
+    static_assert(kL2Cluster * (kL2Threads / 32) == 64, "gather assumes 64 partials = 2 per lane");
     cg::cluster_group cluster = cg::this_cluster();
-    __shared__ float s_warp[32];
-    __shared__ float s_part;  // this CTA's partial sum of squares, read by its cluster peers
+    __shared__ float s_wsum[2][kL2Threads / 32];  // [pass][warp], read by the cluster peers
     const unsigned int rank = cluster.block_rank();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t b = blockIdx.x / kL2Cluster;
     const int64_t base = b * a.M;
     const int64_t nvec = a.M / 4;
     FVec<4> v[NV];
+    FVec<4> im[IMG ? NV : 1];
     float ss = 0.0f;
-    pdl_launch_dependents();
     pdl_wait();
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
         const int64_t q = ((int64_t)j * kL2Cluster + rank) * kL2Threads + threadIdx.x;  // float4 index in sample
         if (q < nvec) {
             v[j] = ld_stream<4>(a.d + base + q * 4);
-            ss += v[j].v[0] * v[j].v[0] + v[j].v[1] * v[j].v[1] + v[j].v[2] * v[j].v[2] + v[j].v[3] * v[j].v[3];
+            if constexpr (IMG) im[j] = ld_stream<4>(a.img + base + q * 4);
         }
     }
-    for (int pass = 0; pass < a.passes; ++pass) {
-        float cta = block_sum_f(ss, s_warp);
-        if (threadIdx.x == 0) s_part = cta;
-        cluster.sync();
-        float tot = 0.0f;
 #pragma unroll
-        for (int r = 0; r < kL2Cluster; ++r) tot += *cluster.map_shared_rank(&s_part, r);  // DSMEM, fixed order
-        cluster.sync();  // nobody may overwrite / free s_part before every peer has read it
-        const float nrm = sqrtf(tot) + 1e-16f;
+    for (int j = 0; j < NV; ++j) {
+        const int64_t q = ((int64_t)j * kL2Cluster + rank) * kL2Threads + threadIdx.x;
+        if (q < nvec) ss += v[j].v[0] * v[j].v[0] + v[j].v[1] * v[j].v[1] + v[j].v[2] * v[j].v[2] + v[j].v[3] * v[j].v[3];
+    }
+    for (int pass = 0; pass < a.passes; ++pass) {
+        const float w = warp_sum(ss);
+        if (lane == 0) s_wsum[pass][wid] = w;
+        cluster.sync();
+        float t = *cluster.map_shared_rank(&s_wsum[pass][lane & 7], lane >> 3) +
+                  *cluster.map_shared_rank(&s_wsum[pass][lane & 7], 4 + (lane >> 3));
+        t = warp_sum(t);
+        const float nrm = sqrtf(t) + 1e-16f;
         ss = 0.0f;
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
@@ -112,8 +109,22 @@ l2_cluster_kernel(const L2Args a) {
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
         const int64_t q = ((int64_t)j * kL2Cluster + rank) * kL2Threads + threadIdx.x;
-        if (q < nvec) l2_emit(a, base + q * 4, v[j]);
+        if (q < nvec) {
+            const int64_t off = base + q * 4;
+            FVec<4> o;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o.v[e] = a.scale * v[j].v[e];  // (d / norm) was formed in registers; then scale * d
+            st_stream<4>(a.out + off, o);
+            if constexpr (IMG) {
+                FVec<4> ad;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) ad.v[e] = fminf(fmaxf(im[j].v[e] + o.v[e], 0.0f), 1.0f);
+                st_stream<4>(a.adv + off, ad);
+            }
+        }
     }
+    pdl_launch_dependents();
+    cluster.sync();  // no CTA may exit (and free s_wsum) while a peer can still be reading it
 }
 
 // fallback pass 1: per-(sample, CTA) sum of squares -> workspace partials[b * gx + x] (double)
@@ -206,11 +217,14 @@ extern "C" int dct_l2_normalize_f32(const float* d, float* out, int64_t B, int64
     if (vec_ok && nv <= kL2MaxVecPerThread && B * kL2Cluster <= 0x7fffffff) {
         dim3 grid((unsigned)(B * kL2Cluster));
         cudaError_t e;
-        if (nv <= 1) e = launch_pdl(l2_cluster_kernel<1>, grid, dim3(kL2Threads), 0, s, a);
-        else if (nv <= 2) e = launch_pdl(l2_cluster_kernel<2>, grid, dim3(kL2Threads), 0, s, a);
-        else if (nv <= 4) e = launch_pdl(l2_cluster_kernel<4>, grid, dim3(kL2Threads), 0, s, a);
-        else if (nv <= 8) e = launch_pdl(l2_cluster_kernel<8>, grid, dim3(kL2Threads), 0, s, a);
-        else e = launch_pdl(l2_cluster_kernel<16>, grid, dim3(kL2Threads), 0, s, a);
+#define DCT_L2_GO(NVV) (img != nullptr ? launch_pdl(l2_cluster_kernel<NVV, true>, grid, dim3(kL2Threads), 0, s, a) \
+                                       : launch_pdl(l2_cluster_kernel<NVV, false>, grid, dim3(kL2Threads), 0, s, a))
+        if (nv <= 1) e = DCT_L2_GO(1);
+        else if (nv <= 2) e = DCT_L2_GO(2);
+        else if (nv <= 4) e = DCT_L2_GO(4);
+        else if (nv <= 8) e = DCT_L2_GO(8);
+        else e = DCT_L2_GO(16);
+#undef DCT_L2_GO
         if (e != cudaSuccess) { g_last_cuda_error = e; return DCT_ERR_CUDA; }
         return check_launch();
     }

@@ -18,5 +18,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python bench.py --steps 4 --warmup 3 --no-cpu-baseline --e2e-steps 3 > $out/ncu_launch_bench.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:tile_kernel -s 6 -c 3 -o $out/prof_jsd \
     python bench.py --steps 4 --warmup 3 --no-cpu-baseline --e2e-steps 3 --graph 0 > $out/ncu_full.log 2>&1
+( timeout 600 python tools/sweep.py --out $out/sweep 2>&1 | tail -12 ) > $out/sweep.log
 ls -la $out
 cat $out/pytest_gpu.log | tail -5; cat $out/smoke.log; cat $out/bench.log

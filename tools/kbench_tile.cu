@@ -116,15 +116,56 @@ int main(int argc, char** argv) {
     if (argc > 2) g_only = atoi(argv[2]);
     int64_t B = argc > 3 ? atoi(argv[3]) : 32;
     if (argc > 4) g_pdl = atoi(argv[4]) != 0;
+    int which = argc > 5 ? atoi(argv[5]) : 0;  // 0: C=4 family, 1: C=19 family
     const int64_t HW = 65536;
-    sweep<JsdOp<3, true, kFwdBwd, true>, 4>("jsd+dice c2", B, HW, reps, 104, true);
-    sweep<JsdOp<3, true, kFwdBwd, false>, 4>("jsd c2", B, HW, reps, 96, false);
-    sweep<CopyOp<3>, 4>("copy3x4", B, HW, reps, 96, false);
-    sweep<CopyOp<1>, 4>("copy1x4", B, HW, reps, 32, false);
-    sweep<KlFromLogits, 4>("klfromlogits", B, HW, reps, 48, false);
-    sweep<KlLogit<true>, 4>("kllogit", B, HW, reps, 64, false);
-    sweep<DiceOpB, 4>("dice", B, HW, reps, 24, true);
-    sweep<JsdOp<2, true, kFwdBwd, true>, 2>("jsd+dice c3", B / 4, 262144, reps, 40, true);
-    sweep<JsdOp<2, true, kFwdBwd, true>, 4>("jsd+dice c1x8", B, 65536, reps, 72, true);
+    if (which == 0) {
+        sweep<JsdOp<3, true, kFwdBwd, true>, 4>("jsd+dice c2", B, HW, reps, 104, true);
+        sweep<JsdOp<3, true, kFwdBwd, false>, 4>("jsd c2", B, HW, reps, 96, false);
+        sweep<CopyOp<3>, 4>("copy3x4", B, HW, reps, 96, false);
+        sweep<CopyOp<1>, 4>("copy1x4", B, HW, reps, 32, false);
+        sweep<KlFromLogits, 4>("klfromlogits", B, HW, reps, 48, false);
+        sweep<KlLogit<true>, 4>("kllogit", B, HW, reps, 64, false);
+        sweep<DiceOpB, 4>("dice", B, HW, reps, 24, true);
+        sweep<JsdOp<2, true, kFwdBwd, true>, 2>("jsd+dice c3", B / 4, 262144, reps, 40, true);
+        sweep<JsdOp<2, true, kFwdBwd, true>, 4>("jsd+dice c1x8", B, 65536, reps, 72, true);
+    } else {
+        // Cityscapes-like: C = 19, 512x1024 images
+        const int64_t HWc = 512 * 1024;
+        using J19 = JsdOp<2, true, kFwdBwd, false>;
+        run_auto<J19, 19, 1, 8, 1>("jsd K2 C19", B, HWc, reps, 304, false);
+        run_auto<J19, 19, 1, 4, 1>("jsd K2 C19", B, HWc, reps, 304, false);
+        run_auto<J19, 19, 1, 4, 2>("jsd K2 C19", B, HWc, reps, 304, false);
+        run_auto<J19, 19, 2, 4, 1>("jsd K2 C19", B, HWc, reps, 304, false);
+        run_auto<J19, 19, 1, 16, 1>("jsd K2 C19", B, HWc, reps, 304, false);
+        run_auto<J19, 19, 1, 2, 2>("jsd K2 C19", B, HWc, reps, 304, false);
+        run_auto<CopyOp<2>, 19, 1, 8, 1>("copy2x19", B, HWc, reps, 304, false);
+        run_auto<CopyOp<2>, 19, 1, 4, 2>("copy2x19", B, HWc, reps, 304, false);
+        run_auto<CopyOp<2>, 19, 4, 4, 1>("copy2x19", B, HWc, reps, 304, false);
+        run_auto<KlFromLogits, 19, 1, 8, 1>("klfromlogits19", B, HWc, reps, 228, false);
+        run_auto<KlFromLogits, 19, 1, 4, 2>("klfromlogits19", B, HWc, reps, 228, false);
+        run_auto<KlLogit<true>, 19, 1, 8, 1>("kllogit19", B, HWc, reps, 304, false);
+    }
+    if (which == 2) {
+        const int64_t HWc = 512 * 1024;
+        using J3 = JsdOp<3, true, kFwdBwd, false>;
+        using J4 = JsdOp<4, true, kFwdBwd, false>;
+        run_auto<J3, 19, 1, 4, 1>("jsd K3 C19", B, HWc, reps, 456, false);
+        run_auto<J3, 19, 1, 4, 2>("jsd K3 C19", B, HWc, reps, 456, false);
+        run_auto<J3, 19, 1, 8, 1>("jsd K3 C19", B, HWc, reps, 456, false);
+        run_auto<J3, 19, 2, 2, 2>("jsd K3 C19", B, HWc, reps, 456, false);
+        run_auto<J3, 19, 2, 4, 1>("jsd K3 C19", B, HWc, reps, 456, false);
+        run_auto<J4, 19, 1, 4, 1>("jsd K4 C19", B, HWc, reps, 608, false);
+        run_auto<J4, 19, 1, 2, 2>("jsd K4 C19", B, HWc, reps, 608, false);
+        run_auto<J4, 19, 1, 8, 1>("jsd K4 C19", B, HWc, reps, 608, false);
+        run_auto<KlFromLogits, 19, 2, 4, 1>("klfromlogits19", B, HWc, reps, 228, false);
+        run_auto<KlFromLogits, 19, 2, 4, 2>("klfromlogits19", B, HWc, reps, 228, false);
+        run_auto<KlFromLogits, 19, 2, 8, 1>("klfromlogits19", B, HWc, reps, 228, false);
+        run_auto<KlLogit<true>, 19, 2, 4, 1>("kllogit19", B, HWc, reps, 304, false);
+        run_auto<KlLogit<true>, 19, 2, 4, 2>("kllogit19", B, HWc, reps, 304, false);
+        run_auto<JsdOp<2, true, kFwdBwd, false>, 19, 2, 4, 1>("jsd K2 C19", B, HWc, reps, 304, false);
+        run_auto<JsdOp<2, true, kFwdBwd, false>, 19, 2, 6, 1>("jsd K2 C19", B, HWc, reps, 304, false);
+        run_auto<JsdOp<2, true, kFwd, false>, 19, 2, 4, 1>("jsdfwd K2 C19", B, HWc, reps, 152, false);
+        run_auto<JsdOp<2, true, kFwd, false>, 19, 2, 8, 1>("jsdfwd K2 C19", B, HWc, reps, 152, false);
+    }
     return 0;
 }
