@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstddef>
 #include <type_traits>
 
 #include "../../include/dct_b200.h"
@@ -13,12 +14,19 @@ constexpr int kSMs = 148;             // B200: 2 dies x 74 SMs
 constexpr int kMaxPartials = 8192;    // per-launch CTA partial sums kept in the workspace
 constexpr float kEntEps = 1e-16f;     // Entropy / Entropy_2D epsilon (generalframework/loss/loss.py:64,81)
 
-// workspace layout: [0,8) uint32 ticket (+pad) | [64, 64+8*kMaxPartials) double partials
+// workspace layout: 64-byte header (all fields zero between launches: the last CTA of a launch re-arms them)
+// followed by kMaxPartials double partials
 struct Workspace {
-    unsigned int ticket;
-    unsigned int pad[15];
+    unsigned int ticket;         // CTAs that have finished
+    unsigned int tile_counter;   // dynamic tile scheduler of the tile pipeline (dct_tile.cuh)
+    unsigned int nonfinite;      // #CTAs that saw a NaN / inf / out-of-range per-thread partial sum
+    unsigned int pad0;
+    unsigned long long fx_lo;    // order-independent loss sum in 2^-40 fixed point: sum of the low 32 bits ...
+    long long fx_hi;             // ... and of the (signed) high bits of every partial
+    unsigned int pad[8];
     double partials[kMaxPartials];
 };
+static_assert(offsetof(Workspace, partials) == 64, "workspace header is 64 bytes");
 
 struct Upstream {          // see "dct_upstream" in include/dct_b200.h
     const float* gmap;     // [B,HW] or null
@@ -54,6 +62,12 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 bool pdl_enabled();  // dct_abi.cu
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 template <class... KArgs, class... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
@@ -182,6 +196,71 @@ __device__ __forceinline__ void grid_sum_to(double v, Workspace* ws, double* out
                 *out = t;
                 ws->ticket = 0u;
             }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Order-independent, bit-reproducible grid sum for the dynamically scheduled tile pipeline.
+// Every per-thread fp32 partial (the sum of one thread's 1..4 pixel values of one tile) is
+// converted exactly to 2^-40 fixed point (fp32 * 2^40 is exact; the int64 conversion is exact for
+// |partial| < 2^23) and accumulated with integer adds, which are associative: the result does not
+// depend on which CTA processed which tile.  Low and high halves are summed separately so that
+// nothing can overflow (N < 2^31 partials).  NaN / inf partials poison the result (NaN).
+// ---------------------------------------------------------------------------------------------
+constexpr float kFxScale = 1099511627776.0f;  // 2^40
+__device__ __forceinline__ long long to_fixed(float part, bool& nonfinite) {
+    nonfinite |= !(fabsf(part) < 8388608.0f);
+    return __float2ll_rn(part * kFxScale);
+}
+__device__ __forceinline__ long long warp_sum(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Called by every thread of the CTA at the end of a tile-pipeline kernel.  `out` may be null.
+// Also re-arms the workspace header (ticket, tile counter, accumulators) when the last CTA is through.
+__device__ __forceinline__ void tile_grid_finish(long long acc_fx, bool nonfinite, Workspace* ws, double* out, int num_ctas) {
+    if (ws == nullptr) return;
+    __shared__ long long s_lo[20], s_hi[20];  // <= 17 warps per CTA
+    __shared__ int s_nf;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if (out != nullptr) {
+        if (threadIdx.x == 0) s_nf = 0;
+        long long lo = (long long)((unsigned long long)acc_fx & 0xffffffffull), hi = acc_fx >> 32;
+        lo = warp_sum(lo);
+        hi = warp_sum(hi);
+        const bool wnf = __any_sync(0xffffffffu, nonfinite);
+        __syncthreads();
+        if (lane == 0) { s_lo[wid] = lo; s_hi[wid] = hi; if (wnf) s_nf = 1; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (out != nullptr) {
+            long long lo = 0, hi = 0;
+            for (int w = 0; w < nw; ++w) { lo += s_lo[w]; hi += s_hi[w]; }
+            atomicAdd(&ws->fx_lo, (unsigned long long)lo);
+            atomicAdd(reinterpret_cast<unsigned long long*>(&ws->fx_hi), (unsigned long long)hi);
+            if (s_nf) atomicAdd(&ws->nonfinite, 1u);
+        }
+        __threadfence();
+        const unsigned int ticket = atomicAdd(&ws->ticket, 1u);
+        if (ticket == (unsigned int)num_ctas - 1u) {  // last CTA: publish the sum and re-arm the header
+            __threadfence();
+            if (out != nullptr) {
+                const unsigned long long lo = __ldcg(&ws->fx_lo);
+                const long long hi = __ldcg(&ws->fx_hi);
+                const unsigned int nf = __ldcg(&ws->nonfinite);
+                const double total = ((double)hi * 4294967296.0 + (double)lo) * (1.0 / 1099511627776.0);
+                *out = nf ? __longlong_as_double(0x7ff8000000000000ll) : total;
+                ws->fx_lo = 0ull;
+                ws->fx_hi = 0ll;
+                ws->nonfinite = 0u;
+            }
+            ws->tile_counter = 0u;
+            __threadfence();
+            ws->ticket = 0u;
         }
     }
 }

@@ -45,6 +45,9 @@ struct TileArgs {
     int64_t count_view_stride;     // B*C*3
     int tiles_per_image;
     int num_tiles;
+    int pool_div;                  // developer knob: the tail pool is 1/pool_div of every CTA's range (0 = default 5)
+    int force_static;              // developer switch (tools/kbench_tile.cu): 1 = no tail pool (purely static contiguous ranges) even with a workspace
+    unsigned long long* trace;     // developer tracing (tools/kbench_tile.cu): per CTA {t_start, t_end} in ns; null in the product
 };
 
 // float rows + optional side rows: int64 labels (Dice ops) and the upstream-gradient map (backward ops)
@@ -70,16 +73,20 @@ struct TileCfg {
     static constexpr size_t kStageBytes = (size_t)WORDS * TP * 4;
     static constexpr int kLabelOff = ROWS * TP;                     // in floats; labels are 8-byte, TP*8 bytes
     static constexpr int kGmapOff = (ROWS + (Op::NDICE > 0 ? 2 : 0)) * TP;  // valid when Op::GMAP
-    static constexpr size_t kSmemBytes = kStageBytes * STAGES + 16 * STAGES + 128;
+    static constexpr size_t kSmemBytes = kStageBytes * STAGES + 16 * STAGES;
 };
 
 // Warp-specialised persistent kernel: NCW consumer warps + 1 producer warp per CTA.
-//   producer (one elected lane): issues every bulk load / store; recycles a stage when its `done`
-//       mbarrier (NCW arrivals) has completed and, for ops with outputs, when the bulk store group
-//       that drains it has finished reading shared memory;
-//   consumers: wait on the stage's `full` mbarrier (transaction bytes), compute in registers, write
-//       results back in place, fence to the async proxy, arrive on `done`.  No CTA-wide barrier in
-//       the tile loop: a fast warp runs ahead by up to STAGES-1 tiles.
+//   producer: lane 0 owns the tile schedule (a contiguous range per CTA whose last fifth is shared through an
+//       atomic counter, see draw() below), publishes each tile index in the stage's shared-memory slot, issues every
+//       bulk load / store, and recycles a stage when its `done` mbarrier (NCW arrivals) has completed and, for ops
+//       with outputs, when the bulk store group that drains it has finished reading shared memory.  All 32 lanes
+//       fold the consumers' per-tile Dice counters into per-image registers (global int64 atomics on image change).
+//   consumers: wait on the stage's `full` mbarrier (transaction bytes), read the tile index (-1 = no more work),
+//       compute in registers, write results back in place, fence to the async proxy, arrive on `done`.
+//       No CTA-wide barrier in the tile loop: a fast warp runs ahead by up to STAGES-1 tiles.
+// Nothing depends on WHICH CTA processes a tile: Dice counts are integer atomics, the loss sum is accumulated in
+// exact fixed point (tile_grid_finish), so results are bit-reproducible under the dynamic part of the schedule.
 template <class Op, int CT, int PPT, int NCW, int STAGES, int MINB = 1>
 __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArgs a) {
     constexpr int CTHREADS = NCW * 32;
@@ -90,22 +97,19 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
     constexpr int NG = PPT / LW;
     using T = typename std::conditional<LW == 2, f2, float>::type;
     static_assert(!DICE || CT <= 4, "fused Dice counters are packed 8-bit fields: C <= 4");
+    static_assert(!DICE || PPT <= 4, "per-tile packed Dice counters: 32 lanes * PPT must stay below 256");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stages = reinterpret_cast<float*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + Cfg::kStageBytes * STAGES);
     uint64_t* done = full + STAGES;
-    __shared__ int s_cnt[DICE ? Op::NDICE * CT * 3 : 1];
+    __shared__ int s_tile[STAGES];  // tile index held by each stage; -1 = end of work
     const int tid = threadIdx.x, lane = tid & 31;
     const bool is_producer = tid >= CTHREADS;
     const int64_t HW = a.HW;
     const int tpi = a.tiles_per_image;
     const bool do_dice = DICE && a.labels != nullptr;
     const bool has_gmap = Op::GMAP && a.up.gmap != nullptr;
-
-    // contiguous tile range of this CTA
-    const int per = a.num_tiles / gridDim.x, extra = a.num_tiles % gridDim.x;
-    const int t_begin = blockIdx.x * per + min((int)blockIdx.x, extra);
-    const int n_tiles = per + ((int)blockIdx.x < extra ? 1 : 0);
+    const bool dynamic = a.ws != nullptr && !a.force_static;
 
     if (tid == 0) {
 #pragma unroll
@@ -115,47 +119,135 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
         }
         tma::fence_barrier_init();
     }
-    if constexpr (DICE) {
-        for (int j = tid; j < Op::NDICE * CT * 3; j += blockDim.x) s_cnt[j] = 0;
-    }
     __syncthreads();
     pdl_wait();               // the previous grid has completed and its writes are visible (no-op without PDL)
+    if (a.trace != nullptr && tid == 0) a.trace[2 * blockIdx.x] = globaltimer_ns();
 
-    double acc = 0.0;
+    long long acc_fx = 0;     // this thread's share of the map sum, 2^-40 fixed point
+    bool nonfinite = false;
     bool bad = false;
 
     if (is_producer) {
+        // scheduling state lives in lane 0; the other lanes only help with the Dice counter flush
+        // Tile schedule: every CTA owns a CONTIGUOUS range of tiles (image locality: its Dice counters change image
+        // once or twice), but the last fifth of every range goes to a pool that is handed out through an atomic counter
+        // in the workspace: CTAs on faster SMs finish their own share early and drain the pool, which removes a
+        // measured 10 us spread of CTA finishing times on a 40 us kernel.  Pool draws are made one tile ahead of use.
+        const int per = a.num_tiles / (int)gridDim.x, extra = a.num_tiles % (int)gridDim.x;
+        const int my_begin = (int)blockIdx.x * per + min((int)blockIdx.x, extra);
+        const int my_n = per + ((int)blockIdx.x < extra ? 1 : 0);
+        const int pool_q = dynamic ? per / (a.pool_div > 0 ? a.pool_div : 5) : 0;             // pool tiles taken from the end of every CTA's range
+        const int my_static = my_n - pool_q;
+        int draws = 0;
+        auto draw = [&]() -> int {  // next tile index for this CTA; >= num_tiles when there is no more work
+            int t;
+            if (draws < my_static) t = my_begin + draws;
+            else if (pool_q == 0) t = a.num_tiles;
+            else {
+                // inline PTX: the compiler's warp-aggregated atomicAdd shuffles the result right away, which
+                // would expose the atomic's round trip at every draw; this way it is consumed one tile later
+                unsigned int got;
+                asm volatile("atom.global.relaxed.gpu.add.u32 %0, [%1], 1;" : "=r"(got) : "l"(&a.ws->tile_counter) : "memory");
+                const int j = (int)(got % gridDim.x), k = (int)(got / gridDim.x);  // k-th pool tile of CTA j's range
+                t = k < pool_q ? j * per + min(j, extra) + per + (j < extra ? 1 : 0) - pool_q + k : a.num_tiles;
+            }
+            ++draws;
+            return t;
+        };
+        int issued = 0;        // loads issued so far; the k-th goes to stage k % STAGES
+        bool more = true;
+        int pending = 0;       // drawn one ahead of its use
+        auto try_issue = [&]() {  // lane 0 only
+            if (!more) return;
+            const int tile = pending, stage = issued % STAGES;
+            if (tile >= a.num_tiles) {  // publish "no more work" through the same barrier
+                more = false;
+                s_tile[stage] = -1;
+                tma::mbar_arrive(&full[stage]);
+                return;
+            }
+            pending = draw();
+            s_tile[stage] = tile;
+            const int b = tile / tpi;
+            const int64_t off = (int64_t)(tile - b * tpi) * TP;
+            const int64_t rem = HW - off;
+            const uint32_t bytes = (uint32_t)((rem < TP ? rem : TP) * 4);
+            float* dst = stages + (size_t)stage * WORDS * TP;
+            uint32_t total = bytes * ROWS;
+            if constexpr (DICE) total += do_dice ? 2u * bytes : 0u;
+            if constexpr (Op::GMAP) total += has_gmap ? bytes : 0u;
+            tma::mbar_expect_tx(&full[stage], total);  // release: the tile index above is visible to the waiters
+#pragma unroll
+            for (int n = 0; n < NIN; ++n)
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                    tma::bulk_load(dst + (n * C + c) * TP, a.in[n] + ((int64_t)b * C + c) * HW + off, bytes, &full[stage]);
+            if constexpr (DICE) {
+                if (do_dice) tma::bulk_load(dst + Cfg::kLabelOff, a.labels + (int64_t)b * HW + off, 2u * bytes, &full[stage]);
+            }
+            if constexpr (Op::GMAP) {
+                if (has_gmap) tma::bulk_load(dst + Cfg::kGmapOff, a.up.gmap + (int64_t)b * HW + off, bytes, &full[stage]);
+            }
+            ++issued;
+        };
+        // Dice: producer lane r (and r + 32) keeps counter r = (view, class, kind) of the image being processed in a
+        // register and adds it to the global int64 counters when the image changes (integer atomics: order-independent)
+        constexpr int kDiceCounters = DICE ? Op::NDICE * C * 3 : 0;
+        constexpr int kDiceRounds = (kDiceCounters + 31) / 32;
+        unsigned int dacc[kDiceRounds > 0 ? kDiceRounds : 1] = {};
+        int cur_b = -1;
+        auto flush_dice = [&](int bb) {
+            if constexpr (DICE) {
+#pragma unroll
+                for (int rr = 0; rr < kDiceRounds; ++rr) {
+                    const int r = rr * 32 + lane;
+                    if (r < kDiceCounters && dacc[rr] != 0u) {
+                        const int n = r / (C * 3), rc = r - n * C * 3;
+                        atomicAdd(a.counts + (int64_t)n * a.count_view_stride + (int64_t)bb * C * 3 + rc, (unsigned long long)dacc[rr]);
+                    }
+                    dacc[rr] = 0u;
+                }
+            }
+        };
         if (lane == 0) {
-            auto issue_load = [&](int i) {  // i-th tile of this CTA into stage i % STAGES
-                const int tile = t_begin + i, stage = i % STAGES;
-                const int b = tile / tpi;
-                const int64_t off = (int64_t)(tile - b * tpi) * TP;
-                const int64_t rem = HW - off;
-                const uint32_t bytes = (uint32_t)((rem < TP ? rem : TP) * 4);
-                float* dst = stages + (size_t)stage * WORDS * TP;
-                uint32_t total = bytes * ROWS;
-                if constexpr (DICE) total += do_dice ? 2u * bytes : 0u;
-                if constexpr (Op::GMAP) total += has_gmap ? bytes : 0u;
-                tma::mbar_expect_tx(&full[stage], total);
+            pending = draw();
+#pragma unroll 1
+            for (int s = 0; s < STAGES; ++s) try_issue();
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int i = 0;; ++i) {
+            if (!__shfl_sync(0xffffffffu, (int)(i < issued), 0)) break;
+            const int stage = i % STAGES;
+            tma::mbar_wait(&done[stage], (uint32_t)(i / STAGES) & 1u);  // every consumer warp is through with load i
+            const int tile = s_tile[stage];
+            const int b = tile / tpi;
+            // Dice counts of this tile: every consumer warp left its warp-reduced packed counters (8-bit fields,
+            // word 0 = |gt==c|, words 1+2n / 2+2n = I / P of view n) in its own slice of the stage's label row; the
+            // 32 producer lanes sum one (view, class, kind) counter each over the warps (before the stage is refilled)
+            // and, AFTER this iteration's copies have been issued, add it to their per-image registers (any global
+            // atomics of an image change then never sit in front of the release of the refill's barrier arrive).
+            unsigned int dsum[kDiceRounds > 0 ? kDiceRounds : 1];
+            if constexpr (DICE) {
+                if (do_dice) {
+                    const unsigned int* pkw = reinterpret_cast<const unsigned int*>(stages + (size_t)stage * WORDS * TP + Cfg::kLabelOff);
 #pragma unroll
-                for (int n = 0; n < NIN; ++n)
+                    for (int rr = 0; rr < kDiceRounds; ++rr) {
+                        const int r = rr * 32 + lane;
+                        unsigned int sum = 0u;
+                        if (r < kDiceCounters) {
+                            const int n = r / (C * 3), rc = r - n * C * 3, c = rc / 3, kind = rc - c * 3;
+                            const int widx = kind == 1 ? 0 : (kind == 0 ? 1 + 2 * n : 2 + 2 * n);
 #pragma unroll
-                    for (int c = 0; c < C; ++c)
-                        tma::bulk_load(dst + (n * C + c) * TP, a.in[n] + ((int64_t)b * C + c) * HW + off, bytes, &full[stage]);
-                if constexpr (DICE) {
-                    if (do_dice) tma::bulk_load(dst + Cfg::kLabelOff, a.labels + (int64_t)b * HW + off, 2u * bytes, &full[stage]);
+                            for (int w = 0; w < NCW; ++w) sum += (pkw[w * 64 * PPT + widx] >> (8 * c)) & 0xffu;
+                        }
+                        dsum[rr] = sum;
+                    }
                 }
-                if constexpr (Op::GMAP) {
-                    if (has_gmap) tma::bulk_load(dst + Cfg::kGmapOff, a.up.gmap + (int64_t)b * HW + off, bytes, &full[stage]);
-                }
-            };
-            for (int i = 0; i < STAGES && i < n_tiles; ++i) issue_load(i);
-            for (int i = 0; i < n_tiles; ++i) {
-                const int stage = i % STAGES;
-                tma::mbar_wait(&done[stage], (uint32_t)(i / STAGES) & 1u);  // every consumer warp is through with tile i
+            }
+            __syncwarp();
+            if (lane == 0) {
                 if constexpr (NOUT > 0) {
-                    const int tile = t_begin + i;
-                    const int b = tile / tpi;
                     const int64_t off = (int64_t)(tile - b * tpi) * TP;
                     const int64_t rem = HW - off;
                     const uint32_t bytes = (uint32_t)((rem < TP ? rem : TP) * 4);
@@ -168,70 +260,45 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
                                 tma::bulk_store(a.out[n] + ((int64_t)b * C + c) * HW + off, st + (n * C + c) * TP, bytes);
                         }
                     tma::bulk_commit();
-                    // tile i-1's store group has drained its stage once at most one group is still reading
-                    if (i >= 1 && i - 1 + STAGES < n_tiles) {
+                    // load i-1's store group has drained its stage once at most one group is still reading:
+                    // that stage (== issued % STAGES) takes the next load or the end marker
+                    if (i >= 1) {
                         tma::bulk_wait_read<1>();
-                        issue_load(i - 1 + STAGES);
+                        try_issue();
                     }
                 } else {
-                    if (i + STAGES < n_tiles) issue_load(i + STAGES);
+                    try_issue();
                 }
             }
-            if constexpr (NOUT > 0) tma::bulk_wait_all<0>();
+            if constexpr (DICE) {
+                if (do_dice) {
+                    if (b != cur_b) {  // uniform across the warp
+                        if (cur_b >= 0) flush_dice(cur_b);
+                        cur_b = b;
+                    }
+#pragma unroll
+                    for (int rr = 0; rr < kDiceRounds; ++rr) dacc[rr] += dsum[rr];
+                }
+            }
+            __syncwarp();
+        }
+        if constexpr (DICE) {
+            if (do_dice && cur_b >= 0) flush_dice(cur_b);
+        }
+        if constexpr (NOUT > 0) {
+            if (lane == 0) tma::bulk_wait_all<0>();
         }
         __syncwarp();
     } else {
         float gs = 1.0f;
         if constexpr (Op::USES_UP) gs = upstream_scalar(a.up);
         int nbad_label = 0;
-        unsigned int pk[DICE ? Op::NDICE : 1][2];  // packed 8-bit per-class counters: [view][I,P]
-        unsigned int pkG = 0u;                     // |gt == c| is the same for every view
-        if constexpr (DICE) {
-#pragma unroll
-            for (int n = 0; n < Op::NDICE; ++n) pk[n][0] = pk[n][1] = 0u;
-        }
-        int cur_b = -1, since_flush = 0;
-        auto consumer_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(CTHREADS) : "memory"); };
-
-        // flush this thread's packed counters into the CTA's shared counters, then (all consumers) to global
-        auto flush_counts = [&](int b) {
-            if constexpr (DICE) {
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    int g = (int)((pkG >> (8 * c)) & 0xffu);
-                    g = __reduce_add_sync(0xffffffffu, g);
-#pragma unroll
-                    for (int n = 0; n < Op::NDICE; ++n) {
-                        int vi = (int)((pk[n][0] >> (8 * c)) & 0xffu);
-                        int vp = (int)((pk[n][1] >> (8 * c)) & 0xffu);
-                        vi = __reduce_add_sync(0xffffffffu, vi);
-                        vp = __reduce_add_sync(0xffffffffu, vp);
-                        if (lane == 0) {
-                            if (vi) atomicAdd(&s_cnt[(n * C + c) * 3 + 0], vi);
-                            if (g) atomicAdd(&s_cnt[(n * C + c) * 3 + 1], g);
-                            if (vp) atomicAdd(&s_cnt[(n * C + c) * 3 + 2], vp);
-                        }
-                    }
-                }
-                pkG = 0u;
-#pragma unroll
-                for (int n = 0; n < Op::NDICE; ++n) pk[n][0] = pk[n][1] = 0u;
-                consumer_sync();
-                for (int j = tid; j < Op::NDICE * C * 3; j += CTHREADS) {
-                    const int v = s_cnt[j];
-                    if (v) {
-                        const int n = j / (C * 3), r = j - n * C * 3;
-                        atomicAdd(&a.counts[(int64_t)n * a.count_view_stride + (int64_t)b * C * 3 + r], (unsigned long long)v);
-                        s_cnt[j] = 0;
-                    }
-                }
-                consumer_sync();
-            }
-        };
-
-        for (int i = 0; i < n_tiles; ++i) {
-            const int tile = t_begin + i;
+#pragma unroll 1
+        for (int i = 0;; ++i) {
             const int stage = i % STAGES;
+            tma::mbar_wait(&full[stage], (uint32_t)(i / STAGES) & 1u);
+            const int tile = s_tile[stage];
+            if (tile < 0) break;
             const int b = tile / tpi;
             const int64_t off = (int64_t)(tile - b * tpi) * TP;
             const int64_t rem = HW - off;
@@ -239,14 +306,12 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
             float* st = stages + (size_t)stage * WORDS * TP;
             const int p0 = tid * PPT;
             const bool active = p0 < len;
+            unsigned int pk[DICE ? Op::NDICE : 1][2];  // this tile's packed 8-bit per-class counters: [view][I,P]
+            unsigned int pkG = 0u;                     // |gt == c| is the same for every view
             if constexpr (DICE) {
-                if (do_dice && (b != cur_b || since_flush > 255 - PPT)) {  // uniform across the consumers
-                    if (cur_b >= 0) flush_counts(cur_b);
-                    cur_b = b;
-                    since_flush = 0;
-                }
+#pragma unroll
+                for (int n = 0; n < Op::NDICE; ++n) pk[n][0] = pk[n][1] = 0u;
             }
-            tma::mbar_wait(&full[stage], (uint32_t)(i / STAGES) & 1u);
             if (active) {
                 FVec<PPT> gm;
 #pragma unroll
@@ -323,8 +388,8 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
                             else xin[n][c].v[gi] = vget(x[n][c], 0);
                         }
                 }
-                acc += (double)part;
                 if constexpr (Op::HAS_MAP) {
+                    acc_fx += to_fixed(part, nonfinite);
                     if (a.map != nullptr) st_stream<PPT>(a.map + (int64_t)b * HW + off + p0, mapv);
                 }
 #pragma unroll
@@ -334,14 +399,30 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
                         for (int c = 0; c < C; ++c) *reinterpret_cast<FVec<PPT>*>(st + (n * C + c) * TP + p0) = xin[n][c];
                     }
             }
-            since_flush += PPT;
             if constexpr (NOUT > 0) tma::fence_proxy_async_smem();
             __syncwarp();
+            if constexpr (DICE) {
+                if (do_dice) {
+                    // every packed field is <= 32 lanes * PPT < 256, so the packed words are reduced across the warp as
+                    // they are (REDUX); the warp's labels have all been read, so its slice of the label row is free
+                    const unsigned int wG = __reduce_add_sync(0xffffffffu, pkG);
+                    unsigned int mine = wG;
+#pragma unroll
+                    for (int n = 0; n < Op::NDICE; ++n) {
+                        const unsigned int ri = __reduce_add_sync(0xffffffffu, pk[n][0]);
+                        const unsigned int rp = __reduce_add_sync(0xffffffffu, pk[n][1]);
+                        if (lane == 1 + 2 * n) mine = ri;
+                        if (lane == 2 + 2 * n) mine = rp;
+                    }
+                    if (lane < 1 + 2 * Op::NDICE)
+                        reinterpret_cast<unsigned int*>(st + Cfg::kLabelOff)[(tid >> 5) * 64 * PPT + lane] = mine;
+                    __syncwarp();
+                }
+            }
             if (lane == 0) tma::mbar_arrive(&done[stage]);
         }
         if constexpr (DICE) {
             if (do_dice) {
-                if (cur_b >= 0) flush_counts(cur_b);
                 nbad_label = __reduce_add_sync(0xffffffffu, nbad_label);
                 if (lane == 0 && nbad_label != 0 && a.flags != nullptr) atomicAdd(&a.flags[DCT_FLAG_LABEL], nbad_label);
             }
@@ -355,7 +436,8 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
             if (bad) atomicAdd(&a.flags[DCT_FLAG_SIMPLEX], 1);
         }
     }
-    if constexpr (Op::HAS_MAP) grid_sum_to(acc, a.ws, a.sum, blockIdx.x, gridDim.x);
+    tile_grid_finish(acc_fx, nonfinite, a.ws, Op::HAS_MAP ? a.sum : nullptr, gridDim.x);
+    if (a.trace != nullptr && tid == 0) a.trace[2 * blockIdx.x + 1] = globaltimer_ns();
 }
 
 // Host side: does this problem fit the tile pipeline?  (16-byte aligned rows and segments)
@@ -377,12 +459,12 @@ int tile_launch_ct(TileArgs a, int64_t B, cudaStream_t stream) {
     constexpr int ROWS = Op::NIN * CT;
     static_assert(ROWS <= kTileMaxRows, "tile pipeline instantiations are for NIN*C <= 80");
     // Launch shapes measured on B200 (tools/kbench_tile.cu, profiles/):
-    //   rows <= 8        4 pixels/thread, 8 consumer warps, 2 CTAs/SM
-    //   rows <= 16       2 pixels/thread (math-heavy: ACDC K*C = 12..16), 8 warps, 2 CTAs/SM
+    //   rows <= 4        4 pixels/thread, 8 consumer warps, 2 CTAs/SM (Dice counting, spleen K = C = 2)
+    //   rows <= 16       2 pixels/thread (ACDC: K*C = 8..16, the KL family), 8 warps, 2 CTAs/SM, 4..7 stages
     //   rows <= 40       Cityscapes C = 19 with 2 tensors: 2 pixels/thread keeps the packed FP32x2 math; one CTA per SM
     //                    of 4 warps (8 for read-only ops) so that a [rows][TP] stage leaves room for >= 2..5 stages
     //   rows <= 80       one pixel/thread (a pixel pair would need > 255 registers), 4 warps
-    constexpr int PPT = ROWS <= 8 ? 4 : (ROWS <= 40 ? 2 : 1);
+    constexpr int PPT = ROWS <= 4 ? 4 : (ROWS <= 40 ? 2 : 1);
     constexpr int NCW = ROWS <= 16 ? 8 : (ROWS <= 40 ? (Op::NOUT == 0 ? 8 : 4) : 4);
     constexpr int MINB = ROWS <= 16 ? 2 : (ROWS <= 40 ? 1 : (ROWS <= 60 ? 2 : 1));
     constexpr int STAGES = tile_stages<tile_row_words<Op, CT>(), PPT, NCW * 32, MINB>();

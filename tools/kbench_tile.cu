@@ -1,6 +1,7 @@
 // kbench_tile.cu -- developer micro-benchmark: tile_kernel<Op,...> configurations (PPT, THREADS, STAGES, CTAs/SM)
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <vector>
 
 #include "dct_jsd_kernels.cuh"
@@ -12,6 +13,8 @@ namespace dct {
 // pull in the KL ops (defined in dct_kl.cu) without its extern "C" part clashing: include the TU
 #include "dct_kl.cu"
 static bool g_pdl = true;
+static int g_pool_div = 0;
+static bool g_static = false;  // 1: no workspace -> static round-robin tile schedule (and no loss sum)
 namespace dct { bool pdl_enabled() { return g_pdl; } }
 
 using namespace dct;
@@ -70,7 +73,7 @@ void run(const char* tag, int64_t B, int64_t HW, int reps, double bytes_per_px, 
         if (labels) { long long* l; CK(cudaMalloc(&l, (size_t)B * HW * 8)); allocs.push_back(l); filll<<<1024, 256>>>(l, (size_t)B * HW, CT); a.labels = (const int64_t*)l; }
         a.counts = counts; a.count_view_stride = B * CT * 3;
         a.HW = HW; a.map = nullptr; a.sum = Op::HAS_MAP ? sum : nullptr; a.up = Upstream{nullptr, nullptr, 1e-6f};
-        a.eps = 1e-10f; a.flags = nullptr; a.ws = ws;
+        a.eps = 1e-10f; a.flags = nullptr; a.ws = ws; a.force_static = g_static ? 1 : 0; a.pool_div = g_pool_div;
         a.tiles_per_image = (int)((HW + Cfg::TP - 1) / Cfg::TP); a.num_tiles = (int)(a.tiles_per_image * B);
         sets[r] = a;
     }
@@ -85,6 +88,26 @@ void run(const char* tag, int64_t B, int64_t HW, int reps, double bytes_per_px, 
     CK(cudaDeviceSynchronize());
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
     double us = ms * 1e3 / reps;
+    // in-kernel trace of a chain of 8 launches: CTA residency window vs launch-to-launch spacing
+    {
+        const int NL = 8;
+        unsigned long long* tr; CK(cudaMalloc(&tr, (size_t)NL * grid * 16));
+        for (int i = 0; i < NL; ++i) { TileArgs t = sets[i % R]; t.trace = tr + (size_t)i * grid * 2; launch_pdl(kern, dim3(grid), dim3(THREADS), Cfg::kSmemBytes, (cudaStream_t)0, t); }
+        CK(cudaDeviceSynchronize());
+        std::vector<unsigned long long> h((size_t)NL * grid * 2);
+        CK(cudaMemcpy(h.data(), tr, h.size() * 8, cudaMemcpyDeviceToHost));
+        double win = 0, gap = 0, cta = 0, spread_s = 0, spread_e = 0; unsigned long long prev_end = 0, prev_start = 0; double spacing = 0;
+        for (int i = 0; i < NL; ++i) {
+            unsigned long long s0 = ~0ull, s1 = 0, e0_ = ~0ull, e1_ = 0; double d = 0;
+            for (int c = 0; c < grid; ++c) { auto a0 = h[((size_t)i * grid + c) * 2], a1 = h[((size_t)i * grid + c) * 2 + 1]; s0 = std::min(s0, a0); s1 = std::max(s1, a0); e0_ = std::min(e0_, a1); e1_ = std::max(e1_, a1); d += (double)(a1 - a0); }
+            if (i >= 2) { win += (double)(e1_ - s0); gap += (double)(s0 - prev_end); cta += d / grid; spread_s += (double)(s1 - s0); spread_e += (double)(e1_ - e0_); spacing += (double)(s0 - prev_start); }
+            prev_end = e1_; prev_start = s0;
+        }
+        int n = NL - 2;
+        printf("      trace: spacing %.2f us = window %.2f (first start -> last end) + gap %.2f | mean CTA life %.2f, start spread %.2f, end spread %.2f\n",
+               spacing / n / 1e3, win / n / 1e3, gap / n / 1e3, cta / n / 1e3, spread_s / n / 1e3, spread_e / n / 1e3);
+        cudaFree(tr);
+    }
     cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
     printf("%-14s C=%d PPT=%d thr=%4d stages=%d minb=%d regs=%3d smem=%3zuKB grid=%3d  %8.2f us  %7.1f GB/s  %6.2f Gpix/s\n", tag, CT, PPT,
            THREADS, STAGES, MINB, fa.numRegs, Cfg::kSmemBytes / 1024, grid, us, bytes_per_px * B * HW / us / 1e3, B * HW / us / 1e3);
@@ -116,7 +139,9 @@ int main(int argc, char** argv) {
     if (argc > 2) g_only = atoi(argv[2]);
     int64_t B = argc > 3 ? atoi(argv[3]) : 32;
     if (argc > 4) g_pdl = atoi(argv[4]) != 0;
-    int which = argc > 5 ? atoi(argv[5]) : 0;  // 0: C=4 family, 1: C=19 family
+    int which = argc > 5 ? atoi(argv[5]) : 0;
+    if (argc > 6) g_static = atoi(argv[6]) != 0;
+    if (argc > 7) g_pool_div = atoi(argv[7]);  // 0: C=4 family, 1: C=19 family
     const int64_t HW = 65536;
     if (which == 0) {
         sweep<JsdOp<3, true, kFwdBwd, true>, 4>("jsd+dice c2", B, HW, reps, 104, true);
