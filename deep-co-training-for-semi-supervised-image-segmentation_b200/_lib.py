@@ -45,6 +45,10 @@ _SIGNATURES = {
     "dct_dice_from_counts_f32": [_p, _i64, _i, _i, _p, _p],
     "dct_confusion_f32": [_p, _p, _i, _i64, _i64, _p, _p],
     "dct_confusion_labels_i64": [_p, _p, _i64, _i, _p, _p, _p],
+    "dct_label_hist_i64": [_p, _i64, _i, _i64, _p, _p],
+    "dct_ce_fwd_f32": [_p, _p, _i, _i64, _i64, _p, _i64, _p, _p, _p, _p, _p],
+    "dct_ce_bwd_f32": [_p, _p, _i, _i64, _i64, _p, _i64, _p, _p, _f, _p, _p, _p],
+    "dct_ce_fwdbwd_f32": [_p, _p, _i, _i64, _i64, _p, _i64, _p, _f, _p, _p, _p, _p, _p, _p, _p],
 }
 _RESTYPES = {"dct_error_string": C.c_char_p, "dct_last_cuda_error": C.c_char_p, "dct_workspace_bytes": C.c_size_t}
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

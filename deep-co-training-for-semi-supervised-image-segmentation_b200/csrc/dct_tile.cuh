@@ -21,6 +21,9 @@
 //   CHECKS_SIMPLEX   sets the simplex flag through `bad`
 //   NDICE            number of leading input tensors whose Dice counts are accumulated (0 = none)
 //   apply<CM>(x[NIN][CM], C, g, eps, bad) -> map value; outputs left in x[0..NOUT)
+//   LABELS (optional) the op itself consumes the int64 label of every pixel (supervised cross-entropy): it then
+//                    provides apply_lab<CM>(x, C, g, cls[LW], w[LW], bad) instead, with cls = label in [0,C) or -1
+//                    (ignored / out of range) and w = class weight of the label (0 when cls < 0 or ignored)
 #pragma once
 #include "dct_common.cuh"
 #include "dct_tma.cuh"
@@ -43,6 +46,8 @@ struct TileArgs {
     const int64_t* labels;         // Dice: [B,HW] int64 (NDICE > 0 and non-null => count)
     unsigned long long* counts;    // Dice: [NDICE][B][C][3] (I,G,P), accumulated into
     int64_t count_view_stride;     // B*C*3
+    const float* class_w;          // LABELS ops: per-class weight [C] (device) or null = 1
+    int64_t ignore_index;          // LABELS ops: label value that contributes nothing (nn.NLLLoss ignore_index)
     int tiles_per_image;
     int num_tiles;
     int pool_div;                  // developer knob: the tail pool is 1/pool_div of every CTA's range (0 = default 5)
@@ -50,10 +55,18 @@ struct TileArgs {
     unsigned long long* trace;     // developer tracing (tools/kbench_tile.cu): per CTA {t_start, t_end} in ns; null in the product
 };
 
-// float rows + optional side rows: int64 labels (Dice ops) and the upstream-gradient map (backward ops)
+// does the op read the labels itself (Op::LABELS == true)?  Ops without the member do not.
+template <class Op, class = void>
+struct op_labels : std::false_type {};
+template <class Op>
+struct op_labels<Op, std::enable_if_t<Op::LABELS>> : std::true_type {};
+template <class Op>
+constexpr bool op_label_row() { return Op::NDICE > 0 || op_labels<Op>::value; }
+
+// float rows + optional side rows: int64 labels (Dice / label ops) and the upstream-gradient map (backward ops)
 template <class Op, int CT>
 constexpr int tile_row_words() {
-    return Op::NIN * CT + (Op::NDICE > 0 ? 2 : 0) + (Op::GMAP ? 1 : 0);
+    return Op::NIN * CT + (op_label_row<Op>() ? 2 : 0) + (Op::GMAP ? 1 : 0);
 }
 
 template <int WORDS, int PPT, int CTHREADS, int MINB>
@@ -72,7 +85,7 @@ struct TileCfg {
     static constexpr int WORDS = tile_row_words<Op, CT>();          // 4-byte words per pixel incl. side rows
     static constexpr size_t kStageBytes = (size_t)WORDS * TP * 4;
     static constexpr int kLabelOff = ROWS * TP;                     // in floats; labels are 8-byte, TP*8 bytes
-    static constexpr int kGmapOff = (ROWS + (Op::NDICE > 0 ? 2 : 0)) * TP;  // valid when Op::GMAP
+    static constexpr int kGmapOff = (ROWS + (op_label_row<Op>() ? 2 : 0)) * TP;  // valid when Op::GMAP
     static constexpr size_t kSmemBytes = kStageBytes * STAGES + 16 * STAGES;
 };
 
@@ -93,6 +106,8 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
     using Cfg = TileCfg<Op, CT, PPT, CTHREADS, STAGES>;
     constexpr int TP = Cfg::TP, ROWS = Cfg::ROWS, WORDS = Cfg::WORDS, NIN = Op::NIN, NOUT = Op::NOUT, C = CT;
     constexpr bool DICE = Op::NDICE > 0;
+    constexpr bool LAB = op_labels<Op>::value;   // the op consumes the labels itself
+    constexpr bool LROW = DICE || LAB;           // the stage carries a label row
     constexpr int LW = (PPT % 2 == 0) ? 2 : 1;   // pixels per math lane group: pairs use packed FP32x2
     constexpr int NG = PPT / LW;
     using T = typename std::conditional<LW == 2, f2, float>::type;
@@ -107,7 +122,8 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
     const bool is_producer = tid >= CTHREADS;
     const int64_t HW = a.HW;
     const int tpi = a.tiles_per_image;
-    const bool do_dice = DICE && a.labels != nullptr;
+    const bool do_lab = LROW && a.labels != nullptr;
+    const bool do_dice = DICE && do_lab;
     const bool has_gmap = Op::GMAP && a.up.gmap != nullptr;
     const bool dynamic = a.ws != nullptr && !a.force_static;
 
@@ -174,7 +190,7 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
             const uint32_t bytes = (uint32_t)((rem < TP ? rem : TP) * 4);
             float* dst = stages + (size_t)stage * WORDS * TP;
             uint32_t total = bytes * ROWS;
-            if constexpr (DICE) total += do_dice ? 2u * bytes : 0u;
+            if constexpr (LROW) total += do_lab ? 2u * bytes : 0u;
             if constexpr (Op::GMAP) total += has_gmap ? bytes : 0u;
             tma::mbar_expect_tx(&full[stage], total);  // release: the tile index above is visible to the waiters
 #pragma unroll
@@ -182,8 +198,8 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
 #pragma unroll
                 for (int c = 0; c < C; ++c)
                     tma::bulk_load(dst + (n * C + c) * TP, a.in[n] + ((int64_t)b * C + c) * HW + off, bytes, &full[stage]);
-            if constexpr (DICE) {
-                if (do_dice) tma::bulk_load(dst + Cfg::kLabelOff, a.labels + (int64_t)b * HW + off, 2u * bytes, &full[stage]);
+            if constexpr (LROW) {
+                if (do_lab) tma::bulk_load(dst + Cfg::kLabelOff, a.labels + (int64_t)b * HW + off, 2u * bytes, &full[stage]);
             }
             if constexpr (Op::GMAP) {
                 if (has_gmap) tma::bulk_load(dst + Cfg::kGmapOff, a.up.gmap + (int64_t)b * HW + off, bytes, &full[stage]);
@@ -320,8 +336,8 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
                     if (has_gmap) gm = *reinterpret_cast<const FVec<PPT>*>(st + Cfg::kGmapOff + p0);
                 }
                 uint2 lab[PPT];  // int64 labels as (lo, hi) words
-                if constexpr (DICE) {
-                    if (do_dice) {
+                if constexpr (LROW) {
+                    if (do_lab) {
                         if constexpr (PPT % 2 == 0) {
 #pragma unroll
                             for (int v = 0; v < PPT / 2; ++v) {  // two labels per 128-bit shared load
@@ -376,7 +392,25 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
                     T gv;
                     if constexpr (LW == 2) gv = mk2(gs * gm.v[2 * gi], gs * gm.v[2 * gi + 1]);
                     else gv = gs * gm.v[gi];
-                    const T mv = Op::template apply<C, T>(x, C, gv, a.eps, bad);
+                    T mv;
+                    if constexpr (LAB) {
+                        int cls[LW];
+                        float cw[LW];
+#pragma unroll
+                        for (int j = 0; j < LW; ++j) {
+                            const uint2 lb = lab[gi * LW + j];
+                            const bool valid = (lb.y == 0u) & (lb.x < (unsigned int)C);
+                            const bool ign = (lb.x == (unsigned int)((unsigned long long)a.ignore_index & 0xffffffffull)) &
+                                             (lb.y == (unsigned int)((unsigned long long)a.ignore_index >> 32));
+                            if constexpr (!DICE) nbad_label += (!valid) & (!ign);  // (the Dice block counts every label outside [0,C))
+                            const bool use = valid & !ign;
+                            cls[j] = use ? (int)lb.x : -1;
+                            cw[j] = use ? (a.class_w != nullptr ? __ldg(a.class_w + lb.x) : 1.0f) : 0.0f;
+                        }
+                        mv = Op::template apply_lab<C, T>(x, C, gv, cls, cw, bad);
+                    } else {
+                        mv = Op::template apply<C, T>(x, C, gv, a.eps, bad);
+                    }
                     if constexpr (LW == 2) { mapv.v[2 * gi] = vget(mv, 0); mapv.v[2 * gi + 1] = vget(mv, 1); }
                     else mapv.v[gi] = vget(mv, 0);
                     part += vhsum(mv);
@@ -421,8 +455,8 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
             }
             if (lane == 0) tma::mbar_arrive(&done[stage]);
         }
-        if constexpr (DICE) {
-            if (do_dice) {
+        if constexpr (LROW) {
+            if (do_lab) {
                 nbad_label = __reduce_add_sync(0xffffffffu, nbad_label);
                 if (lane == 0 && nbad_label != 0 && a.flags != nullptr) atomicAdd(&a.flags[DCT_FLAG_LABEL], nbad_label);
             }
@@ -458,15 +492,20 @@ template <class Op, int CT>
 int tile_launch_ct(TileArgs a, int64_t B, cudaStream_t stream) {
     constexpr int ROWS = Op::NIN * CT;
     static_assert(ROWS <= kTileMaxRows, "tile pipeline instantiations are for NIN*C <= 80");
-    // Launch shapes measured on B200 (tools/kbench_tile.cu, profiles/):
+    // Launch shapes measured on B200 (tools/kbench_tile.cu; profiles/r01/kbench_c19_sweep.md).  What decides: the
+    // consumer warps are latency-bound (ncu: 21% issue-slot use with one warp per scheduler), so the shape must put
+    // >= 6 consumer warps on an SM while keeping >= 3 stages for ops with outputs (2 stages stall on the store drain);
+    // two small CTAs per SM beat one large CTA (two independent producers).
     //   rows <= 4        4 pixels/thread, 8 consumer warps, 2 CTAs/SM (Dice counting, spleen K = C = 2)
     //   rows <= 16       2 pixels/thread (ACDC: K*C = 8..16, the KL family), 8 warps, 2 CTAs/SM, 4..7 stages
-    //   rows <= 40       Cityscapes C = 19 with 2 tensors: 2 pixels/thread keeps the packed FP32x2 math; one CTA per SM
-    //                    of 4 warps (8 for read-only ops) so that a [rows][TP] stage leaves room for >= 2..5 stages
-    //   rows <= 80       one pixel/thread (a pixel pair would need > 255 registers), 4 warps
-    constexpr int PPT = ROWS <= 4 ? 4 : (ROWS <= 40 ? 2 : 1);
-    constexpr int NCW = ROWS <= 16 ? 8 : (ROWS <= 40 ? (Op::NOUT == 0 ? 8 : 4) : 4);
-    constexpr int MINB = ROWS <= 16 ? 2 : (ROWS <= 40 ? 1 : (ROWS <= 60 ? 2 : 1));
+    //   rows <= 24       one C = 19 tensor (cross-entropy): 4 warps, 2 CTAs/SM, 5 stages        (99% of the copy peak)
+    //   rows <= 40       Cityscapes C = 19 with 2 tensors: 3 warps, 2 CTAs/SM, 3 stages           (JSD 4449 -> 5930 GB/s)
+    //                    read-only ops: 8 warps, 1 CTA/SM, 2 stages
+    //   rows <= 60       K = 3, C = 19: 5 warps, 1 CTA/SM, 3 stages (a pixel pair takes 255 registers)
+    //   rows <= 80       one pixel/thread (a pixel pair would need > 255 registers), 8 warps
+    constexpr int PPT = ROWS <= 4 ? 4 : (ROWS <= 60 ? 2 : 1);
+    constexpr int NCW = ROWS <= 16 ? 8 : (ROWS <= 24 ? 4 : (ROWS <= 40 ? (Op::NOUT == 0 ? 8 : 3) : (ROWS <= 60 ? 5 : 8)));
+    constexpr int MINB = ROWS <= 24 ? 2 : (ROWS <= 40 ? (Op::NOUT == 0 ? 1 : 2) : 1);
     constexpr int STAGES = tile_stages<tile_row_words<Op, CT>(), PPT, NCW * 32, MINB>();
     using Cfg = TileCfg<Op, CT, PPT, NCW * 32, STAGES>;
     auto kern = tile_kernel<Op, CT, PPT, NCW, STAGES, MINB>;

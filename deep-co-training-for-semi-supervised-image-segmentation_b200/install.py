@@ -6,7 +6,7 @@
 
 After ``install()`` the reference's trainers pick up the CUDA-backed classes at
 their existing call sites:
-  get_loss_fn('jsd')                       -> loss.LOSS['jsd']                (loss/__init__.py:6-16)
+  get_loss_fn('jsd' | 'cross_entropy')     -> loss.LOSS[...]                  (loss/__init__.py:6-16)
   KL_Divergence_2D(reduce=True)(adv, real) -> trainer-module globals           (cotraining_totalloss.py:13,392)
   VATGenerator / FSGMGenerator             -> trainer-module globals           (cotraining_totalloss.py:15)
   DiceMeter / IoU                          -> metrics package + trainer globals (cotraining_totalloss.py:18)
@@ -20,7 +20,7 @@ from . import generators, loss, metrics
 _REBIND = {
     "JSD_2D": loss.JSD_2D, "JSD": loss.JSD, "Entropy_2D": loss.Entropy_2D, "Entropy": loss.Entropy,
     "KL_Divergence_2D": loss.KL_Divergence_2D, "KL_Divergence_2D_Logit": loss.KL_Divergence_2D_Logit,
-    "KL_div": loss.KL_div,
+    "KL_div": loss.KL_div, "CrossEntropyLoss2d": loss.CrossEntropyLoss2d,
     "FSGMGenerator": generators.FSGMGenerator, "VATGenerator": generators.VATGenerator,
     "DiceMeter": metrics.DiceMeter, "IoU": metrics.IoU, "ConfusionMatrix": metrics.ConfusionMatrix,
 }
@@ -45,10 +45,12 @@ def install(package: str = "generalframework") -> int:
                 setattr(mod, name, repl)
                 n += 1
         reg = mod.__dict__.get("LOSS")
-        if isinstance(reg, dict) and "jsd" in reg and reg["jsd"] is not loss.JSD_2D:
-            _saved.append((reg, "jsd", reg["jsd"]))
-            reg["jsd"] = loss.JSD_2D
-            n += 1
+        if isinstance(reg, dict) and "jsd" in reg:
+            for key, repl in (("jsd", loss.JSD_2D), ("cross_entropy", loss.CrossEntropyLoss2d)):
+                if key in reg and reg[key] is not repl:
+                    _saved.append((reg, key, reg[key]))
+                    reg[key] = repl
+                    n += 1
     return n
 
 

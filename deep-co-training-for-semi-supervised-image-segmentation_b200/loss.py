@@ -8,7 +8,8 @@ arguments, call signatures, return shapes/dtypes, AssertionError behaviour):
   KL_Divergence_2D       loss.py:110-134
   KL_Divergence_2D_Logit loss.py:137-162
   KL_div                 loss.py:87-107
-  get_loss_fn / LOSS     loss/__init__.py:6-16   (only the consistency entries)
+  CrossEntropyLoss2d     loss.py:12-25           (supervised branch)
+  get_loss_fn / LOSS     loss/__init__.py:6-16   (the hot-path entries)
 
 plus the fast path the north star asks for -- one pass over the K views' LOGITS
 producing the weighted mean JSD, its gradient and (optionally) the K Dice count
@@ -474,9 +475,153 @@ def softmax_dim1(x: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------
-# registry (loss/__init__.py:6-16); only the entries that live on the consistency path
+# supervised branch: CrossEntropyLoss2d (+ the Dice counting of the same logits / labels), SURVEY.md 8f.1
 # ------------------------------------------------------------------------------------------------
-LOSS = {"jsd": JSD_2D}
+def _ce_labels(targets: torch.Tensor, b: int, hw: int) -> torch.Tensor:
+    _runtime.require_cuda(targets, "CrossEntropyLoss2d targets")
+    if targets.dtype != torch.int64:
+        raise TypeError(f"CrossEntropyLoss2d: int64 targets expected, got {targets.dtype}")
+    assert targets.numel() == b * hw, "targets must be [B,H,W] (or [B,1,H,W]) matching the logits"
+    return targets.contiguous()
+
+
+def _ce_weight_sum(lab, c, ignore_index, weight, st, dev):
+    """W = sum_i w[t_i] over the kept pixels as a float64 device scalar (dct_label_hist_i64 + a C-element dot)."""
+    hist = torch.empty(c + 2, dtype=torch.int64, device=dev)
+    _lib.check(_lib.lib().dct_label_hist_i64(lab.data_ptr(), lab.numel(), c, int(ignore_index), hist.data_ptr(),
+                                             _runtime.stream_ptr(dev)), "dct_label_hist_i64")
+    kept = hist[:c].to(torch.float64)
+    return kept.sum() if weight is None else (kept * weight.to(torch.float64)).sum()
+
+
+class _CEFn(torch.autograd.Function):
+    """nn.NLLLoss(weight, ignore_index, reduction)(log_softmax(logits, 1), targets) -- one pass for mean / sum
+    (loss AND gradient from dct_ce_fwdbwd_f32, optionally with the Dice counts of the same tensors), map forward +
+    map backward for reduction 'none'."""
+
+    @staticmethod
+    def forward(ctx, logits, targets, weight, ignore_index: int, reduction: str, n_global, dice_counts):
+        x = _prep(logits, "CrossEntropyLoss2d")
+        assert x.dim() >= 2
+        b, c, hw = _bchw(x)
+        if c > _lib.MAX_CLASSES:
+            raise ValueError(f"CrossEntropyLoss2d: at most {_lib.MAX_CLASSES} classes are supported")
+        dev = x.device
+        lab = _ce_labels(targets, b, hw)
+        st = _runtime.state(dev)
+        h = _lib.lib()
+        w = None
+        if weight is not None:
+            w = weight.to(device=dev, dtype=torch.float32).contiguous()
+            assert w.numel() == c, "weight must have one entry per class"
+        if dice_counts is not None:
+            assert dice_counts.dtype == torch.int64 and dice_counts.is_cuda and dice_counts.numel() == b * c * 3
+        fl, ws, s = _runtime.flags_ptr(st), st.workspace.data_ptr(), _runtime.stream_ptr(dev)
+        ctx.reduction, ctx.ignore_index = reduction, int(ignore_index)
+        if reduction == "none":
+            out = torch.empty((b,) + tuple(x.shape[2:]), dtype=torch.float32, device=dev)
+            _lib.check(h.dct_ce_fwd_f32(x.data_ptr(), lab.data_ptr(), c, b, hw, _ptr(w), int(ignore_index),
+                                        out.data_ptr(), None, fl, ws, s), "dct_ce_fwd_f32")
+            if dice_counts is not None:
+                _lib.check(h.dct_dice_counts_f32(x.data_ptr(), lab.data_ptr(), c, b, hw, dice_counts.data_ptr(), 1, fl, s),
+                           "dct_dice_counts_f32")
+            _runtime.after_call(st)
+            ctx.save_for_backward(x, lab, *([w] if w is not None else []))
+            ctx.grad = None
+            return out
+        total = torch.empty(1, dtype=torch.float64, device=dev)
+        inv = None        # float32 device scalar 1/W ('mean' with a data-dependent denominator)
+        gconst = 1.0
+        if reduction == "mean":
+            if n_global is not None:
+                gconst = 1.0 / float(n_global)
+            elif w is None and dice_counts is not None:
+                # the fused meter asserts every label in [0,C) (class2one_hot, utils/utils.py:190; raised through
+                # the label flag), so no pixel is ignored and W is the pixel count: no histogram pass
+                gconst = 1.0 / float(b * hw)
+            else:
+                inv64 = 1.0 / _ce_weight_sum(lab, c, ignore_index, w, st, dev)
+                inv = inv64.to(torch.float32).reshape(1)
+        if ctx.needs_input_grad[0]:
+            grad = torch.empty_like(x)
+            _lib.check(h.dct_ce_fwdbwd_f32(x.data_ptr(), lab.data_ptr(), c, b, hw, _ptr(w), int(ignore_index),
+                                           _ptr(inv), gconst, None, total.data_ptr(), grad.data_ptr(),
+                                           _ptr(dice_counts), fl, ws, s), "dct_ce_fwdbwd_f32")
+            ctx.grad = grad
+        else:
+            _lib.check(h.dct_ce_fwd_f32(x.data_ptr(), lab.data_ptr(), c, b, hw, _ptr(w), int(ignore_index), None,
+                                        total.data_ptr(), fl, ws, s), "dct_ce_fwd_f32")
+            if dice_counts is not None:
+                _lib.check(h.dct_dice_counts_f32(x.data_ptr(), lab.data_ptr(), c, b, hw, dice_counts.data_ptr(), 1, fl, s),
+                           "dct_dice_counts_f32")
+            ctx.grad = None
+        _runtime.after_call(st)
+        if inv is not None:
+            return (total * inv.to(torch.float64)).to(torch.float32).reshape(())
+        return (total * gconst).to(torch.float32).reshape(())
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        g = g.contiguous().to(torch.float32)
+        h = _lib.lib()
+        if ctx.reduction == "none":
+            x, lab = ctx.saved_tensors[:2]
+            w = ctx.saved_tensors[2] if len(ctx.saved_tensors) > 2 else None
+            b, c, hw = _bchw(x)
+            grad = torch.empty_like(x)
+            _lib.check(h.dct_ce_bwd_f32(x.data_ptr(), lab.data_ptr(), c, b, hw, _ptr(w), ctx.ignore_index, g.data_ptr(),
+                                        None, 1.0, grad.data_ptr(), None, _runtime.stream_ptr(x.device)),
+                       "dct_ce_bwd_f32")
+            return grad, None, None, None, None, None, None
+        grad = ctx.grad
+        ctx.grad = None
+        if grad is None:
+            raise RuntimeError("CrossEntropyLoss2d: backward called twice or without grad-requiring logits")
+        _lib.check(h.dct_scale_if_not_one_f32(grad.data_ptr(), grad.numel(), g.data_ptr(),
+                                              _runtime.stream_ptr(grad.device)), "dct_scale_if_not_one_f32")
+        return grad, None, None, None, None, None, None
+
+
+class CrossEntropyLoss2d(nn.Module):
+    """Drop-in for ``CrossEntropyLoss2d`` (loss.py:12-25): ``NLLLoss(weight, ignore_index)(log_softmax(x,1), t)``.
+
+    Same ctor (``weight=None, reduce=True, size_average=True, ignore_index=255``) and call
+    (``forward(outputs[B,C,H,W], targets[B,H,W] int64)``).  The loss and its gradient come from one
+    pass over the logits; ``loss.backward()`` costs no further pass for the default reductions."""
+
+    def __init__(self, weight=None, reduce=True, size_average=True, ignore_index=255):
+        super().__init__()
+        self.ignore_index = ignore_index
+        self.reduction = "none" if not reduce else ("mean" if size_average else "sum")
+        if weight is not None:
+            self.register_buffer("weight", torch.as_tensor(weight, dtype=torch.float32).clone())
+        else:
+            self.weight = None
+
+    def forward(self, outputs: torch.Tensor, targets: torch.Tensor):
+        return _CEFn.apply(outputs, targets, self.weight, int(self.ignore_index), self.reduction, None, None)
+
+
+def supervised_from_logits(logits: torch.Tensor, gt: torch.Tensor, weight: Optional[torch.Tensor] = None,
+                           ignore_index: int = 255, dice_counts: Optional[torch.Tensor] = None,
+                           n_global: Optional[int] = None) -> torch.Tensor:
+    """``CrossEntropyLoss2d(weight)(logits, gt.squeeze(1))`` and ``DiceMeter.add(logits, gt)`` in ONE pass.
+
+    The two consecutive lines of the labeled loop (cotraining_totalloss.py:211-212) read the same
+    logits and labels; here one kernel launch produces the mean cross-entropy, its gradient
+    (upstream 1/W folded in) and, if ``dice_counts`` (int64 ``[B,C,3]``, accumulated into) is given,
+    the (I, G, P) counts of ``argmax softmax(logits)`` against ``gt`` (feed them to
+    ``DiceMeter.add_counts``).  ``n_global``: pixel count over all data-parallel ranks for the
+    unweighted global mean (defaults to the local denominator)."""
+    w = None if weight is None else torch.as_tensor(weight, dtype=torch.float32)
+    return _CEFn.apply(logits, gt, w, int(ignore_index), "mean", n_global, dice_counts)
+
+
+# ------------------------------------------------------------------------------------------------
+# registry (loss/__init__.py:6-16); the entries that live on the hot path
+# ------------------------------------------------------------------------------------------------
+LOSS = {"jsd": JSD_2D, "cross_entropy": CrossEntropyLoss2d}
 
 
 def get_loss_fn(name: str, **kwargs):

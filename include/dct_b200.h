@@ -197,6 +197,47 @@ DCT_API int dct_confusion_f32(const float* x, const int64_t* labels, int C, int6
 DCT_API int dct_confusion_labels_i64(const int64_t* pred, const int64_t* labels, int64_t n, int C,
                              int64_t* conf, int32_t* flags, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Supervised branch: pixel-wise cross-entropy fused with the Dice counting of the
+ * same (logits, labels) pair.
+ * Replaces CrossEntropyLoss2d.forward (generalframework/loss/loss.py:12-25) =
+ *   nn.NLLLoss(weight, ignore_index)(F.log_softmax(outputs, 1), targets)
+ * as called at generalframework/trainer/cotraining_totalloss.py:211 (and :294, trainer.py:171), and the
+ * diceMeters[k].add(pred, gt) of the next line (:212) when `dice_counts` is given.
+ *   l_i = -w[t_i] * log_softmax(x_i)[t_i]  (0 where t_i == ignore_index; w = 1 without class_weight)
+ *   d l_i / d x_ic = w[t_i] * (softmax(x_i)_c - [c == t_i])
+ * The 'mean' reduction divides by W = sum_i w[t_i] over the non-ignored pixels: W comes from
+ * dct_label_hist_i64 (8 B/pixel) or is simply the pixel count when there is neither a class weight nor an
+ * ignored pixel; the caller folds 1/W into the upstream (gscalar / gconst).
+ * `class_weight`: device float[C] or NULL.  Labels outside [0,C) other than ignore_index are counted in
+ * flags[DCT_FLAG_LABEL] (PyTorch raises "Target out of bounds") and treated as ignored.
+ * ------------------------------------------------------------------------------------------ */
+
+/* hist int64[C+2], overwritten: hist[c] = #{label == c} (c < C, the ignore_index excluded even if it is < C),
+ * hist[C] = #{label == ignore_index}, hist[C+1] = #{other labels outside [0,C)}. */
+DCT_API int dct_label_hist_i64(const int64_t* labels, int64_t n, int C, int64_t ignore_index, int64_t* hist,
+                               void* stream);
+
+/* forward: map (nullable) [B,HW] = l_i; sum (nullable) double[1] = sum_i l_i (bit-reproducible). */
+DCT_API int dct_ce_fwd_f32(const float* logits, const int64_t* labels, int C, int64_t B, int64_t HW,
+                           const float* class_weight, int64_t ignore_index, float* map, double* sum,
+                           int32_t* flags, void* workspace, void* stream);
+
+/* backward: grad_logits = upstream * d l_i / d x  (upstream as "dct_upstream": gmap for reduce=False). */
+DCT_API int dct_ce_bwd_f32(const float* logits, const int64_t* labels, int C, int64_t B, int64_t HW,
+                           const float* class_weight, int64_t ignore_index, const float* gmap,
+                           const float* gscalar, float gconst, float* grad_logits, int32_t* flags, void* stream);
+
+/* one pass: forward (map / sum nullable) AND grad_logits = gconst * (gscalar ? *gscalar : 1) * d l_i / d x.
+ * If dice_counts != NULL (int64 [B][C][3], ACCUMULATED into) the Dice counts (I, G, P) of
+ * argmax softmax(logits) against `labels` are produced from the same read, exactly as
+ * dct_dice_counts_f32 (every label outside [0,C), the ignore_index included, then raises
+ * flags[DCT_FLAG_LABEL] as DiceMeter.add's class2one_hot assert does). */
+DCT_API int dct_ce_fwdbwd_f32(const float* logits, const int64_t* labels, int C, int64_t B, int64_t HW,
+                              const float* class_weight, int64_t ignore_index, const float* gscalar, float gconst,
+                              float* map, double* sum, float* grad_logits, int64_t* dice_counts, int32_t* flags,
+                              void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,6 +44,8 @@ def lib():
         _lib.dcto_simplex_violations_f32.restype = _i64
         _lib.dcto_simplex_violations_f64.restype = _i64
         _lib.dcto_confusion_from_labels.restype = _i64
+        _lib.dcto_ce_f32.restype = _i64
+        _lib.dcto_ce_f64.restype = _i64
         _lib.dcto_spec_expf.restype = C.c_float
         _lib.dcto_spec_expf.argtypes = [C.c_float]
         _lib.dcto_num_threads.restype = _int
@@ -209,6 +211,38 @@ def vat_apply(img, d, eps):
 def _labels(gt, b, hw):
     g = np.ascontiguousarray(gt, dtype=np.int64).reshape(b, hw)
     return g
+
+
+def cross_entropy(z, gt, weight=None, ignore_index=255, reduction="mean", upstream=1.0, gout=None,
+                  want_grad=True, n_global=None):
+    """CrossEntropyLoss2d(weight, ignore_index)(z, gt) (loss/loss.py:12-25) and its autograd gradient.
+
+    reduction 'mean' | 'sum' | 'none'.  Returns (loss, grad_z, n_bad): loss is a python float for
+    mean/sum and a [B,H,W] map for 'none' (then ``gout`` [B,H,W] is the upstream of the map).
+    ``n_global`` replaces the 'mean' denominator W (data-parallel global mean with unit weights)."""
+    dt = _dt(z); z = _c(z, dt); b, c, hw = _bchw(z); g = _labels(gt, b, hw)
+    cw = None if weight is None else _c(np.asarray(weight), dt)
+    f = getattr(lib(), "dcto_ce" + _suf(dt))
+    sums = np.zeros(2, dtype=np.float64)
+    m = np.empty((b,) + z.shape[2:], dtype=dt)
+    nul = _p(None)
+    bad = int(f(_ptr(z), _ptr(g), nul if cw is None else _ptr(cw), _i64(int(ignore_index)), _i64(b), _int(c), _i64(hw),
+                _ptr(m), _ptr(sums), _real(dt, 1.0), nul, nul))
+    W = float(sums[1]) if n_global is None else float(n_global)
+    if reduction == "mean":
+        with np.errstate(invalid="ignore", divide="ignore"):   # every pixel ignored: 0/0 = NaN as in ATen
+            loss, gs = float(np.float64(sums[0]) / np.float64(W)), float(np.float64(upstream) / np.float64(W))
+    elif reduction == "sum":
+        loss, gs = sums[0], upstream
+    else:
+        loss, gs = m, 1.0
+    gz = None
+    if want_grad:
+        gz = np.empty_like(z)
+        go = None if (reduction != "none" or gout is None) else _c(gout, dt)
+        f(_ptr(z), _ptr(g), nul if cw is None else _ptr(cw), _i64(int(ignore_index)), _i64(b), _int(c), _i64(hw),
+          nul, nul, _real(dt, gs), nul if go is None else _ptr(go), _ptr(gz))
+    return loss, gz, bad
 
 
 def predict(x, mode="dice"):

@@ -21,6 +21,13 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_sup():
+    """Supervised-branch fixtures (oracle/make_golden_sup.py): CrossEntropyLoss2d + the meter of the same line."""
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "reference_golden_sup.npz"))
+
+
+@pytest.fixture(scope="session")
 def oracle():
     import oracle as O  # oracle/oracle.py (test infrastructure)
     O.build()

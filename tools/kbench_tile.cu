@@ -12,6 +12,7 @@ namespace dct {
 }
 // pull in the KL ops (defined in dct_kl.cu) without its extern "C" part clashing: include the TU
 #include "dct_kl.cu"
+#include "dct_ce.cu"
 static bool g_pdl = true;
 static int g_pool_div = 0;
 static bool g_static = false;  // 1: no workspace -> static round-robin tile schedule (and no loss sum)
@@ -73,7 +74,7 @@ void run(const char* tag, int64_t B, int64_t HW, int reps, double bytes_per_px, 
         if (labels) { long long* l; CK(cudaMalloc(&l, (size_t)B * HW * 8)); allocs.push_back(l); filll<<<1024, 256>>>(l, (size_t)B * HW, CT); a.labels = (const int64_t*)l; }
         a.counts = counts; a.count_view_stride = B * CT * 3;
         a.HW = HW; a.map = nullptr; a.sum = Op::HAS_MAP ? sum : nullptr; a.up = Upstream{nullptr, nullptr, 1e-6f};
-        a.eps = 1e-10f; a.flags = nullptr; a.ws = ws; a.force_static = g_static ? 1 : 0; a.pool_div = g_pool_div;
+        a.eps = 1e-10f; a.ignore_index = 255; a.class_w = nullptr; a.flags = nullptr; a.ws = ws; a.force_static = g_static ? 1 : 0; a.pool_div = g_pool_div;
         a.tiles_per_image = (int)((HW + Cfg::TP - 1) / Cfg::TP); a.num_tiles = (int)(a.tiles_per_image * B);
         sets[r] = a;
     }
@@ -153,7 +154,7 @@ int main(int argc, char** argv) {
         sweep<DiceOpB, 4>("dice", B, HW, reps, 24, true);
         sweep<JsdOp<2, true, kFwdBwd, true>, 2>("jsd+dice c3", B / 4, 262144, reps, 40, true);
         sweep<JsdOp<2, true, kFwdBwd, true>, 4>("jsd+dice c1x8", B, 65536, reps, 72, true);
-    } else {
+    } else if (which <= 2) {
         // Cityscapes-like: C = 19, 512x1024 images
         const int64_t HWc = 512 * 1024;
         using J19 = JsdOp<2, true, kFwdBwd, false>;
@@ -191,6 +192,62 @@ int main(int argc, char** argv) {
         run_auto<JsdOp<2, true, kFwdBwd, false>, 19, 2, 6, 1>("jsd K2 C19", B, HWc, reps, 304, false);
         run_auto<JsdOp<2, true, kFwd, false>, 19, 2, 4, 1>("jsdfwd K2 C19", B, HWc, reps, 152, false);
         run_auto<JsdOp<2, true, kFwd, false>, 19, 2, 8, 1>("jsdfwd K2 C19", B, HWc, reps, 152, false);
+    }
+    if (which == 3) {
+        // rows = 38 family (Cityscapes C = 19, two tensors) and the C = 19 cross-entropy: consumer warps vs stages
+        const int64_t HWc = 512 * 1024;
+        using J19 = JsdOp<2, true, kFwdBwd, false>;
+        run_auto<J19, 19, 2, 5, 1>("jsd K2 C19", B, HWc, reps, 304, false);
+        run_auto<J19, 19, 2, 6, 1>("jsd K2 C19", B, HWc, reps, 304, false);
+        run_auto<J19, 19, 2, 7, 1>("jsd K2 C19", B, HWc, reps, 304, false);
+        run_auto<J19, 19, 2, 8, 1>("jsd K2 C19", B, HWc, reps, 304, false);
+        run_auto<J19, 19, 2, 3, 2>("jsd K2 C19", B, HWc, reps, 304, false);
+        run_auto<J19, 19, 2, 4, 2>("jsd K2 C19", B, HWc, reps, 304, false);
+        run_auto<KlFromLogits, 19, 2, 6, 1>("klfromlogits19", B, HWc, reps, 228, false);
+        run_auto<KlFromLogits, 19, 2, 8, 1>("klfromlogits19", B, HWc, reps, 228, false);
+        run_auto<KlFromLogits, 19, 2, 3, 2>("klfromlogits19", B, HWc, reps, 228, false);
+        run_auto<KlFromLogits, 19, 2, 6, 2>("klfromlogits19", B, HWc, reps, 228, false);
+        run_auto<KlLogit<true>, 19, 2, 6, 1>("kllogit19", B, HWc, reps, 304, false);
+        run_auto<KlLogit<true>, 19, 2, 8, 1>("kllogit19", B, HWc, reps, 304, false);
+        run_auto<KlLogit<true>, 19, 2, 3, 2>("kllogit19", B, HWc, reps, 304, false);
+        using CE = CeOp<true, false, false>;
+        run_auto<CE, 19, 2, 4, 1>("ce C19", B, HWc, reps, 160, true);
+        run_auto<CE, 19, 2, 8, 1>("ce C19", B, HWc, reps, 160, true);
+        run_auto<CE, 19, 2, 4, 2>("ce C19", B, HWc, reps, 160, true);
+        run_auto<CE, 19, 2, 6, 2>("ce C19", B, HWc, reps, 160, true);
+        run_auto<CE, 19, 4, 4, 2>("ce C19", B, HWc, reps, 160, true);
+        using J3 = JsdOp<3, true, kFwdBwd, false>;
+        run_auto<J3, 19, 2, 5, 1>("jsd K3 C19", B, HWc, reps, 456, false);
+        run_auto<J3, 19, 2, 6, 1>("jsd K3 C19", B, HWc, reps, 456, false);
+    }
+    if (which == 5) {
+        const int64_t HWc = 512 * 1024;
+        using JF = JsdOp<2, true, kFwd, false>;
+        run_auto<JF, 19, 2, 8, 1>("jsdfwd K2 C19", B, HWc, reps, 152, false);
+        run_auto<JF, 19, 2, 3, 2>("jsdfwd K2 C19", B, HWc, reps, 152, false);
+        run_auto<JF, 19, 2, 4, 2>("jsdfwd K2 C19", B, HWc, reps, 152, false);
+        run_auto<JF, 19, 2, 6, 1>("jsdfwd K2 C19", B, HWc, reps, 152, false);
+        using J4 = JsdOp<4, true, kFwdBwd, false>;
+        run_auto<J4, 19, 1, 6, 1>("jsd K4 C19", B, HWc, reps, 608, false);
+        run_auto<J4, 19, 1, 3, 2>("jsd K4 C19", B, HWc, reps, 608, false);
+        run_auto<J4, 19, 1, 4, 2>("jsd K4 C19", B, HWc, reps, 608, false);
+        run_auto<J4, 19, 1, 5, 1>("jsd K4 C19", B, HWc, reps, 608, false);
+        using J3 = JsdOp<3, true, kFwdBwd, false>;
+        run_auto<J3, 19, 2, 5, 1>("jsd K3 C19", B, HWc, reps, 456, false);
+        run_auto<J3, 19, 1, 6, 2>("jsd K3 C19", B, HWc, reps, 456, false);
+        run_auto<J3, 19, 1, 8, 1>("jsd K3 C19", B, HWc, reps, 456, false);
+        using CF = CeOp<false, false, false>;
+        run_auto<CF, 19, 2, 4, 2>("cefwd C19", B, HWc, reps, 84, true);
+        run_auto<CF, 19, 4, 4, 2>("cefwd C19", B, HWc, reps, 84, true);
+        run_auto<CF, 19, 2, 8, 1>("cefwd C19", B, HWc, reps, 84, true);
+    }
+    if (which == 4) {
+        // ACDC-sized cross-entropy + Dice (C = 4, 256x256) and the plain variant
+        using CED = CeOp<true, true, false>;
+        using CE = CeOp<true, false, false>;
+        sweep<CED, 4>("ce+dice C4", B, HW, reps, 40, true);
+        sweep<CE, 4>("ce C4", B, HW, reps, 40, true);
+        sweep<CED, 2>("ce+dice C2", B / 4, 262144, reps, 24, true);
     }
     return 0;
 }
