@@ -14,7 +14,7 @@ _CSRC = os.path.join(_PKG, "csrc")
 
 OK = 0
 IN_PROBS, IN_LOGITS = 0, 1
-FLAG_SIMPLEX, FLAG_LABEL, FLAG_PRED, NUM_FLAGS = 0, 1, 2, 4
+FLAG_SIMPLEX, FLAG_LABEL, FLAG_PRED, FLAG_ONEHOT, NUM_FLAGS = 0, 1, 2, 3, 4
 MAX_VIEWS, MAX_CLASSES = 8, 64
 
 _p, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
@@ -49,6 +49,10 @@ _SIGNATURES = {
     "dct_ce_fwd_f32": [_p, _p, _i, _i64, _i64, _p, _i64, _p, _p, _p, _p, _p],
     "dct_ce_bwd_f32": [_p, _p, _i, _i64, _i64, _p, _i64, _p, _p, _f, _p, _p, _p],
     "dct_ce_fwdbwd_f32": [_p, _p, _i, _i64, _i64, _p, _i64, _p, _f, _p, _p, _p, _p, _p, _p, _p],
+    "dct_classmap_f32": [_p, _i, _i64, _i64, _i, _p, _p, _p, _p, _p],
+    "dct_onehot_from_labels_i64": [_p, _i, _i64, _i64, _p, _p, _p],
+    "dct_onehot_dice_counts_i32": [_p, _p, _i, _i64, _i64, _p, _p, _p],
+    "dct_vote_f32": [_p, _i, _i, _i64, _i64, _i, _p, _p, _p, _p],
 }
 _RESTYPES = {"dct_error_string": C.c_char_p, "dct_last_cuda_error": C.c_char_p, "dct_workspace_bytes": C.c_size_t}
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

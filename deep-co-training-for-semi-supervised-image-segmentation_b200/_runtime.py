@@ -27,6 +27,7 @@ _FLAG_MESSAGES = {
     _lib.FLAG_SIMPLEX: "input is not a probability simplex along dim 1 (utils.simplex)",
     _lib.FLAG_LABEL: "labels outside [0, C) (class2one_hot)",
     _lib.FLAG_PRED: "predictions outside [0, C) (ConfusionMatrix bincount size)",
+    _lib.FLAG_ONEHOT: "tensor is not one-hot along dim 1 (utils.one_hot)",
 }
 
 

@@ -24,6 +24,9 @@
  *      flags[DCT_FLAG_SIMPLEX]  += #pixels whose class sum fails the reference's
  *                                  utils.simplex allclose(sum,1) (utils/utils.py:142-151)
  *      flags[DCT_FLAG_LABEL]    += #labels outside [0,C) (class2one_hot's assert, utils.py:190)
+ *      flags[DCT_FLAG_PRED]     += #integer predictions outside [0,C) (ConfusionMatrix's bincount assert)
+ *      flags[DCT_FLAG_ONEHOT]   += #violations of utils.one_hot (a value outside {0,1}, or a pixel whose class
+ *                                  column does not hold exactly one 1; utils.py:154-161)
  *    May be NULL (checks compiled out of the launch).
  *  - Upstream gradient of a [B,HW] map output ("dct_upstream"): the per-pixel
  *    incoming gradient is   gconst * (gscalar ? *gscalar : 1) * (gmap ? gmap[b,i] : 1).
@@ -57,7 +60,7 @@ enum {
     DCT_ERR_NO_DEVICE = -5     /* no CUDA device / not an sm_100 device */
 };
 
-enum { DCT_FLAG_SIMPLEX = 0, DCT_FLAG_LABEL = 1, DCT_FLAG_PRED = 2, DCT_NUM_FLAGS = 4 };
+enum { DCT_FLAG_SIMPLEX = 0, DCT_FLAG_LABEL = 1, DCT_FLAG_PRED = 2, DCT_FLAG_ONEHOT = 3, DCT_NUM_FLAGS = 4 };
 
 /* input kind of the K view tensors handed to the JSD entry points */
 enum { DCT_IN_PROBS = 0, DCT_IN_LOGITS = 1 };
@@ -237,6 +240,43 @@ DCT_API int dct_ce_fwdbwd_f32(const float* logits, const int64_t* labels, int C,
                               const float* class_weight, int64_t ignore_index, const float* gscalar, float gconst,
                               float* map, double* sum, float* grad_logits, int64_t* dice_counts, int32_t* flags,
                               void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Class maps, one-hot tensors and the functional Dice on one-hot inputs (SURVEY.md 8a11 / 8b "Functional Dice").
+ * Replaces generalframework/utils/utils.py: pred2class :73-80, probs2class :178-184, class2one_hot :187-198,
+ * probs2one_hot :201-207, predlogit2one_hot :210-217, one_hot :154-161, intersection :164-168,
+ * meta_dice / dice_coef / dice_batch :221-235 (called by trainer/trainer.py:171-175,222-227).
+ * ------------------------------------------------------------------------------------------ */
+
+/* scores [B,C,HW] -> class map and/or one-hot (each output nullable, at least one given):
+ *   cls int64 [B,HW], cls_u8 uint8 [B,HW] (save_images' uint8 PNG plane, utils.py:238-250), onehot int32 [B,C,HW].
+ *   mode 0: raw arg-max with torch.max semantics (first index on ties, NaN maximal)      -- pred2class
+ *   mode 1: arg-max of softmax(x) in the pinned Dice arithmetic (DESIGN.md "Dice spec")  -- predlogit2one_hot
+ *   mode 2: mode 0 + flags[DCT_FLAG_SIMPLEX] on columns failing utils.simplex             -- probs2class / probs2one_hot */
+DCT_API int dct_classmap_f32(const float* x, int C, int64_t B, int64_t HW, int mode, int64_t* cls, uint8_t* cls_u8,
+                             int32_t* onehot, int32_t* flags, void* stream);
+
+/* class2one_hot: int64 labels [B,HW] -> int32 one-hot [B,C,HW]; labels outside [0,C) are counted in
+ * flags[DCT_FLAG_LABEL] (the reference's sset assert) and produce an all-zero column. */
+DCT_API int dct_onehot_from_labels_i64(const int64_t* labels, int C, int64_t B, int64_t HW, int32_t* onehot,
+                                       int32_t* flags, void* stream);
+
+/* meta_dice's counting on int32 one-hot tensors [B,C,HW]: counts int64 [B][C][3] = (sum label&pred, sum label,
+ * sum pred), OVERWRITTEN (nullable: predicate only); flags[DCT_FLAG_ONEHOT] += violations of utils.one_hot in
+ * either tensor.  pred_onehot may be NULL (one_hot(label) alone).  dct_dice_from_counts_f32 finishes
+ * dice_coef (batch_sum = 0) / dice_batch (batch_sum = 1). */
+DCT_API int dct_onehot_dice_counts_i32(const int32_t* label_onehot, const int32_t* pred_onehot, int C, int64_t B,
+                                       int64_t HW, int64_t* counts, int32_t* flags, void* stream);
+
+/* Ensemble voting over K views [B,C,HW] (HOST array of K device pointers) -- SURVEY.md 8f.4, replaces
+ * Ensembleway._softVoting / _hardVoting (Summary.py:88-120).
+ *   hard = 0: out (nullable) [B,C,HW] = ((x_0 + x_1) + ...) / K; cls / cls_u8 (nullable) = raw arg-max of the mean
+ *   hard = 1: per-view raw arg-max, most voted class per pixel (smallest class on ties, np.bincount(...).argmax());
+ *             out (nullable) = one-hot of the winner as float; cls / cls_u8 (nullable) = the winner.
+ * (The reference's hard vote concatenates the views along the batch axis, i.e. it assumes B = 1; here every
+ * image of the batch is voted on its own, which is the same thing at B = 1.) */
+DCT_API int dct_vote_f32(const float* const* views, int K, int C, int64_t B, int64_t HW, int hard, float* out,
+                         int64_t* cls, uint8_t* cls_u8, void* stream);
 
 #ifdef __cplusplus
 }

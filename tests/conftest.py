@@ -28,6 +28,13 @@ def golden_sup():
 
 
 @pytest.fixture(scope="session")
+def golden_aux():
+    """Class-map / one-hot / ensemble / kappa fixtures (oracle/make_golden_aux.py)."""
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "reference_golden_aux.npz"))
+
+
+@pytest.fixture(scope="session")
 def oracle():
     import oracle as O  # oracle/oracle.py (test infrastructure)
     O.build()
