@@ -9,13 +9,17 @@ their existing call sites:
   get_loss_fn('jsd' | 'cross_entropy')     -> loss.LOSS[...]                  (loss/__init__.py:6-16)
   KL_Divergence_2D(reduce=True)(adv, real) -> trainer-module globals           (cotraining_totalloss.py:13,392)
   VATGenerator / FSGMGenerator             -> trainer-module globals           (cotraining_totalloss.py:15)
-  DiceMeter / IoU                          -> metrics package + trainer globals (cotraining_totalloss.py:18)
+  DiceMeter / IoU / KappaMetrics           -> metrics package + trainer globals (cotraining_totalloss.py:18)
+  dice_coef / dice_batch / class2one_hot / probs2one_hot / pred2class / ... (the star-imported helpers of
+  utils/utils.py:73-235)                   -> trainer-module globals ONLY      (trainer/trainer.py:171-175,222-227)
+The helper functions are rebound only inside ``<package>.trainer.*``: the dataset code calls ``class2one_hot`` on
+host tensors inside DataLoader workers (utils.py:188), which must keep the reference's CPU implementation.
 ``uninstall()`` restores the originals.
 """
 import importlib
 import sys
 
-from . import generators, loss, metrics
+from . import ensemble, generators, loss, metrics, utils
 
 _REBIND = {
     "JSD_2D": loss.JSD_2D, "JSD": loss.JSD, "Entropy_2D": loss.Entropy_2D, "Entropy": loss.Entropy,
@@ -23,7 +27,11 @@ _REBIND = {
     "KL_div": loss.KL_div, "CrossEntropyLoss2d": loss.CrossEntropyLoss2d,
     "FSGMGenerator": generators.FSGMGenerator, "VATGenerator": generators.VATGenerator,
     "DiceMeter": metrics.DiceMeter, "IoU": metrics.IoU, "ConfusionMatrix": metrics.ConfusionMatrix,
+    "KappaMetrics": ensemble.KappaMetrics, "Kappa2Annotator": ensemble.Kappa2Annotator,
 }
+_REBIND_TRAINER_FUNCS = {name: getattr(utils, name) for name in (
+    "simplex", "one_hot", "uniq", "sset", "intersection", "union", "pred2class", "probs2class", "class2one_hot",
+    "probs2one_hot", "predlogit2one_hot", "meta_dice", "dice_coef", "dice_batch")}
 _saved = []
 
 
@@ -44,6 +52,13 @@ def install(package: str = "generalframework") -> int:
                 _saved.append((mod, name, cur))
                 setattr(mod, name, repl)
                 n += 1
+        if modname.startswith(package + ".trainer"):
+            for name, repl in _REBIND_TRAINER_FUNCS.items():
+                cur = mod.__dict__.get(name)
+                if cur is not None and cur is not repl and callable(cur):
+                    _saved.append((mod, name, cur))
+                    setattr(mod, name, repl)
+                    n += 1
         reg = mod.__dict__.get("LOSS")
         if isinstance(reg, dict) and "jsd" in reg:
             for key, repl in (("jsd", loss.JSD_2D), ("cross_entropy", loss.CrossEntropyLoss2d)):

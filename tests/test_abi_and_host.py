@@ -122,6 +122,11 @@ def test_install_rebinds_reference_call_sites():
         assert gl.get_loss_fn("jsd").__class__ is dct_b200.JSD_2D          # registry path, loss/__init__.py:12-16
         assert ct.KL_Divergence_2D is dct_b200.KL_Divergence_2D            # trainer global, cotraining_totalloss.py:13
         assert ct.DiceMeter is dct_b200.DiceMeter and ct.FSGMGenerator is dct_b200.FSGMGenerator
+        # functional Dice of the supervised baseline (trainer/trainer.py:171-175): rebound in trainer modules only
+        import generalframework.trainer.trainer as tr
+        import generalframework.utils.utils as gu
+        assert tr.dice_coef is dct_b200.utils.dice_coef and tr.probs2one_hot is dct_b200.utils.probs2one_hot
+        assert gu.class2one_hot is not dct_b200.utils.class2one_hot       # dataset workers keep the host version
     finally:
         dct_b200.uninstall()
     assert gl.LOSS["jsd"] is orig and ct.DiceMeter is not dct_b200.DiceMeter

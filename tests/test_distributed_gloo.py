@@ -71,3 +71,47 @@ def test_shard_batch_covers_everything():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _report_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK="0")
+    from dct_b200.cotrain import DeviceReport, init_distributed
+    import oracle as O
+    assert init_distributed("gloo") == (rank, world, 0)
+    g = torch.Generator().manual_seed(1234)
+    K, B, C, H, W = 2, 6, 4, 16, 16
+    z = [3 * torch.randn(B, C, H, W, generator=g) for _ in range(K)]
+    gt = torch.randint(0, C, (B, 1, H, W), generator=g)
+    lo, hi = (rank * B // world, (rank + 1) * B // world)
+    rep = DeviceReport(K, C, torch.device("cpu"))
+    for k in range(K):   # what CoTrainStep.step feeds it: the fused kernel's per-image counts of this rank's shard
+        counts, _ = O.dice_counts(z[k][lo:hi].numpy(), gt[lo:hi].numpy())
+        rep.add_counts("unlab", k, torch.from_numpy(counts))
+    rep.add_losses([torch.tensor(1.0 + rank), torch.tensor(2.0)], torch.tensor(0.25 * (rank + 1)), None)
+    out = rep.reduce()
+    q.put((rank, out["unlab_dice"].numpy(), out["losses"].numpy(), out["world"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_device_report_reduces_to_the_unsharded_batch_dice():
+    """CoTrainStep's reporting: per-rank integer counters + loss sums -> ONE all-reduce -> the Dice of
+    the un-sharded batch ('3d' arithmetic, exact) and the mean of the per-rank losses."""
+    import oracle as O
+    world, port = 2, 31500 + os.getpid() % 2000
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_report_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    g = torch.Generator().manual_seed(1234)
+    K, B, C, H, W = 2, 6, 4, 16, 16
+    z = [3 * torch.randn(B, C, H, W, generator=g) for _ in range(K)]
+    gt = torch.randint(0, C, (B, 1, H, W), generator=g)
+    want = np.stack([O.dice_from_counts(O.dice_counts(z[k].numpy(), gt.numpy())[0].sum(0, keepdims=True))[0] for k in range(K)])
+    for rank, dice, losses, w in res:
+        assert w == 2 and np.array_equal(dice, want)
+        assert np.allclose(losses, [1.5, 2.0, 0.375, 0.0])
