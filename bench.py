@@ -34,6 +34,14 @@ METRIC = "consistency-loss pixels/sec (fwd+bwd)"
 UNIT = "pixels/s"
 
 
+def load_traffic(workload):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[workload]
+    except Exception:
+        return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -306,7 +314,8 @@ def run_ours(args, wl):
                 "launches_timed": rounds * R,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "frac_of_8TBps_nominal": achieved / 8000.0, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms, "traffic": None,
+                "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms,
+                "traffic": (load_traffic(args.workload) or {}).get("bytes"), "traffic_detail": load_traffic(args.workload),
                 "step_algorithmic_bytes": step.algorithmic_bytes(),
                 "step_achieved_GBps": sum(step.algorithmic_bytes().values()) / (ms_total * 1e-3 / args.steps) / 1e9}
 

@@ -13,6 +13,7 @@ _SO = os.path.join(_PKG, "libdct_b200.so")
 _CSRC = os.path.join(_PKG, "csrc")
 
 OK = 0
+ERR_UNSUPPORTED = -2
 IN_PROBS, IN_LOGITS = 0, 1
 FLAG_SIMPLEX, FLAG_LABEL, FLAG_PRED, FLAG_ONEHOT, NUM_FLAGS = 0, 1, 2, 3, 4
 MAX_VIEWS, MAX_CLASSES = 8, 64
@@ -53,6 +54,10 @@ _SIGNATURES = {
     "dct_onehot_from_labels_i64": [_p, _i, _i64, _i64, _p, _p, _p],
     "dct_onehot_dice_counts_i32": [_p, _p, _i, _i64, _i64, _p, _p, _p],
     "dct_vote_f32": [_p, _i, _i, _i64, _i64, _i, _p, _p, _p, _p],
+    "dct_jsd_fwdbwd_bf16": [_p, _i, _i, _i64, _i64, _f, _p, _p, _p, _p, _p, _p, _p, _p],
+    "dct_kl_logit_bf16": [_p, _p, _i, _i64, _i64, _p, _p, _i, _p, _p, _f, _p, _p, _p, _p],
+    "dct_kl_from_logits_fwdbwd_bf16": [_p, _p, _i, _i64, _i64, _f, _f, _p, _p, _p, _p, _p, _p],
+    "dct_ce_fwdbwd_bf16": [_p, _p, _i, _i64, _i64, _p, _i64, _p, _f, _p, _p, _p, _p, _p, _p, _p],
 }
 _RESTYPES = {"dct_error_string": C.c_char_p, "dct_last_cuda_error": C.c_char_p, "dct_workspace_bytes": C.c_size_t}
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

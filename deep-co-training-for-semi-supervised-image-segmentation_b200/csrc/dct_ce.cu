@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256) ce_kernel_rt(const CeArgs a) {
     grid_sum_to(acc, a.ws, a.sum, blockIdx.y * gridDim.x + blockIdx.x, gridDim.x * gridDim.y);
 }
 
-template <class Op>
+template <class Op, class ET = float>
 static int ce_tile(const CeArgs& c, int64_t B, unsigned long long* counts, cudaStream_t stream, bool& done) {
     done = false;
     TileArgs t{};
@@ -140,14 +140,14 @@ static int ce_tile(const CeArgs& c, int64_t B, unsigned long long* counts, cudaS
     t.HW = c.HW; t.map = c.map; t.sum = c.sum; t.up = c.up; t.eps = 0.0f; t.flags = c.flags; t.ws = c.ws;
     t.labels = c.labels; t.counts = counts; t.count_view_stride = B * c.C * 3;
     t.class_w = c.class_w; t.ignore_index = c.ignore_index;
-    if (!tile_eligible<Op>(t, B)) return DCT_OK;
+    if (!tile_eligible<Op, ET>(t, B)) return DCT_OK;
     int rc = DCT_ERR_UNSUPPORTED;
     switch (c.C) {
-        case 2: rc = tile_launch_ct<Op, 2>(t, B, stream); break;
-        case 3: rc = tile_launch_ct<Op, 3>(t, B, stream); break;
-        case 4: rc = tile_launch_ct<Op, 4>(t, B, stream); break;
+        case 2: rc = tile_launch_ct<Op, 2, ET>(t, B, stream); break;
+        case 3: rc = tile_launch_ct<Op, 3, ET>(t, B, stream); break;
+        case 4: rc = tile_launch_ct<Op, 4, ET>(t, B, stream); break;
         case 19:
-            if constexpr (Op::NDICE == 0) rc = tile_launch_ct<Op, 19>(t, B, stream);
+            if constexpr (Op::NDICE == 0) rc = tile_launch_ct<Op, 19, ET>(t, B, stream);
             break;
         default: break;
     }
@@ -263,5 +263,27 @@ extern "C" int dct_ce_fwdbwd_f32(const float* logits, const int64_t* labels, int
     if (dice_counts != nullptr)  // Dice counting of the same logits in its own launch (C > 4 or a non-tile shape)
         return dct_dice_counts_f32(logits, labels, C, B, HW, dice_counts, 1, flags, stream);
     return DCT_OK;
+}
+
+// bf16 logits / gradients (fp32 math, fp32 map / sum): the tile pipeline only; DCT_ERR_UNSUPPORTED for other shapes
+// (C not in {2,3,4,19}, HW % 8 != 0, misaligned rows, Dice counts with C > 4): the caller converts to float32 then.
+extern "C" int dct_ce_fwdbwd_bf16(const void* logits, const int64_t* labels, int C, int64_t B, int64_t HW,
+                                  const float* class_weight, int64_t ignore_index, const float* gscalar, float gconst,
+                                  float* map, double* sum, void* grad_logits, int64_t* dice_counts, int32_t* flags,
+                                  void* workspace, void* stream) {
+    if (logits == nullptr || labels == nullptr || grad_logits == nullptr || C < 1 || B < 1 || HW < 1) return DCT_ERR_BAD_ARG;
+    if (sum != nullptr && workspace == nullptr) return DCT_ERR_BAD_ARG;
+    if (C > DCT_MAX_CLASSES || B > 65535 || (dice_counts != nullptr && C > 4)) return DCT_ERR_UNSUPPORTED;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CeArgs c{reinterpret_cast<const float*>(logits), labels, class_weight, ignore_index, C, HW, map, sum,
+             reinterpret_cast<float*>(grad_logits), Upstream{nullptr, gscalar, gconst}, flags, static_cast<Workspace*>(workspace)};
+    bool done = false;
+    int rc;
+    if (dice_counts != nullptr)
+        rc = ce_tile<CeOp<true, true, false>, bf16>(c, B, reinterpret_cast<unsigned long long*>(dice_counts), s, done);
+    else
+        rc = ce_tile<CeOp<true, false, false>, bf16>(c, B, nullptr, s, done);
+    if (rc != DCT_OK) return rc;
+    return done ? DCT_OK : DCT_ERR_UNSUPPORTED;
 }
 #endif  // DCT_KBENCH

@@ -47,7 +47,7 @@ static int jsd_dispatch(const JsdCall& c) {
         case 4: rc = jsd_launch_k4(c); break;
         default: break;
     }
-    if (rc == DCT_ERR_UNSUPPORTED) rc = jsd_launch_rt(c);
+    if (rc == DCT_ERR_UNSUPPORTED && c.elem == 0) rc = jsd_launch_rt(c);
     return rc;
 }
 
@@ -91,4 +91,22 @@ extern "C" int dct_jsd_fwdbwd_f32(const float* const* views, int K, int C, int64
         }
     }
     return DCT_OK;
+}
+
+// bf16 tensors (networks under autocast): logits in, fp32 math in registers, bf16 gradients out; the tile pipeline
+// only.  grad_views == NULL: forward only (evaluation).  Returns DCT_ERR_UNSUPPORTED for shapes outside the pipeline
+// (K*C > 80, C not in {2,3,4,19}, HW % 8 != 0, rows not 16-byte aligned): the caller converts to float32 then.
+extern "C" int dct_jsd_fwdbwd_bf16(const void* const* views, int K, int C, int64_t B, int64_t HW, float gconst,
+                                   float* map, double* sum, void* const* grad_views, const int64_t* labels,
+                                   int64_t* counts, int32_t* flags, void* workspace, void* stream) {
+    if (labels != nullptr && counts == nullptr) return DCT_ERR_BAD_ARG;
+    if (labels != nullptr && (C > 4 || !aligned(labels, 16) || grad_views == nullptr)) return DCT_ERR_UNSUPPORTED;
+    bool dice_done = false;
+    JsdCall c{labels, counts, &dice_done, reinterpret_cast<const float* const*>(views),
+              reinterpret_cast<float* const*>(grad_views), K, C, B, HW, DCT_IN_LOGITS, grad_views ? kFwdBwd : kFwd, map, sum,
+              Upstream{nullptr, nullptr, gconst}, flags, static_cast<Workspace*>(workspace),
+              static_cast<cudaStream_t>(stream), 1};
+    int rc = jsd_dispatch(c);
+    if (rc == DCT_OK && labels != nullptr && !dice_done) return DCT_ERR_UNSUPPORTED;  // (not reachable: C <= 4 fuses)
+    return rc;
 }

@@ -363,6 +363,7 @@ struct JsdCall {
     int32_t* flags;
     Workspace* ws;
     cudaStream_t stream;
+    int elem = 0;               // 0: float32 tensors; 1: bfloat16 tensors (views / grads point to bf16; tile pipeline only)
 };
 
 // returns DCT_ERR_UNSUPPORTED when (K,C) has no register-tiled instantiation
@@ -370,7 +371,7 @@ int jsd_launch_k2(const JsdCall& c);
 int jsd_launch_k3(const JsdCall& c);
 int jsd_launch_k4(const JsdCall& c);
 
-template <int K, int C>
+template <int K, int C, class ET = float>
 int jsd_launch_tile(const JsdCall& c) {
     TileArgs a{};
     for (int k = 0; k < K; ++k) {
@@ -380,33 +381,58 @@ int jsd_launch_tile(const JsdCall& c) {
     a.HW = c.HW; a.map = c.map; a.sum = c.sum; a.up = c.up; a.eps = 0.0f; a.flags = c.flags; a.ws = c.ws;
     a.labels = nullptr; a.counts = nullptr; a.count_view_stride = c.B * C * 3;
     const bool lg = c.in_kind == DCT_IN_LOGITS;
+    if constexpr (!std::is_same<ET, float>::value) {
+        // bf16 tensors: the one-pass-over-logits forms only (fused forward+backward [+ Dice], or forward for eval)
+        if (!lg || c.mode == kBwd) return DCT_ERR_UNSUPPORTED;
+        if (c.mode == kFwd) {
+            if (!tile_eligible<JsdOp<K, true, kFwd, false>, ET>(a, c.B)) return DCT_ERR_UNSUPPORTED;
+            return tile_launch_ct<JsdOp<K, true, kFwd, false>, C, ET>(a, c.B, c.stream);
+        }
+        if constexpr (C <= 4) {
+            if (c.labels != nullptr && aligned(c.labels, 16)) {
+                a.labels = c.labels;
+                a.counts = reinterpret_cast<unsigned long long*>(c.counts);
+                if (!tile_eligible<JsdOp<K, true, kFwdBwd, true>, ET>(a, c.B)) return DCT_ERR_UNSUPPORTED;
+                int rc = tile_launch_ct<JsdOp<K, true, kFwdBwd, true>, C, ET>(a, c.B, c.stream);
+                if (rc == DCT_OK && c.dice_done) *c.dice_done = true;
+                return rc;
+            }
+        }
+        if (!tile_eligible<JsdOp<K, true, kFwdBwd, false>, ET>(a, c.B)) return DCT_ERR_UNSUPPORTED;
+        return tile_launch_ct<JsdOp<K, true, kFwdBwd, false>, C, ET>(a, c.B, c.stream);
+    } else {
     if (c.mode == kFwdBwd) {
         if constexpr (C <= 4) {
             if (lg && c.labels != nullptr && aligned(c.labels, 16)) {
                 a.labels = c.labels;
                 a.counts = reinterpret_cast<unsigned long long*>(c.counts);
-                if (!tile_eligible<JsdOp<K, true, kFwdBwd, true>>(a, c.B)) return DCT_ERR_UNSUPPORTED;
-                int rc = tile_launch_ct<JsdOp<K, true, kFwdBwd, true>, C>(a, c.B, c.stream);
+                if (!tile_eligible<JsdOp<K, true, kFwdBwd, true>, ET>(a, c.B)) return DCT_ERR_UNSUPPORTED;
+                int rc = tile_launch_ct<JsdOp<K, true, kFwdBwd, true>, C, ET>(a, c.B, c.stream);
                 if (rc == DCT_OK && c.dice_done) *c.dice_done = true;
                 return rc;
             }
         }
-        if (!tile_eligible<JsdOp<K, true, kFwdBwd, false>>(a, c.B)) return DCT_ERR_UNSUPPORTED;
-        return lg ? tile_launch_ct<JsdOp<K, true, kFwdBwd, false>, C>(a, c.B, c.stream)
-                  : tile_launch_ct<JsdOp<K, false, kFwdBwd, false>, C>(a, c.B, c.stream);
+        if (!tile_eligible<JsdOp<K, true, kFwdBwd, false>, ET>(a, c.B)) return DCT_ERR_UNSUPPORTED;
+        return lg ? tile_launch_ct<JsdOp<K, true, kFwdBwd, false>, C, ET>(a, c.B, c.stream)
+                  : tile_launch_ct<JsdOp<K, false, kFwdBwd, false>, C, ET>(a, c.B, c.stream);
     }
     if (c.mode == kBwd) {
-        if (!tile_eligible<JsdOp<K, true, kBwd, false>>(a, c.B)) return DCT_ERR_UNSUPPORTED;
-        return lg ? tile_launch_ct<JsdOp<K, true, kBwd, false>, C>(a, c.B, c.stream)
-                  : tile_launch_ct<JsdOp<K, false, kBwd, false>, C>(a, c.B, c.stream);
+        if (!tile_eligible<JsdOp<K, true, kBwd, false>, ET>(a, c.B)) return DCT_ERR_UNSUPPORTED;
+        return lg ? tile_launch_ct<JsdOp<K, true, kBwd, false>, C, ET>(a, c.B, c.stream)
+                  : tile_launch_ct<JsdOp<K, false, kBwd, false>, C, ET>(a, c.B, c.stream);
     }
-    if (!tile_eligible<JsdOp<K, true, kFwd, false>>(a, c.B)) return DCT_ERR_UNSUPPORTED;
-    return lg ? tile_launch_ct<JsdOp<K, true, kFwd, false>, C>(a, c.B, c.stream)
-              : tile_launch_ct<JsdOp<K, false, kFwd, false>, C>(a, c.B, c.stream);
+    if (!tile_eligible<JsdOp<K, true, kFwd, false>, ET>(a, c.B)) return DCT_ERR_UNSUPPORTED;
+    return lg ? tile_launch_ct<JsdOp<K, true, kFwd, false>, C, ET>(a, c.B, c.stream)
+              : tile_launch_ct<JsdOp<K, false, kFwd, false>, C, ET>(a, c.B, c.stream);
+    }
 }
 
 template <int K, int C>
 int jsd_launch_kc(const JsdCall& c) {
+    if (c.elem == 1) {
+        if constexpr (K * C <= kTileMaxRows) return jsd_launch_tile<K, C, bf16>(c);
+        return DCT_ERR_UNSUPPORTED;
+    }
     if constexpr (K * C <= kTileMaxRows) {
         // TMA tile pipeline (falls through to the register-tiled kernel when rows are not 16-byte aligned)
         int rc = jsd_launch_tile<K, C>(c);

@@ -260,6 +260,26 @@ static PixArgs make_args(const float* in0, const float* in1, float* out0, float*
     return a;
 }
 
+// bf16 tensors: the tile pipeline only (DCT_ERR_UNSUPPORTED otherwise: the caller converts to float32)
+template <class Op>
+static int tile_bf16(const void* in0, const void* in1, void* out0, void* out1, int C, int64_t B, int64_t HW, float* map,
+                     double* sum, Upstream up, float eps, int32_t* flags, void* ws, cudaStream_t stream) {
+    if (in0 == nullptr || (Op::NIN > 1 && in1 == nullptr) || C < 1 || B < 1 || HW < 1) return DCT_ERR_BAD_ARG;
+    if (Op::HAS_MAP && sum != nullptr && ws == nullptr) return DCT_ERR_BAD_ARG;
+    if (B > 65535) return DCT_ERR_UNSUPPORTED;
+    TileArgs t{};
+    t.in[0] = in0; t.in[1] = in1; t.out[0] = out0; t.out[1] = out1;
+    t.HW = HW; t.map = map; t.sum = sum; t.up = up; t.eps = eps; t.flags = flags; t.ws = static_cast<Workspace*>(ws);
+    if (!tile_eligible<Op, bf16>(t, B)) return DCT_ERR_UNSUPPORTED;
+    switch (C) {
+        case 2: return tile_launch_ct<Op, 2, bf16>(t, B, stream);
+        case 3: return tile_launch_ct<Op, 3, bf16>(t, B, stream);
+        case 4: return tile_launch_ct<Op, 4, bf16>(t, B, stream);
+        case 19: return tile_launch_ct<Op, 19, bf16>(t, B, stream);
+        default: return DCT_ERR_UNSUPPORTED;
+    }
+}
+
 }  // namespace dct
 
 using namespace dct;
@@ -325,4 +345,23 @@ extern "C" int dct_softmax_bwd_f32(const float* p, const float* gp, int C, int64
     if (gx == nullptr) return DCT_ERR_BAD_ARG;
     PixArgs a = make_args(p, gp, gx, nullptr, C, HW, nullptr, nullptr, Upstream{nullptr, nullptr, 1.0f}, 0.0f, nullptr, nullptr);
     return pix_launch<SoftmaxBwd>(a, B, static_cast<cudaStream_t>(stream));
+}
+
+// ---- bf16 twins of the two one-pass-over-logits ops of the adversarial branch (fp32 math, fp32 map / sum) ----
+extern "C" int dct_kl_logit_bf16(const void* q_logit, const void* p_logit, int C, int64_t B, int64_t HW, float* map,
+                                 double* sum, int has_upstream, const float* gmap, const float* gscalar, float gconst,
+                                 void* grad_p_logit, void* grad_q_logit, void* workspace, void* stream) {
+    const Upstream up{gmap, gscalar, gconst};
+    if (has_upstream)
+        return tile_bf16<KlLogit<true>>(q_logit, p_logit, grad_q_logit, grad_p_logit, C, B, HW, map, sum, up, 0.0f, nullptr,
+                                        workspace, static_cast<cudaStream_t>(stream));
+    return tile_bf16<KlLogit<false>>(q_logit, p_logit, nullptr, nullptr, C, B, HW, map, sum, up, 0.0f, nullptr, workspace,
+                                     static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dct_kl_from_logits_fwdbwd_bf16(const void* p_logit, const void* y_prob, int C, int64_t B, int64_t HW,
+                                              float eps, float gconst, float* map, double* sum, void* grad_p_logit,
+                                              int32_t* flags, void* workspace, void* stream) {
+    return tile_bf16<KlFromLogits>(p_logit, y_prob, grad_p_logit, nullptr, C, B, HW, map, sum,
+                                   Upstream{nullptr, nullptr, gconst}, eps, flags, workspace, static_cast<cudaStream_t>(stream));
 }

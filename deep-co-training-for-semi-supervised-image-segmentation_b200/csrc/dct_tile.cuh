@@ -25,17 +25,61 @@
 //                    provides apply_lab<CM>(x, C, g, cls[LW], w[LW], bad) instead, with cls = label in [0,C) or -1
 //                    (ignored / out of range) and w = class weight of the label (0 when cls < 0 or ignored)
 #pragma once
+#include <cuda_bf16.h>
+
 #include "dct_common.cuh"
 #include "dct_tma.cuh"
 
 namespace dct {
 
+// Element type of the [B,C,HW] tensors a tile kernel moves: float (the reference's dtype) or __nv_bfloat16 (networks
+// under autocast; the math is fp32 in registers either way, only the HBM / shared-memory rows are 2-byte).
+using bf16 = __nv_bfloat16;
+
+// PPT consecutive elements of one shared-memory row -> fp32 registers, and back (round-to-nearest-even)
+template <int PPT, class ET>
+__device__ __forceinline__ FVec<PPT> tile_ld_row(const unsigned char* row, int p0) {
+    if constexpr (std::is_same<ET, float>::value) {
+        return *reinterpret_cast<const FVec<PPT>*>(row + (size_t)p0 * 4);
+    } else {
+        FVec<PPT> r;
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(row + (size_t)p0 * 2);
+        if constexpr (PPT == 1) {
+            r.v[0] = __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(row + (size_t)p0 * 2)) << 16);
+        } else if constexpr (PPT == 2) {
+            const uint32_t u = w[0];
+            r.v[0] = __uint_as_float(u << 16); r.v[1] = __uint_as_float(u & 0xffff0000u);
+        } else {
+            const uint2 u = *reinterpret_cast<const uint2*>(w);
+            r.v[0] = __uint_as_float(u.x << 16); r.v[1] = __uint_as_float(u.x & 0xffff0000u);
+            r.v[2] = __uint_as_float(u.y << 16); r.v[3] = __uint_as_float(u.y & 0xffff0000u);
+        }
+        return r;
+    }
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t u;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(hi), "f"(lo));
+    return u;
+}
+template <int PPT, class ET>
+__device__ __forceinline__ void tile_st_row(unsigned char* row, int p0, const FVec<PPT>& r) {
+    if constexpr (std::is_same<ET, float>::value) {
+        *reinterpret_cast<FVec<PPT>*>(row + (size_t)p0 * 4) = r;
+    } else {
+        uint32_t* w = reinterpret_cast<uint32_t*>(row + (size_t)p0 * 2);
+        if constexpr (PPT == 1) *reinterpret_cast<uint16_t*>(row + (size_t)p0 * 2) = (uint16_t)(pack_bf16x2(r.v[0], 0.0f) & 0xffffu);
+        else if constexpr (PPT == 2) w[0] = pack_bf16x2(r.v[0], r.v[1]);
+        else *reinterpret_cast<uint2*>(w) = make_uint2(pack_bf16x2(r.v[0], r.v[1]), pack_bf16x2(r.v[2], r.v[3]));
+    }
+}
+
 constexpr int kTileMaxTensors = 8;
 constexpr int kTileMaxRows = 80;   // NIN*C rows per stage
 
 struct TileArgs {
-    const float* in[kTileMaxTensors];
-    float* out[kTileMaxTensors];   // each nullable
+    const void* in[kTileMaxTensors];   // [B,C,HW] of the kernel's element type (float or bf16)
+    void* out[kTileMaxTensors];        // each nullable; same element type
     int64_t HW;
     float* map;                    // nullable
     double* sum;                   // nullable
@@ -63,29 +107,33 @@ struct op_labels<Op, std::enable_if_t<Op::LABELS>> : std::true_type {};
 template <class Op>
 constexpr bool op_label_row() { return Op::NDICE > 0 || op_labels<Op>::value; }
 
-// float rows + optional side rows: int64 labels (Dice / label ops) and the upstream-gradient map (backward ops)
-template <class Op, int CT>
-constexpr int tile_row_words() {
-    return Op::NIN * CT + (op_label_row<Op>() ? 2 : 0) + (Op::GMAP ? 1 : 0);
+// data rows + optional side rows: int64 labels (Dice / label ops) and the fp32 upstream-gradient map (backward ops);
+// in BYTES per pixel
+template <class Op, int CT, class ET = float>
+constexpr int tile_row_bytes() {
+    return Op::NIN * CT * (int)sizeof(ET) + (op_label_row<Op>() ? 8 : 0) + (Op::GMAP ? 4 : 0);
 }
+template <class Op, int CT>
+constexpr int tile_row_words() { return tile_row_bytes<Op, CT, float>() / 4; }
 
-template <int WORDS, int PPT, int CTHREADS, int MINB>
+template <int WORDS, int PPT, int CTHREADS, int MINB, int UNIT = 4>
 constexpr int tile_stages() {
-    // as many stages as fit in this CTA's share of shared memory, between 2 and 8
-    constexpr size_t stage = (size_t)WORDS * PPT * CTHREADS * 4;
+    // as many stages as fit in this CTA's share of shared memory, between 2 and 8 (WORDS in units of UNIT bytes per pixel)
+    constexpr size_t stage = (size_t)WORDS * PPT * CTHREADS * UNIT;
     // 228 KB per SM, 1 KB reserved per CTA, < 1 KB of static shared memory + barriers + alignment slack
     constexpr size_t n = (233472 / MINB - 2048) / stage;
     return n < 2 ? 2 : (n > 8 ? 8 : (int)n);
 }
 
-template <class Op, int CT, int PPT, int CTHREADS, int STAGES>
+template <class Op, int CT, int PPT, int CTHREADS, int STAGES, class ET = float>
 struct TileCfg {
     static constexpr int TP = CTHREADS * PPT;                       // pixels per tile
-    static constexpr int ROWS = Op::NIN * CT;                       // float data rows
-    static constexpr int WORDS = tile_row_words<Op, CT>();          // 4-byte words per pixel incl. side rows
-    static constexpr size_t kStageBytes = (size_t)WORDS * TP * 4;
-    static constexpr int kLabelOff = ROWS * TP;                     // in floats; labels are 8-byte, TP*8 bytes
-    static constexpr int kGmapOff = (ROWS + (op_label_row<Op>() ? 2 : 0)) * TP;  // valid when Op::GMAP
+    static constexpr int ROWS = Op::NIN * CT;                       // data rows (element type ET)
+    static constexpr int ES = (int)sizeof(ET);
+    static constexpr size_t kStageBytes = (size_t)tile_row_bytes<Op, CT, ET>() * TP;
+    static constexpr size_t kRowBytes = (size_t)TP * ES;            // one data row
+    static constexpr size_t kLabelOffB = (size_t)ROWS * TP * ES;    // in bytes; labels are 8-byte, TP*8 bytes
+    static constexpr size_t kGmapOffB = kLabelOffB + (op_label_row<Op>() ? (size_t)TP * 8 : 0);  // valid when Op::GMAP (fp32 row)
     static constexpr size_t kSmemBytes = kStageBytes * STAGES + 16 * STAGES;
 };
 
@@ -100,11 +148,11 @@ struct TileCfg {
 //       No CTA-wide barrier in the tile loop: a fast warp runs ahead by up to STAGES-1 tiles.
 // Nothing depends on WHICH CTA processes a tile: Dice counts are integer atomics, the loss sum is accumulated in
 // exact fixed point (tile_grid_finish), so results are bit-reproducible under the dynamic part of the schedule.
-template <class Op, int CT, int PPT, int NCW, int STAGES, int MINB = 1>
+template <class Op, int CT, int PPT, int NCW, int STAGES, int MINB = 1, class ET = float>
 __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArgs a) {
     constexpr int CTHREADS = NCW * 32;
-    using Cfg = TileCfg<Op, CT, PPT, CTHREADS, STAGES>;
-    constexpr int TP = Cfg::TP, ROWS = Cfg::ROWS, WORDS = Cfg::WORDS, NIN = Op::NIN, NOUT = Op::NOUT, C = CT;
+    using Cfg = TileCfg<Op, CT, PPT, CTHREADS, STAGES, ET>;
+    constexpr int TP = Cfg::TP, ROWS = Cfg::ROWS, ES = Cfg::ES, NIN = Op::NIN, NOUT = Op::NOUT, C = CT;
     constexpr bool DICE = Op::NDICE > 0;
     constexpr bool LAB = op_labels<Op>::value;   // the op consumes the labels itself
     constexpr bool LROW = DICE || LAB;           // the stage carries a label row
@@ -114,7 +162,7 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
     static_assert(!DICE || CT <= 4, "fused Dice counters are packed 8-bit fields: C <= 4");
     static_assert(!DICE || PPT <= 4, "per-tile packed Dice counters: 32 lanes * PPT must stay below 256");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* stages = reinterpret_cast<float*>(smem_raw);
+    unsigned char* stages = smem_raw;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + Cfg::kStageBytes * STAGES);
     uint64_t* done = full + STAGES;
     __shared__ int s_tile[STAGES];  // tile index held by each stage; -1 = end of work
@@ -187,22 +235,24 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
             const int b = tile / tpi;
             const int64_t off = (int64_t)(tile - b * tpi) * TP;
             const int64_t rem = HW - off;
-            const uint32_t bytes = (uint32_t)((rem < TP ? rem : TP) * 4);
-            float* dst = stages + (size_t)stage * WORDS * TP;
+            const uint32_t npix = (uint32_t)(rem < TP ? rem : TP);
+            const uint32_t bytes = npix * (uint32_t)ES;   // one data row segment
+            unsigned char* dst = stages + (size_t)stage * Cfg::kStageBytes;
             uint32_t total = bytes * ROWS;
-            if constexpr (LROW) total += do_lab ? 2u * bytes : 0u;
-            if constexpr (Op::GMAP) total += has_gmap ? bytes : 0u;
+            if constexpr (LROW) total += do_lab ? 8u * npix : 0u;
+            if constexpr (Op::GMAP) total += has_gmap ? 4u * npix : 0u;
             tma::mbar_expect_tx(&full[stage], total);  // release: the tile index above is visible to the waiters
 #pragma unroll
             for (int n = 0; n < NIN; ++n)
 #pragma unroll
                 for (int c = 0; c < C; ++c)
-                    tma::bulk_load(dst + (n * C + c) * TP, a.in[n] + ((int64_t)b * C + c) * HW + off, bytes, &full[stage]);
+                    tma::bulk_load(dst + (size_t)(n * C + c) * Cfg::kRowBytes,
+                                   static_cast<const ET*>(a.in[n]) + ((int64_t)b * C + c) * HW + off, bytes, &full[stage]);
             if constexpr (LROW) {
-                if (do_lab) tma::bulk_load(dst + Cfg::kLabelOff, a.labels + (int64_t)b * HW + off, 2u * bytes, &full[stage]);
+                if (do_lab) tma::bulk_load(dst + Cfg::kLabelOffB, a.labels + (int64_t)b * HW + off, 8u * npix, &full[stage]);
             }
             if constexpr (Op::GMAP) {
-                if (has_gmap) tma::bulk_load(dst + Cfg::kGmapOff, a.up.gmap + (int64_t)b * HW + off, bytes, &full[stage]);
+                if (has_gmap) tma::bulk_load(dst + Cfg::kGmapOffB, a.up.gmap + (int64_t)b * HW + off, 4u * npix, &full[stage]);
             }
             ++issued;
         };
@@ -246,7 +296,7 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
             unsigned int dsum[kDiceRounds > 0 ? kDiceRounds : 1];
             if constexpr (DICE) {
                 if (do_dice) {
-                    const unsigned int* pkw = reinterpret_cast<const unsigned int*>(stages + (size_t)stage * WORDS * TP + Cfg::kLabelOff);
+                    const unsigned int* pkw = reinterpret_cast<const unsigned int*>(stages + (size_t)stage * Cfg::kStageBytes + Cfg::kLabelOffB);
 #pragma unroll
                     for (int rr = 0; rr < kDiceRounds; ++rr) {
                         const int r = rr * 32 + lane;
@@ -266,14 +316,15 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
                 if constexpr (NOUT > 0) {
                     const int64_t off = (int64_t)(tile - b * tpi) * TP;
                     const int64_t rem = HW - off;
-                    const uint32_t bytes = (uint32_t)((rem < TP ? rem : TP) * 4);
-                    const float* st = stages + (size_t)stage * WORDS * TP;
+                    const uint32_t bytes = (uint32_t)(rem < TP ? rem : TP) * (uint32_t)ES;
+                    const unsigned char* st = stages + (size_t)stage * Cfg::kStageBytes;
 #pragma unroll
                     for (int n = 0; n < NOUT; ++n)
                         if (a.out[n] != nullptr) {
 #pragma unroll
                             for (int c = 0; c < C; ++c)
-                                tma::bulk_store(a.out[n] + ((int64_t)b * C + c) * HW + off, st + (n * C + c) * TP, bytes);
+                                tma::bulk_store(static_cast<ET*>(a.out[n]) + ((int64_t)b * C + c) * HW + off,
+                                                st + (size_t)(n * C + c) * Cfg::kRowBytes, bytes);
                         }
                     tma::bulk_commit();
                     // load i-1's store group has drained its stage once at most one group is still reading:
@@ -319,7 +370,7 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
             const int64_t off = (int64_t)(tile - b * tpi) * TP;
             const int64_t rem = HW - off;
             const int len = (int)(rem < TP ? rem : TP);
-            float* st = stages + (size_t)stage * WORDS * TP;
+            unsigned char* st = stages + (size_t)stage * Cfg::kStageBytes;
             const int p0 = tid * PPT;
             const bool active = p0 < len;
             unsigned int pk[DICE ? Op::NDICE : 1][2];  // this tile's packed 8-bit per-class counters: [view][I,P]
@@ -333,7 +384,7 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
 #pragma unroll
                 for (int v = 0; v < PPT; ++v) gm.v[v] = 1.0f;
                 if constexpr (Op::GMAP) {
-                    if (has_gmap) gm = *reinterpret_cast<const FVec<PPT>*>(st + Cfg::kGmapOff + p0);
+                    if (has_gmap) gm = *reinterpret_cast<const FVec<PPT>*>(st + Cfg::kGmapOffB + (size_t)p0 * 4);
                 }
                 uint2 lab[PPT];  // int64 labels as (lo, hi) words
                 if constexpr (LROW) {
@@ -341,13 +392,13 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
                         if constexpr (PPT % 2 == 0) {
 #pragma unroll
                             for (int v = 0; v < PPT / 2; ++v) {  // two labels per 128-bit shared load
-                                const uint4 q = reinterpret_cast<const uint4*>(st + Cfg::kLabelOff)[(p0 >> 1) + v];
+                                const uint4 q = reinterpret_cast<const uint4*>(st + Cfg::kLabelOffB)[(p0 >> 1) + v];
                                 lab[2 * v] = make_uint2(q.x, q.y);
                                 lab[2 * v + 1] = make_uint2(q.z, q.w);
                             }
                         } else {
 #pragma unroll
-                            for (int v = 0; v < PPT; ++v) lab[v] = reinterpret_cast<const uint2*>(st + Cfg::kLabelOff)[p0 + v];
+                            for (int v = 0; v < PPT; ++v) lab[v] = reinterpret_cast<const uint2*>(st + Cfg::kLabelOffB)[p0 + v];
                         }
                     }
                 }
@@ -355,7 +406,7 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
 #pragma unroll
                 for (int n = 0; n < NIN; ++n)
 #pragma unroll
-                    for (int c = 0; c < C; ++c) xin[n][c] = *reinterpret_cast<const FVec<PPT>*>(st + (n * C + c) * TP + p0);
+                    for (int c = 0; c < C; ++c) xin[n][c] = tile_ld_row<PPT, ET>(st + (size_t)(n * C + c) * Cfg::kRowBytes, p0);
                 FVec<PPT> mapv;
                 float part = 0.0f;
 #pragma unroll
@@ -430,7 +481,7 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
                 for (int n = 0; n < NOUT; ++n)
                     if (a.out[n] != nullptr) {
 #pragma unroll
-                        for (int c = 0; c < C; ++c) *reinterpret_cast<FVec<PPT>*>(st + (n * C + c) * TP + p0) = xin[n][c];
+                        for (int c = 0; c < C; ++c) tile_st_row<PPT, ET>(st + (size_t)(n * C + c) * Cfg::kRowBytes, p0, xin[n][c]);
                     }
             }
             if constexpr (NOUT > 0) tma::fence_proxy_async_smem();
@@ -449,7 +500,7 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
                         if (lane == 2 + 2 * n) mine = rp;
                     }
                     if (lane < 1 + 2 * Op::NDICE)
-                        reinterpret_cast<unsigned int*>(st + Cfg::kLabelOff)[(tid >> 5) * 64 * PPT + lane] = mine;
+                        reinterpret_cast<unsigned int*>(st + Cfg::kLabelOffB)[(tid >> 5) * 64 * PPT + lane] = mine;
                     __syncwarp();
                 }
             }
@@ -475,9 +526,9 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
 }
 
 // Host side: does this problem fit the tile pipeline?  (16-byte aligned rows and segments)
-template <class Op>
+template <class Op, class ET = float>
 inline bool tile_eligible(const TileArgs& a, int64_t B) {
-    if ((a.HW % 4) != 0 || B * ((a.HW + 255) / 256) > 0x7fffffffLL) return false;
+    if ((a.HW % (16 / (int)sizeof(ET))) != 0 || B * ((a.HW + 255) / 256) > 0x7fffffffLL) return false;
     for (int n = 0; n < Op::NIN; ++n)
         if (!aligned(a.in[n], 16)) return false;
     for (int n = 0; n < Op::NOUT; ++n)
@@ -488,7 +539,7 @@ inline bool tile_eligible(const TileArgs& a, int64_t B) {
     return true;
 }
 
-template <class Op, int CT>
+template <class Op, int CT, class ET = float>
 int tile_launch_ct(TileArgs a, int64_t B, cudaStream_t stream) {
     constexpr int ROWS = Op::NIN * CT;
     static_assert(ROWS <= kTileMaxRows, "tile pipeline instantiations are for NIN*C <= 80");
@@ -506,9 +557,11 @@ int tile_launch_ct(TileArgs a, int64_t B, cudaStream_t stream) {
     constexpr int PPT = ROWS <= 4 ? 4 : (ROWS <= 60 ? 2 : 1);
     constexpr int NCW = ROWS <= 16 ? 8 : (ROWS <= 24 ? 4 : (ROWS <= 40 ? (Op::NOUT == 0 ? 8 : 3) : (ROWS <= 60 ? 5 : 8)));
     constexpr int MINB = ROWS <= 24 ? 2 : (ROWS <= 40 ? (Op::NOUT == 0 ? 1 : 2) : 1);
-    constexpr int STAGES = tile_stages<tile_row_words<Op, CT>(), PPT, NCW * 32, MINB>();
-    using Cfg = TileCfg<Op, CT, PPT, NCW * 32, STAGES>;
-    auto kern = tile_kernel<Op, CT, PPT, NCW, STAGES, MINB>;
+    // bf16 tensors: same shapes (the register budget follows the number of rows, not their width); the 2-byte rows
+    // simply buy more stages
+    constexpr int STAGES = tile_stages<tile_row_bytes<Op, CT, ET>(), PPT, NCW * 32, MINB, 1>();
+    using Cfg = TileCfg<Op, CT, PPT, NCW * 32, STAGES, ET>;
+    auto kern = tile_kernel<Op, CT, PPT, NCW, STAGES, MINB, ET>;
     static bool configured[64] = {};  // per instantiation and device (the attribute is per device function)
     int devid = 0;
     cudaGetDevice(&devid);

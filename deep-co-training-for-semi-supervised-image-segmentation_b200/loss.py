@@ -17,7 +17,10 @@ tensors: :func:`jsd_consistency_from_logits` / :class:`FusedJSDConsistency`, and
 :func:`kl_consistency_from_logits` for the adversarial KL.
 
 Every forward/backward is a ``torch.autograd.Function`` whose body is one call
-into the C ABI (``include/dct_b200.h``); inputs must be CUDA float32 tensors.
+into the C ABI (``include/dct_b200.h``); inputs must be CUDA float32 tensors.  The one-pass-over-logits
+forms (:func:`jsd_consistency_from_logits`, :func:`kl_consistency_from_logits`, :func:`kl_div_with_logit`,
+:func:`supervised_from_logits` / ``CrossEntropyLoss2d``) also take bfloat16 logits (autocast networks): bf16 rows
+through the same tile pipeline, fp32 math and loss, bf16 gradients.
 """
 from typing import List, Optional, Sequence
 
@@ -32,6 +35,23 @@ def _prep(t: torch.Tensor, what: str) -> torch.Tensor:
     if t.dtype != torch.float32:
         raise TypeError(f"{what}: float32 expected, got {t.dtype}")
     return t.contiguous()
+
+
+def _prep_lp(t: torch.Tensor, what: str) -> torch.Tensor:
+    """float32 or bfloat16 (the one-pass-over-logits ops also take the bf16 logits of an autocast network)."""
+    _runtime.require_cuda(t, what)
+    if t.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError(f"{what}: float32 or bfloat16 expected, got {t.dtype}")
+    return t.contiguous()
+
+
+def _promote(t: torch.Tensor) -> torch.Tensor:
+    return t.float() if t.dtype == torch.bfloat16 else t
+
+
+def _all_bf16(ts) -> bool:
+    """bf16 kernels run only when every tensor is bf16; mixed inputs are promoted to float32 (as torch would)."""
+    return all(t.dtype == torch.bfloat16 for t in ts)
 
 
 def _bchw(t: torch.Tensor):
@@ -132,17 +152,37 @@ def jsd_map_from_logits(logits: Sequence[torch.Tensor]) -> torch.Tensor:
     return _JSDFn.apply(_lib.IN_LOGITS, False, *logits)
 
 
+def _finish_grads(grads, g, dtypes):
+    """Upstream scaling of gradients that were produced in the forward pass (a zero-traffic launch for the usual
+    upstream of exactly 1) and the cast back to each input's dtype (no-op unless an input was promoted)."""
+    h = _lib.lib()
+    out = []
+    for gr, dt in zip(grads, dtypes):
+        if gr.dtype == torch.float32:
+            _lib.check(h.dct_scale_if_not_one_f32(gr.data_ptr(), gr.numel(), g.data_ptr(),
+                                                  _runtime.stream_ptr(gr.device)), "dct_scale_if_not_one_f32")
+        else:  # bf16 gradients: the upstream of `total = sup + fused` is exactly 1; anything else is a torch multiply
+            gr = gr * g.to(gr.dtype)
+        out.append(gr if gr.dtype == dt else gr.to(dt))
+    return out
+
+
 class _FusedJSDFn(torch.autograd.Function):
     """weight * mean(JSD(softmax(logits))) and its gradient in ONE pass (dct_jsd_fwdbwd_f32)."""
 
     @staticmethod
     def forward(ctx, weight: float, n_global: Optional[int], labels, counts, in_kind: int, *views):
-        vs = _views_args(views, "jsd_consistency")
+        in_dtypes = [v.dtype for v in views]
+        lp = in_kind == _lib.IN_LOGITS and _all_bf16(views)
+        if in_kind == _lib.IN_LOGITS and not lp and any(d == torch.bfloat16 for d in in_dtypes):
+            views = [_promote(v) for v in views]   # mixed precisions: promote
+        vs = [_prep_lp(v, "jsd_consistency") for v in views] if lp else _views_args(views, "jsd_consistency")
         b, c, hw = _bchw(vs[0])
         dev = vs[0].device
         st = _runtime.state(dev)
         n = b * hw if n_global is None else int(n_global)
         need_grad = any(ctx.needs_input_grad[5:])
+        ctx.in_dtypes = in_dtypes
         total = torch.empty(1, dtype=torch.float64, device=dev)
         h = _lib.lib()
         lab = None
@@ -152,7 +192,31 @@ class _FusedJSDFn(torch.autograd.Function):
             assert counts is not None and counts.dtype == torch.int64 and counts.numel() == len(vs) * b * c * 3
             lab = labels.contiguous()
         fl = _runtime.flags_ptr(st)
-        if need_grad:
+        if lp:
+            # bf16 logits: one launch of the bf16 tile pipeline (fp32 math); shapes it does not take are promoted
+            for v in vs[1:]:
+                assert v.shape == vs[0].shape, "all views must have the same shape"
+            grads = [torch.empty_like(v) for v in vs] if need_grad else None
+            fuse_dice = lab is not None and need_grad and c <= 4
+            rc = h.dct_jsd_fwdbwd_bf16(_lib.ptr_array(vs), len(vs), c, b, hw, float(weight) / n, None, _ptr(total),
+                                       _lib.ptr_array(grads) if need_grad else None, _ptr(lab) if fuse_dice else None,
+                                       _ptr(counts) if fuse_dice else None, fl, st.workspace.data_ptr(),
+                                       _runtime.stream_ptr(dev))
+            if rc == _lib.ERR_UNSUPPORTED:
+                lp = False
+                vs = [v.float() for v in vs]
+            else:
+                _lib.check(rc, "dct_jsd_fwdbwd_bf16")
+                if lab is not None and not fuse_dice:  # C > 4 / evaluation: the meters count on their own
+                    for k, v in enumerate(vs):
+                        vf = v.float()
+                        _lib.check(h.dct_dice_counts_f32(vf.data_ptr(), lab.data_ptr(), c, b, hw,
+                                                         counts.data_ptr() + k * b * c * 3 * 8, 1, fl,
+                                                         _runtime.stream_ptr(dev)), "dct_dice_counts_f32")
+                ctx.grads = grads
+        if lp:
+            pass
+        elif need_grad:
             grads = [torch.empty_like(v) for v in vs]
             _lib.check(h.dct_jsd_fwdbwd_f32(_lib.ptr_array(vs), len(vs), c, b, hw, in_kind, float(weight) / n, None,
                                             _ptr(total), _lib.ptr_array(grads), _ptr(lab), _ptr(counts), fl,
@@ -181,9 +245,7 @@ class _FusedJSDFn(torch.autograd.Function):
         g = g.contiguous().to(torch.float32)
         h = _lib.lib()
         dev = grads[0].device
-        for gr in grads:  # no-op launch (zero traffic) for the usual upstream of exactly 1
-            _lib.check(h.dct_scale_if_not_one_f32(gr.data_ptr(), gr.numel(), g.data_ptr(), _runtime.stream_ptr(dev)),
-                       "dct_scale_if_not_one_f32")
+        grads = _finish_grads(grads, g, ctx.in_dtypes)
         return (None, None, None, None, None) + tuple(grads)
 
 
@@ -322,16 +384,29 @@ class _KLLogitFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, q_logit, p_logit, reduce: bool):
-        ql = _prep(q_logit, "kl_div_with_logit"); pl = _prep(p_logit, "kl_div_with_logit")
+        ctx.in_dtypes = (q_logit.dtype, p_logit.dtype)
+        lp = _all_bf16((q_logit, p_logit))
+        if not lp:
+            q_logit, p_logit = _prep(_promote(q_logit), "kl_div_with_logit"), _prep(_promote(p_logit), "kl_div_with_logit")
+        ql = _prep_lp(q_logit, "kl_div_with_logit"); pl = _prep_lp(p_logit, "kl_div_with_logit")
         assert ql.shape == pl.shape
         b, c, hw = _bchw(ql)
         dev = ql.device
         st = _runtime.state(dev)
         out_map = None if reduce else torch.empty((b,) + tuple(ql.shape[2:]), dtype=torch.float32, device=dev)
         total = torch.empty(1, dtype=torch.float64, device=dev) if reduce else None
-        _lib.check(_lib.lib().dct_kl_logit_f32(ql.data_ptr(), pl.data_ptr(), c, b, hw, _ptr(out_map), _ptr(total), 0,
-                                               None, None, 1.0, None, None, st.workspace.data_ptr(),
-                                               _runtime.stream_ptr(dev)), "dct_kl_logit_f32")
+        if lp:  # bf16 logits (fp32 map): the bf16 tile pipeline, or promotion for shapes it does not take
+            rc = _lib.lib().dct_kl_logit_bf16(ql.data_ptr(), pl.data_ptr(), c, b, hw, _ptr(out_map), _ptr(total), 0,
+                                              None, None, 1.0, None, None, st.workspace.data_ptr(),
+                                              _runtime.stream_ptr(dev))
+            if rc == _lib.ERR_UNSUPPORTED:
+                lp, ql, pl = False, ql.float(), pl.float()
+            else:
+                _lib.check(rc, "dct_kl_logit_bf16")
+        if not lp:
+            _lib.check(_lib.lib().dct_kl_logit_f32(ql.data_ptr(), pl.data_ptr(), c, b, hw, _ptr(out_map), _ptr(total), 0,
+                                                   None, None, 1.0, None, None, st.workspace.data_ptr(),
+                                                   _runtime.stream_ptr(dev)), "dct_kl_logit_f32")
         ctx.save_for_backward(ql, pl)
         ctx.reduce, ctx.n = reduce, b * hw
         if reduce:
@@ -353,9 +428,13 @@ class _KLLogitFn(torch.autograd.Function):
         else:
             gmap, gscalar, gconst = g, None, 1.0
         st = _runtime.state(dev)
-        _lib.check(_lib.lib().dct_kl_logit_f32(ql.data_ptr(), pl.data_ptr(), c, b, hw, None, None, 1, _ptr(gmap),
-                                               _ptr(gscalar), gconst, _ptr(gp), _ptr(gq), st.workspace.data_ptr(),
-                                               _runtime.stream_ptr(dev)), "dct_kl_logit_f32")
+        fn = _lib.lib().dct_kl_logit_bf16 if ql.dtype == torch.bfloat16 else _lib.lib().dct_kl_logit_f32
+        _lib.check(fn(ql.data_ptr(), pl.data_ptr(), c, b, hw, None, None, 1, _ptr(gmap), _ptr(gscalar), gconst,
+                      _ptr(gp), _ptr(gq), st.workspace.data_ptr(), _runtime.stream_ptr(dev)), "dct_kl_logit")
+        if gq is not None and gq.dtype != ctx.in_dtypes[0]:
+            gq = gq.to(ctx.in_dtypes[0])
+        if gp is not None and gp.dtype != ctx.in_dtypes[1]:
+            gp = gp.to(ctx.in_dtypes[1])
         return gq, gp, None
 
 
@@ -405,7 +484,11 @@ class _KLFromLogitsFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, p_logit, y_prob, weight: float, eps: float, n_global: Optional[int]):
-        pl = _prep(p_logit, "kl_consistency"); y = _prep(y_prob, "kl_consistency")
+        ctx.in_dtype = p_logit.dtype
+        lp = _all_bf16((p_logit, y_prob))
+        if not lp:
+            p_logit, y_prob = _prep(_promote(p_logit), "kl_consistency"), _prep(_promote(y_prob), "kl_consistency")
+        pl = _prep_lp(p_logit, "kl_consistency"); y = _prep_lp(y_prob, "kl_consistency")
         assert pl.shape == y.shape
         b, c, hw = _bchw(pl)
         dev = pl.device
@@ -413,10 +496,21 @@ class _KLFromLogitsFn(torch.autograd.Function):
         n = b * hw if n_global is None else int(n_global)
         total = torch.empty(1, dtype=torch.float64, device=dev)
         grad = torch.empty_like(pl) if ctx.needs_input_grad[0] else None
-        _lib.check(_lib.lib().dct_kl_from_logits_fwdbwd_f32(pl.data_ptr(), y.data_ptr(), c, b, hw, float(eps),
-                                                            float(weight) / n, None, total.data_ptr(), _ptr(grad),
-                                                            _runtime.flags_ptr(st), st.workspace.data_ptr(),
-                                                            _runtime.stream_ptr(dev)), "dct_kl_from_logits_fwdbwd_f32")
+        if lp:
+            rc = _lib.lib().dct_kl_from_logits_fwdbwd_bf16(pl.data_ptr(), y.data_ptr(), c, b, hw, float(eps),
+                                                           float(weight) / n, None, total.data_ptr(), _ptr(grad),
+                                                           _runtime.flags_ptr(st), st.workspace.data_ptr(),
+                                                           _runtime.stream_ptr(dev))
+            if rc == _lib.ERR_UNSUPPORTED:  # shape outside the bf16 tile pipeline: promote
+                lp, pl, y = False, pl.float(), y.float()
+                grad = torch.empty_like(pl) if grad is not None else None
+            else:
+                _lib.check(rc, "dct_kl_from_logits_fwdbwd_bf16")
+        if not lp:
+                _lib.check(_lib.lib().dct_kl_from_logits_fwdbwd_f32(pl.data_ptr(), y.data_ptr(), c, b, hw, float(eps),
+                                                                float(weight) / n, None, total.data_ptr(), _ptr(grad),
+                                                                _runtime.flags_ptr(st), st.workspace.data_ptr(),
+                                                                _runtime.stream_ptr(dev)), "dct_kl_from_logits_fwdbwd_f32")
         _runtime.after_call(st)
         ctx.grad = grad
         return (total * (float(weight) / n)).to(torch.float32).reshape(())
@@ -429,9 +523,7 @@ class _KLFromLogitsFn(torch.autograd.Function):
         if grad is None:
             return None, None, None, None, None
         g = g.contiguous().to(torch.float32)
-        _lib.check(_lib.lib().dct_scale_if_not_one_f32(grad.data_ptr(), grad.numel(), g.data_ptr(),
-                                                       _runtime.stream_ptr(grad.device)), "dct_scale_if_not_one_f32")
-        return grad, None, None, None, None
+        return _finish_grads([grad], g, [ctx.in_dtype])[0], None, None, None, None
 
 
 def kl_consistency_from_logits(adv_logit: torch.Tensor, real_prob: torch.Tensor, weight: float = 1.0,
@@ -501,7 +593,9 @@ class _CEFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, logits, targets, weight, ignore_index: int, reduction: str, n_global, dice_counts):
-        x = _prep(logits, "CrossEntropyLoss2d")
+        ctx.in_dtype = logits.dtype
+        lp = logits.dtype == torch.bfloat16 and reduction != "none" and ctx.needs_input_grad[0]
+        x = _prep_lp(logits, "CrossEntropyLoss2d") if lp else _prep(_promote(logits), "CrossEntropyLoss2d")
         assert x.dim() >= 2
         b, c, hw = _bchw(x)
         if c > _lib.MAX_CLASSES:
@@ -542,7 +636,18 @@ class _CEFn(torch.autograd.Function):
             else:
                 inv64 = 1.0 / _ce_weight_sum(lab, c, ignore_index, w, st, dev)
                 inv = inv64.to(torch.float32).reshape(1)
-        if ctx.needs_input_grad[0]:
+        if lp:  # bf16 logits: one launch of the bf16 tile pipeline, or promotion for shapes it does not take
+            grad = torch.empty_like(x)
+            rc = h.dct_ce_fwdbwd_bf16(x.data_ptr(), lab.data_ptr(), c, b, hw, _ptr(w), int(ignore_index), _ptr(inv),
+                                      gconst, None, total.data_ptr(), grad.data_ptr(), _ptr(dice_counts), fl, ws, s)
+            if rc == _lib.ERR_UNSUPPORTED:
+                lp, x = False, x.float()
+            else:
+                _lib.check(rc, "dct_ce_fwdbwd_bf16")
+                ctx.grad = grad
+        if lp:
+            pass
+        elif ctx.needs_input_grad[0]:
             grad = torch.empty_like(x)
             _lib.check(h.dct_ce_fwdbwd_f32(x.data_ptr(), lab.data_ptr(), c, b, hw, _ptr(w), int(ignore_index),
                                            _ptr(inv), gconst, None, total.data_ptr(), grad.data_ptr(),
@@ -573,14 +678,12 @@ class _CEFn(torch.autograd.Function):
             _lib.check(h.dct_ce_bwd_f32(x.data_ptr(), lab.data_ptr(), c, b, hw, _ptr(w), ctx.ignore_index, g.data_ptr(),
                                         None, 1.0, grad.data_ptr(), None, _runtime.stream_ptr(x.device)),
                        "dct_ce_bwd_f32")
-            return grad, None, None, None, None, None, None
+            return grad.to(ctx.in_dtype), None, None, None, None, None, None
         grad = ctx.grad
         ctx.grad = None
         if grad is None:
             raise RuntimeError("CrossEntropyLoss2d: backward called twice or without grad-requiring logits")
-        _lib.check(h.dct_scale_if_not_one_f32(grad.data_ptr(), grad.numel(), g.data_ptr(),
-                                              _runtime.stream_ptr(grad.device)), "dct_scale_if_not_one_f32")
-        return grad, None, None, None, None, None, None
+        return _finish_grads([grad], g, [ctx.in_dtype])[0], None, None, None, None, None, None
 
 
 class CrossEntropyLoss2d(nn.Module):

@@ -278,6 +278,38 @@ DCT_API int dct_onehot_dice_counts_i32(const int32_t* label_onehot, const int32_
 DCT_API int dct_vote_f32(const float* const* views, int K, int C, int64_t B, int64_t HW, int hard, float* out,
                          int64_t* cls, uint8_t* cls_u8, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * bfloat16 twins of the one-pass-over-logits entry points (networks under torch.autocast emit bf16 logits;
+ * north_star: "within 1e-2 relative in bf16").  Tensors [B,C,HW] are bfloat16 (2-byte elements, same NCHW
+ * layout), gradients are written as bfloat16 (round-to-nearest-even); ALL arithmetic is fp32 in registers and the
+ * map / sum outputs, labels, counts, flags and workspace are exactly as in the _f32 functions.  Only the TMA tile
+ * pipeline serves these: HW % 8 == 0, 16-byte aligned tensors, C in {2,3,4,19}, K*C <= 80; any other shape
+ * returns DCT_ERR_UNSUPPORTED with nothing launched and the caller converts to float32.
+ * Algorithmic traffic: 2*K*C*2 (+8 with labels) B/pixel for the JSD step, 3*C*2 for the adversarial KL.
+ * ------------------------------------------------------------------------------------------ */
+
+/* dct_jsd_fwdbwd_f32 with DCT_IN_LOGITS on bf16 views (HOST arrays of K device pointers).  grad_views == NULL:
+ * forward only (evaluation; `labels` must be NULL then).  Fused Dice counting needs C <= 4. */
+DCT_API int dct_jsd_fwdbwd_bf16(const void* const* views, int K, int C, int64_t B, int64_t HW, float gconst,
+                                float* map, double* sum, void* const* grad_views, const int64_t* labels,
+                                int64_t* counts, int32_t* flags, void* workspace, void* stream);
+
+/* dct_kl_logit_f32 (VATGenerator.kl_div_with_logit, AEGenerator.py:78-91) on bf16 logits; bf16 gradients. */
+DCT_API int dct_kl_logit_bf16(const void* q_logit, const void* p_logit, int C, int64_t B, int64_t HW, float* map,
+                              double* sum, int has_upstream, const float* gmap, const float* gscalar, float gconst,
+                              void* grad_p_logit, void* grad_q_logit, void* workspace, void* stream);
+
+/* dct_kl_from_logits_fwdbwd_f32 (cotraining_totalloss.py:391-392) on bf16 p_logit / y_prob; bf16 gradient. */
+DCT_API int dct_kl_from_logits_fwdbwd_bf16(const void* p_logit, const void* y_prob, int C, int64_t B, int64_t HW,
+                                           float eps, float gconst, float* map, double* sum, void* grad_p_logit,
+                                           int32_t* flags, void* workspace, void* stream);
+
+/* dct_ce_fwdbwd_f32 (CrossEntropyLoss2d, loss.py:12-25, + DiceMeter.add) on bf16 logits; bf16 gradient. */
+DCT_API int dct_ce_fwdbwd_bf16(const void* logits, const int64_t* labels, int C, int64_t B, int64_t HW,
+                               const float* class_weight, int64_t ignore_index, const float* gscalar, float gconst,
+                               float* map, double* sum, void* grad_logits, int64_t* dice_counts, int32_t* flags,
+                               void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
