@@ -28,7 +28,8 @@ WORKLOADS = {  # name: (K, C, B per GPU, H, W, Cin, description)
     "c1": (2, 4, 4, 256, 256, 1, "ACDC 2 views C=4 256x256 B=4 (JSD only)"),
     "c2": (3, 4, 32, 256, 256, 1, "ACDC 3 views C=4 256x256 B=32/GPU, JSD + VAT adversarial + Dice meters"),
     "c3": (2, 2, 4, 512, 512, 1, "Spleen 2 views C=2 512x512 B=4/GPU"),
-    "c4": (2, 19, 16, 512, 1024, 3, "Cityscapes 2 views C=19 512x1024 B=16/GPU"),
+    "c4": (2, 19, 16, 512, 1024, 3, "Cityscapes 2 views C=19 512x1024 B=16/GPU, JSD + VAT adversarial (no meters on the "
+                                    "unlabeled branch: trainer/cotraining_city.py:250-257)"),
 }
 METRIC = "consistency-loss pixels/sec (fwd+bwd)"
 UNIT = "pixels/s"
@@ -204,9 +205,31 @@ def run_ours(args, wl):
         dist.init_process_group("nccl", device_id=dev)
     assert dct_b200._lib.lib().dct_device_check(local) == 0, "not an sm_100 device"
     with_vat = args.workload != "c1"
+    # CoTrainer_City keeps its IoU meters on the labeled branch only (trainer/cotraining_city.py:236-241 vs :250-257)
+    with_dice = args.workload != "c4"
     n_local = B * H * W
+    # The path's only exchange: the loss sums of every step.  "p2p" (default at N > 1): the step's last
+    # kernel pushes them into every rank's mailbox over NVLink peer memory (distributed.PeerExchange) -- no collective
+    # launch; "nccl": one all-reduce per step on a side stream (the baseline this replaces, kept for A/B).
+    px, exchange = None, "none"
+    if world > 1:
+        exchange = args.exchange
+        if exchange in ("p2p", "auto"):
+            try:
+                from dct_b200.distributed import PeerExchange
+                px = PeerExchange(dev, n=4, nslots=64)
+                ok = torch.ones(1, device=dev)
+            except Exception as e:  # IPC / peer mapping refused on this box
+                if args.exchange == "p2p":
+                    raise
+                print(f"[bench rank {rank}] peer exchange unavailable ({e}); using NCCL", file=sys.stderr)
+                ok = torch.zeros(1, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() == 0:
+                px = None
+            exchange = "p2p" if px is not None else "nccl"
     step = ConsistencyStep(K, C, B, H, W, cin=cin, jsd_weight=1.0, adv_weight=1.0, n_global=n_local * world,
-                           with_vat=with_vat)
+                           with_vat=with_vat, with_dice=with_dice, exchange=px)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     # R independent buffer sets, rotated every step so that no step finds its inputs in the 126 MB L2
     per_set = sum(t.numel() * t.element_size() for t in StepBuffers.allocate(K, C, 1, H, W, cin, dev).input_tensors()) * B
@@ -217,7 +240,8 @@ def run_ours(args, wl):
     # the path's only exchange: the loss scalars of every step, all-reduced over NCCL on a side stream
     # so that the collective of step i overlaps the kernels of step i+1 (the gradients never depend on it: the
     # global 1/N is folded into the kernels through n_global)
-    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    use_nccl = world > 1 and px is None
+    comm = torch.cuda.Stream(device=dev) if use_nccl else None
     reds = [torch.zeros(4, dtype=torch.float64, device=dev) for _ in range(R)]
     copied = [None] * R
     pending = []
@@ -226,13 +250,13 @@ def run_ours(args, wl):
         j = i % R
         s = sets[j]
         main = torch.cuda.current_stream(dev)
-        if world > 1 and copied[j] is not None:
+        if use_nccl and copied[j] is not None:
             main.wait_event(copied[j])  # step i-R's sums have been staged before this step overwrites them
         if graphs is not None:
             graphs[j].replay()
         else:
             step.run(s)
-        if world > 1:
+        if use_nccl:
             done = torch.cuda.Event()
             done.record(main)
             with torch.cuda.stream(comm):
@@ -246,7 +270,7 @@ def run_ours(args, wl):
                     pending.pop(0).wait()
 
     def drain():
-        if world > 1:
+        if use_nccl:
             with torch.cuda.stream(comm):
                 while pending:
                     pending.pop(0).wait()
@@ -277,11 +301,22 @@ def run_ours(args, wl):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     value = n_local * world * args.steps / (ms_total * 1e-3)
+    exchange_check = None
+    if px is not None:
+        # every rank has finished (barrier above): the last publication of every rank must sit in this rank's mailbox,
+        # and its rank-ordered sum must equal an NCCL all-reduce of the same sums
+        q = px.published()
+        got = px.read(q)
+        last = sets[(args.steps - 1) % R].sums.clone()
+        dist.all_reduce(last)
+        err = float((got - last[:4]).abs().max().item()) / max(float(last[:4].abs().max().item()), 1e-30)
+        assert err <= 1e-12, f"peer exchange disagrees with the NCCL all-reduce of the same sums (rel {err:.2e})"
+        exchange_check = {"publications": q, "rel_err_vs_nccl_allreduce": err}
 
     # ---- roofline of the dominant kernel (fused JSD fwd+bwd, + the K Dice count sets when C <= 4): its average
     # launch duration over a timed region of back-to-back launches on the launching stream, CUDA events on that
     # stream, rotating over the R buffer sets (R x inputs+grads >> the 126 MB L2, so no launch finds its inputs cached)
-    fused_dice = C <= 4 and K * C <= 16
+    fused_dice = with_dice and C <= 4 and K * C <= 16
     jsd_only = ConsistencyStep(K, C, B, H, W, cin=cin, n_global=n_local * world, with_vat=False, with_dice=fused_dice)
     side = torch.cuda.Stream(device=dev)
     side.wait_stream(torch.cuda.current_stream(dev))
@@ -320,7 +355,7 @@ def run_ours(args, wl):
                 "step_achieved_GBps": sum(step.algorithmic_bytes().values()) / (ms_total * 1e-3 / args.steps) / 1e9}
 
     # ---- e2e: host buffers in pinned memory -> H2D -> the public autograd API -> D2H of losses + Dice rows
-    e2e = run_e2e(args, dct_b200, step, sets[0], dev, world, n_local, K, C, B, H, W, with_vat)
+    e2e = run_e2e(args, dct_b200, step, sets[0], dev, world, n_local, K, C, B, H, W, with_vat, with_dice)
     dct_b200.raise_if_flagged()
     clocks = sampler.stop() if rank == 0 else None
 
@@ -334,6 +369,10 @@ def run_ours(args, wl):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"{args.workload}: {desc}", "K": K, "C": C, "H": H, "W": W, "batch_per_gpu": B,
                            "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": bool(args.graph),
+                           "exchange": {"none": "none (1 GPU)", "nccl": "NCCL all-reduce of the loss sums per step (side stream)",
+                                        "p2p": "fused: the step's last kernel stores the loss sums into every rank's "
+                                               "mailbox over NVLink peer memory (no collective launch)"}[exchange],
+                           "exchange_check": exchange_check,
                            "l2": f"inputs larger than L2: {R} rotating buffer sets of {per_set / 2**20:.0f} MiB inputs"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": step.launches_per_step * args.steps,
                 "roofline": roofline, "cpu_baseline": cpu}
@@ -343,7 +382,7 @@ def run_ours(args, wl):
         dist.destroy_process_group()
 
 
-def run_e2e(args, dct, step, dev_set, dev, world, n_local, K, C, B, H, W, with_vat):
+def run_e2e(args, dct, step, dev_set, dev, world, n_local, K, C, B, H, W, with_vat, with_dice=True):
     """Same step through the PUBLIC API (autograd Functions / meters / generators) with host buffers:
     every step copies its inputs from pinned host memory (copy stream, double-buffered against the
     compute of the previous step) and reads the losses and Dice rows back to the host."""
@@ -377,7 +416,10 @@ def run_e2e(args, dct, step, dev_set, dev, world, n_local, K, C, B, H, W, with_v
         logits = [x.requires_grad_() for x in t[:K]]
         labels, d, d_grad, img, yhat, adv, real = t[K:K + 7]
         counts = torch.zeros(K, B, C, 3, dtype=torch.int64, device=dev)
-        loss = dct.jsd_consistency_from_logits(logits, weight=1.0, labels=labels, dice_counts=counts, n_global=n_glob)
+        if with_dice:
+            loss = dct.jsd_consistency_from_logits(logits, weight=1.0, labels=labels, dice_counts=counts, n_global=n_glob)
+        else:
+            loss = dct.jsd_consistency_from_logits(logits, weight=1.0, n_global=n_glob)
         total = loss
         outs = [loss.detach()]
         if with_vat:
@@ -441,6 +483,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--graph", type=int, default=1, help="replay the step as a CUDA graph (1) or launch eagerly (0)")
     ap.add_argument("--e2e-steps", type=int, default=50)
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="N > 1: how the loss sums cross ranks (auto = p2p, NCCL if peer mapping is refused)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

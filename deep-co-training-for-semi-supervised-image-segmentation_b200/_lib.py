@@ -9,7 +9,8 @@ import subprocess
 import threading
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_PKG, "libdct_b200.so")
+# DCT_B200_LIB: developer override (A/B of two builds on the same box); the product always loads the in-tree library
+_SO = os.environ.get("DCT_B200_LIB") or os.path.join(_PKG, "libdct_b200.so")
 _CSRC = os.path.join(_PKG, "csrc")
 
 OK = 0
@@ -17,6 +18,7 @@ ERR_UNSUPPORTED = -2
 IN_PROBS, IN_LOGITS = 0, 1
 FLAG_SIMPLEX, FLAG_LABEL, FLAG_PRED, FLAG_ONEHOT, NUM_FLAGS = 0, 1, 2, 3, 4
 MAX_VIEWS, MAX_CLASSES = 8, 64
+MAX_PEERS, PUB_ROW_WORDS, PUB_MAX_VALUES, IPC_HANDLE_BYTES = 8, 16, 8, 64
 
 _p, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
@@ -58,8 +60,14 @@ _SIGNATURES = {
     "dct_kl_logit_bf16": [_p, _p, _i, _i64, _i64, _p, _p, _i, _p, _p, _f, _p, _p, _p, _p],
     "dct_kl_from_logits_fwdbwd_bf16": [_p, _p, _i, _i64, _i64, _f, _f, _p, _p, _p, _p, _p, _p],
     "dct_ce_fwdbwd_bf16": [_p, _p, _i, _i64, _i64, _p, _i64, _p, _f, _p, _p, _p, _p, _p, _p, _p],
+    "dct_peer_pub_bytes": [],
+    "dct_mailbox_create": [C.c_size_t, _p, _p],
+    "dct_mailbox_open": [_p, _p],
+    "dct_mailbox_close": [_p, _i],
+    "dct_exchange_arm": [_p, _p, _p],
 }
-_RESTYPES = {"dct_error_string": C.c_char_p, "dct_last_cuda_error": C.c_char_p, "dct_workspace_bytes": C.c_size_t}
+_RESTYPES = {"dct_error_string": C.c_char_p, "dct_last_cuda_error": C.c_char_p, "dct_workspace_bytes": C.c_size_t,
+             "dct_peer_pub_bytes": C.c_size_t}
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
 _lib = None

@@ -43,3 +43,57 @@ extern "C" int dct_device_check(int ordinal) {
 }
 
 extern "C" size_t dct_workspace_bytes(void) { return sizeof(Workspace); }
+
+// ---- fused exchange plumbing (include/dct_b200.h "Fused cross-rank exchange") ----
+extern "C" size_t dct_peer_pub_bytes(void) { return sizeof(PeerPub); }
+
+static_assert(sizeof(cudaIpcMemHandle_t) == DCT_IPC_HANDLE_BYTES, "CUDA IPC handles are 64 bytes");
+
+extern "C" int dct_mailbox_create(size_t bytes, void** dev_ptr, void* ipc_handle) {
+    if (bytes == 0 || dev_ptr == nullptr || ipc_handle == nullptr) return DCT_ERR_BAD_ARG;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) e = cudaMemset(p, 0, bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        g_last_cuda_error = e;
+        if (p != nullptr) cudaFree(p);
+        (void)cudaGetLastError();
+        return DCT_ERR_CUDA;
+    }
+    std::memcpy(ipc_handle, &h, sizeof(h));
+    *dev_ptr = p;
+    return DCT_OK;
+}
+
+extern "C" int dct_mailbox_open(const void* ipc_handle, void** dev_ptr) {
+    if (ipc_handle == nullptr || dev_ptr == nullptr) return DCT_ERR_BAD_ARG;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, ipc_handle, sizeof(h));
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { g_last_cuda_error = e; (void)cudaGetLastError(); return DCT_ERR_CUDA; }
+    *dev_ptr = p;
+    return DCT_OK;
+}
+
+extern "C" int dct_mailbox_close(void* dev_ptr, int owned) {
+    if (dev_ptr == nullptr) return DCT_ERR_BAD_ARG;
+    cudaError_t e = owned ? cudaFree(dev_ptr) : cudaIpcCloseMemHandle(dev_ptr);
+    if (e != cudaSuccess) { g_last_cuda_error = e; (void)cudaGetLastError(); return DCT_ERR_CUDA; }
+    return DCT_OK;
+}
+
+namespace dct {
+__global__ void exchange_arm_kernel(Workspace* ws, PeerPub* desc) { ws->pub = desc; }
+}  // namespace dct
+
+extern "C" int dct_exchange_arm(void* workspace, const void* desc_dev, void* stream) {
+    if (workspace == nullptr) return DCT_ERR_BAD_ARG;
+    if (!aligned(workspace, 8) || !aligned(desc_dev, 8)) return DCT_ERR_MISALIGNED;
+    exchange_arm_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<Workspace*>(workspace), static_cast<PeerPub*>(const_cast<void*>(desc_dev)));
+    return check_launch();
+}

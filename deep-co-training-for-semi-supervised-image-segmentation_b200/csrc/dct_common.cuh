@@ -14,7 +14,18 @@ constexpr int kSMs = 148;             // B200: 2 dies x 74 SMs
 constexpr int kMaxPartials = 8192;    // per-launch CTA partial sums kept in the workspace
 constexpr float kEntEps = 1e-16f;     // Entropy / Entropy_2D epsilon (generalframework/loss/loss.py:64,81)
 
-// workspace layout: 64-byte header (all fields zero between launches: the last CTA of a launch re-arms them)
+// Peer publication descriptor ("dct_peer_pub" in include/dct_b200.h): where the last CTA of a launch pushes a step's
+// loss sums -- straight into every data-parallel rank's mailbox over NVLink (see peer_publish below).
+struct PeerPub {
+    const double* trigger;                     // publish when the launch's `sum` output pointer equals this
+    const double* src;                         // n doubles (local device memory) holding the step's sums
+    unsigned long long* seq;                   // device counter of publications made so far (shared by the descriptors of a rank)
+    int n, rank, world, nslots;
+    unsigned long long* mailbox[DCT_MAX_PEERS];  // mailbox[r]: rank r's mailbox (own one included), peer-mapped
+};
+static_assert(sizeof(PeerPub) == sizeof(dct_peer_pub), "PeerPub mirrors dct_peer_pub");
+
+// workspace layout: 64-byte header (all fields but `pub` zero between launches: the last CTA of a launch re-arms them)
 // followed by kMaxPartials double partials
 struct Workspace {
     unsigned int ticket;         // CTAs that have finished
@@ -23,7 +34,8 @@ struct Workspace {
     unsigned int pad0;
     unsigned long long fx_lo;    // order-independent loss sum in 2^-40 fixed point: sum of the low 32 bits ...
     long long fx_hi;             // ... and of the (signed) high bits of every partial
-    unsigned int pad[8];
+    PeerPub* pub;                // null, or the armed publication descriptor (dct_exchange_arm); persistent
+    unsigned int pad[6];
     double partials[kMaxPartials];
 };
 static_assert(offsetof(Workspace, partials) == 64, "workspace header is 64 bytes");
@@ -158,6 +170,36 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused exchange (the path's only cross-rank coupling is a handful of loss scalars).  Instead of a
+// collective launched after the step, the thread that has just written the step's LAST sum pushes all n sums into
+// row `rank` of every rank's mailbox with plain stores over NVLink / NVSwitch peer mappings.  Each double travels as
+// two 8-byte words {32 data bits | 32-bit sequence number}: an aligned 8-byte store is single-copy atomic, so a
+// reader that sees the expected sequence number in a word also sees its data -- no fence, no flag round trip
+// (the "LL" scheme of NCCL's low-latency protocol).  Mailbox row: DCT_PUB_ROW_WORDS u64; slot = seq % nslots.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void peer_publish(PeerPub* pub) {
+    const unsigned long long q = __ldcg(pub->seq) + 1ull;
+    const unsigned long long tag = (q & 0xffffffffull) << 32;
+    const int n = pub->n, world = pub->world;
+    const size_t row = ((size_t)(q % (unsigned long long)pub->nslots) * world + pub->rank) * DCT_PUB_ROW_WORDS;
+    for (int j = 0; j < n; ++j) {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(__ldcg(pub->src + j));
+        const unsigned long long w0 = tag | (bits & 0xffffffffull), w1 = tag | (bits >> 32);
+        for (int p = 0; p < world; ++p) {
+            unsigned long long* dst = pub->mailbox[p] + row + 2 * j;
+            asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(w0), "l"(w1) : "memory");
+        }
+    }
+    *pub->seq = q;
+}
+__device__ __forceinline__ void maybe_publish(Workspace* ws, const double* out) {
+#ifndef DCT_NO_PUBLISH  // developer A/B switch (a build without the hook; never defined in the product build)
+    PeerPub* pub = ws->pub;
+    if (pub != nullptr && out == pub->trigger) peer_publish(pub);
+#endif
+}
+
 // Deterministic grid-wide sum of one double per thread.  Every CTA writes its partial to the
 // workspace; the CTA that draws the last ticket adds the partials in index order and writes
 // *out, then re-arms the ticket.  `out` may be null (nothing is done).
@@ -194,6 +236,7 @@ __device__ __forceinline__ void grid_sum_to(double v, Workspace* ws, double* out
             t = warp_sum(t);
             if (lane == 0) {
                 *out = t;
+                maybe_publish(ws, out);
                 ws->ticket = 0u;
             }
         }
@@ -254,6 +297,7 @@ __device__ __forceinline__ void tile_grid_finish(long long acc_fx, bool nonfinit
                 const unsigned int nf = __ldcg(&ws->nonfinite);
                 const double total = ((double)hi * 4294967296.0 + (double)lo) * (1.0 / 1099511627776.0);
                 *out = nf ? __longlong_as_double(0x7ff8000000000000ll) : total;
+                maybe_publish(ws, out);
                 ws->fx_lo = 0ull;
                 ws->fx_hi = 0ll;
                 ws->nonfinite = 0u;

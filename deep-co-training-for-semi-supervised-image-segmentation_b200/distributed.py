@@ -63,3 +63,142 @@ def all_gather_rows(rows: torch.Tensor, group=None) -> torch.Tensor:
     out = [torch.empty_like(rows) for _ in range(dist.get_world_size(group))]
     dist.all_gather(out, rows.contiguous(), group=group)
     return torch.cat(out, 0)
+
+
+# ----------------------------------------------------------------------------------------------------
+# Fused exchange of the step's loss sums over NVLink peer memory (include/dct_b200.h, "Fused cross-rank exchange")
+# ----------------------------------------------------------------------------------------------------
+class PeerExchange:
+    """Every rank's loss sums in every rank's HBM, written by the step's own last kernel.
+
+    One process per GPU.  Each rank owns a small *mailbox* in device memory, shared with the other ranks of the
+    node through CUDA IPC; a workspace armed with :meth:`arm` makes the kernel that writes the step's last ``sum``
+    output push all ``n`` sums into row ``rank`` of EVERY mailbox with plain NVLink stores (sequence-tagged 8-byte
+    words, see ``peer_publish`` in csrc/dct_common.cuh).  There is no collective launch and no NCCL kernel
+    competing with the persistent CTAs of the next step; :meth:`read` sums the rows in rank order, so all ranks get
+    bit-identical totals.  ``world == 1`` (no process group) is a loopback on the own mailbox.
+
+    The mailbox is a ring of ``nslots`` publications: read a publication before ``nslots`` newer ones have been
+    made (a reporting interval shorter than the ring), or :meth:`read` reports a sequence mismatch.
+    """
+
+    def __init__(self, device, n: int = 4, nslots: int = 64, group=None):
+        import ctypes as C
+        from . import _lib
+        self._lib, self._C = _lib, C
+        h = _lib.lib()
+        assert 1 <= n <= _lib.PUB_MAX_VALUES and nslots >= 1
+        self.device = torch.device(device)
+        self.n, self.nslots, self.group = n, nslots, group
+        self.world = dist.get_world_size(group) if is_distributed() else 1
+        self.rank = dist.get_rank(group) if is_distributed() else 0
+        if self.world > _lib.MAX_PEERS:
+            raise ValueError(f"PeerExchange serves one node: at most {_lib.MAX_PEERS} ranks")
+        self.words = nslots * self.world * _lib.PUB_ROW_WORDS
+        with torch.cuda.device(self.device):
+            own, handle = C.c_void_p(), C.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+            _lib.check(h.dct_mailbox_create(self.words * 8, C.byref(own), handle), "dct_mailbox_create")
+            self._own = own.value
+            self._ptrs = [None] * self.world
+            self._ptrs[self.rank] = self._own
+            if self.world > 1:
+                handles = [None] * self.world
+                dist.all_gather_object(handles, bytes(handle.raw), group=group)
+                for r in range(self.world):
+                    if r == self.rank:
+                        continue
+                    p = C.c_void_p()
+                    _lib.check(h.dct_mailbox_open(handles[r], C.byref(p)), "dct_mailbox_open")
+                    self._ptrs[r] = p.value
+        self.seq = torch.zeros(1, dtype=torch.int64, device=self.device)   # device-side publication counter
+        self._desc = {}      # workspace pointer -> (descriptor tensor, armed src pointer)
+        self._mail = _as_int64_tensor(self._own, self.words, self.device)   # view of the own mailbox
+        assert int(h.dct_peer_pub_bytes()) == 8 * (5 + _lib.MAX_PEERS)
+
+    def _descriptor(self, trigger_ptr: int, src_ptr: int) -> torch.Tensor:
+        """``dct_peer_pub`` as 13 int64 words: trigger, src, seq, {n, rank}, {world, nslots}, mailbox[8]."""
+        pack = lambda lo, hi: (hi << 32) | lo  # noqa: E731  (two int32 fields per word, little endian)
+        words = [trigger_ptr, src_ptr, self.seq.data_ptr(), pack(self.n, self.rank), pack(self.world, self.nslots)]
+        words += [p or 0 for p in self._ptrs] + [0] * (self._lib.MAX_PEERS - self.world)
+        return torch.tensor([_to_signed64(w) for w in words], dtype=torch.int64, device=self.device)
+
+    def arm(self, workspace: torch.Tensor, sums: torch.Tensor, trigger_index: int) -> bool:
+        """Make launches on ``workspace`` whose ``sum`` output is ``&sums[trigger_index]`` publish ``sums[:n]``.
+        Returns True if an arming kernel was enqueued (False: this workspace is already armed for ``sums``)."""
+        assert sums.dtype == torch.float64 and sums.is_cuda and sums.numel() >= self.n
+        key = workspace.data_ptr()
+        src = sums.data_ptr()
+        trig = src + 8 * trigger_index
+        held = self._desc.get(key)
+        if held is not None and held[1] == (src, trig):
+            return False
+        desc = self._descriptor(trig, src)
+        keep = [] if held is None else held[2] + [held[0]]   # earlier descriptors stay alive (a kernel may still read them)
+        self._desc[key] = (desc, (src, trig), keep[-8:])
+        self._lib.check(self._lib.lib().dct_exchange_arm(workspace.data_ptr(), desc.data_ptr(),
+                                                         torch.cuda.current_stream(self.device).cuda_stream),
+                        "dct_exchange_arm")
+        return True
+
+    def disarm(self, workspace: torch.Tensor) -> None:
+        self._desc.pop(workspace.data_ptr(), None)
+        self._lib.check(self._lib.lib().dct_exchange_arm(workspace.data_ptr(), None,
+                                                         torch.cuda.current_stream(self.device).cuda_stream),
+                        "dct_exchange_arm")
+
+    def published(self) -> int:
+        """Publications this rank has made so far (host sync)."""
+        return int(self.seq.item())
+
+    def read(self, seq: int, check: bool = True) -> torch.Tensor:
+        """Global sums ``[n]`` float64 (device) of publication number ``seq``: the rows of all ranks added in rank
+        order.  ``check`` (one host sync) verifies that every row of the slot carries ``seq``."""
+        R = self._lib.PUB_ROW_WORDS
+        slot = seq % self.nslots
+        rows = self._mail[slot * self.world * R:(slot + 1) * self.world * R].view(self.world, R)[:, :2 * self.n]
+        tags = (rows >> 32) & 0xffffffff
+        if check:
+            bad = int((tags != (seq & 0xffffffff)).sum().item())
+            if bad:
+                raise RuntimeError(f"PeerExchange.read({seq}): {bad} word(s) of slot {slot} carry another sequence number "
+                                   "(publication not arrived yet, or overwritten: ring of %d slots)" % self.nslots)
+        lo = rows & 0xffffffff
+        bits = lo[:, 0::2] | (lo[:, 1::2] << 32)
+        vals = bits.contiguous().view(torch.float64)          # [world, n]
+        total = vals[0].clone()
+        for r in range(1, self.world):                        # fixed rank order: bit-identical on every rank
+            total = total + vals[r]
+        return total
+
+    def close(self) -> None:
+        h = self._lib.lib()
+        torch.cuda.synchronize(self.device)
+        if is_distributed():
+            dist.barrier(group=self.group)                    # nobody unmaps while a peer may still be storing
+        for r, p in enumerate(self._ptrs):
+            if p is not None and r != self.rank:
+                h.dct_mailbox_close(p, 0)
+        if is_distributed():
+            dist.barrier(group=self.group)
+        if self._own is not None:
+            self._mail = None
+            h.dct_mailbox_close(self._own, 1)
+            self._own = None
+        self._ptrs = []
+
+
+def _to_signed64(v: int) -> int:
+    v &= (1 << 64) - 1
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
+class _RawCuda:
+    """Minimal ``__cuda_array_interface__`` holder: a torch view of device memory this library allocated."""
+
+    def __init__(self, ptr: int, nwords: int):
+        self.__cuda_array_interface__ = {"shape": (nwords,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+
+
+def _as_int64_tensor(ptr: int, nwords: int, device) -> torch.Tensor:
+    with torch.cuda.device(device):
+        return torch.as_tensor(_RawCuda(ptr, nwords), device=device)

@@ -78,11 +78,14 @@ class ConsistencyStep:
     """
 
     def __init__(self, K, C, B, H, W, cin=1, jsd_weight=1.0, adv_weight=1.0, xi=1e-6, eps=10.0, kl_eps=1e-10,
-                 n_global: Optional[int] = None, with_vat=True, with_dice=True):
+                 n_global: Optional[int] = None, with_vat=True, with_dice=True, exchange=None):
         self.K, self.C, self.B, self.HW, self.M = K, C, B, H * W, cin * H * W
         self.n = B * H * W if n_global is None else int(n_global)
         self.jsd_weight, self.adv_weight, self.xi, self.eps, self.kl_eps = jsd_weight, adv_weight, xi, eps, kl_eps
         self.with_vat, self.with_dice = with_vat, with_dice
+        # distributed.PeerExchange or None: the kernel that writes the step's last sum also pushes the sums into every
+        # data-parallel rank's mailbox over NVLink (no collective launch)
+        self.exchange = exchange
         self._h = _lib.lib()
         # kernels launched per run(): the JSD kernel (Dice fused for C <= 4, else K counting launches) + 4 VAT/KL
         self.launches_per_step = 1 + (0 if (not with_dice or (C <= 4 and K * C <= 16)) else K) + (4 if with_vat else 0)
@@ -106,6 +109,8 @@ class ConsistencyStep:
         ws, s = st.workspace.data_ptr(), _runtime.stream_ptr(dev)
         fl = _runtime.flags_ptr(st)
         sums = bufs.sums.data_ptr()
+        if self.exchange is not None:  # (re-)arm only when this workspace last published another buffer set
+            self.exchange.arm(st.workspace, bufs.sums, 2 if self.with_vat else 0)
         if self.with_dice and zero_counts:
             bufs.dice_counts.zero_()  # the kernels accumulate into the counters
         _lib.check(h.dct_jsd_fwdbwd_f32(_lib.ptr_array(bufs.logits), K, C, B, HW, _lib.IN_LOGITS,

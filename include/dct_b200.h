@@ -77,6 +77,49 @@ DCT_API int dct_device_check(int ordinal);
 DCT_API size_t dct_workspace_bytes(void);
 
 /* ------------------------------------------------------------------------------------------
+ * Fused cross-rank exchange of the step's loss sums (the reference never shards
+ * this path -- nn.DataParallel gathers to cuda:0, generalframework/models/segmentators.py:34-36 --
+ * and reads every loss with .item() per iteration, trainer/cotraining_totalloss.py:251-264).
+ *
+ * Under batch sharding the only cross-rank coupling of the path is a handful of scalars
+ * (sum of the JSD map, of the KL maps).  Instead of a collective launched after the step, the
+ * kernel that writes the step's LAST `sum` output also pushes all sums into every rank's
+ * "mailbox" with plain stores through NVLink / NVSwitch peer mappings (one process per GPU;
+ * mailboxes are shared with CUDA IPC).  No extra launch, no NCCL kernel competing for SMs.
+ *
+ *   mailbox (device memory of each rank):  uint64 [nslots][world][DCT_PUB_ROW_WORDS]
+ *     publication number q (1, 2, ...) of rank r lands in slot q % nslots, row r, of EVERY
+ *     rank's mailbox.  Value j travels as two words {seq32 << 32 | low 32 data bits},
+ *     {seq32 << 32 | high 32 data bits} with seq32 = q mod 2^32: a reader that finds seq32 in
+ *     a word holds valid data (aligned 8-byte stores are single-copy atomic); summing the rows
+ *     in rank order gives every rank the same bits.
+ *   dct_peer_pub: the descriptor (DEVICE memory, 8-byte aligned) a workspace is armed with;
+ *     a launch whose `sum` argument equals `trigger` publishes src[0..n) when it completes.
+ *     `seq` points at a device counter the kernels increment (zero it once).
+ * ------------------------------------------------------------------------------------------ */
+#define DCT_MAX_PEERS 8
+#define DCT_PUB_ROW_WORDS 16
+#define DCT_PUB_MAX_VALUES 8
+#define DCT_IPC_HANDLE_BYTES 64
+typedef struct dct_peer_pub {
+    const double* trigger;
+    const double* src;
+    unsigned long long* seq;
+    int32_t n, rank, world, nslots;
+    unsigned long long* mailbox[DCT_MAX_PEERS];
+} dct_peer_pub;
+DCT_API size_t dct_peer_pub_bytes(void);
+/* cudaMalloc + zero a mailbox of `bytes` on the current device; *dev_ptr receives it and ipc_handle
+ * (host, DCT_IPC_HANDLE_BYTES) the CUDA IPC handle another process of this node opens it with. */
+DCT_API int dct_mailbox_create(size_t bytes, void** dev_ptr, void* ipc_handle);
+/* map a peer's mailbox into this process (peer access enabled lazily); *dev_ptr receives the mapping */
+DCT_API int dct_mailbox_open(const void* ipc_handle, void** dev_ptr);
+/* owned != 0: cudaFree of a created mailbox; owned == 0: unmap an opened one */
+DCT_API int dct_mailbox_close(void* dev_ptr, int owned);
+/* arm (desc_dev != NULL) or disarm (NULL) `workspace`: enqueues on `stream`; the descriptor must outlive the launches */
+DCT_API int dct_exchange_arm(void* workspace, const void* desc_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * K-view Jensen-Shannon divergence.
  * Replaces JSD_2D.forward (generalframework/loss/loss.py:183-196), JSD.forward (:165-180)
  * and, with DCT_IN_LOGITS, the

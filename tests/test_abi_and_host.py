@@ -49,6 +49,18 @@ def test_library_basics_without_gpu():
         assert h.dct_device_check(0) == -5
 
 
+def test_exchange_descriptor_layout_matches_header():
+    """dct_peer_pub (include/dct_b200.h) is built word by word in distributed.PeerExchange._descriptor."""
+    import dct_b200
+    L = dct_b200._lib
+    txt = open(os.path.join(ROOT, "include", "dct_b200.h")).read()
+    defs = {k: int(v) for k, v in re.findall(r"#define\s+(DCT_\w+)\s+(\d+)\s*$", txt, flags=re.M)}
+    assert (defs["DCT_MAX_PEERS"], defs["DCT_PUB_ROW_WORDS"], defs["DCT_PUB_MAX_VALUES"], defs["DCT_IPC_HANDLE_BYTES"]) == \
+        (L.MAX_PEERS, L.PUB_ROW_WORDS, L.PUB_MAX_VALUES, L.IPC_HANDLE_BYTES)
+    assert L.lib().dct_peer_pub_bytes() == 8 * (5 + L.MAX_PEERS)   # 3 pointers, 4 int32, MAX_PEERS pointers
+    assert 2 * L.PUB_MAX_VALUES <= L.PUB_ROW_WORDS                 # two tagged words per published double
+
+
 def test_alias_import_shares_modules():
     import dct_b200
     import dct_b200.loss as L

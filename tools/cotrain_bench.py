@@ -277,7 +277,7 @@ def main():
         else:
             if world > 1:
                 from torch.nn.parallel import DistributedDataParallel as DDP
-                nets = [DDP(n, device_ids=[local]) for n in nets]
+                nets = [DDP(n, device_ids=[local], gradient_as_bucket_view=True, broadcast_buffers=False) for n in nets]
             fn = lambda: nets_only_iteration(nets, opts, lab, unlab, cfg)  # noqa: E731
             ms, wall = timed(fn)
         line = {"metric": "co-train iterations/sec", "arm": arm, "value": 1e3 / ms, "unit": "iterations/s",
@@ -288,12 +288,11 @@ def main():
         lines.append(line)
         if rank == 0:
             print(json.dumps(line), flush=True)
+            with open(os.path.join(args.out, f"cotrain_{args.config}_n{world}.jsonl"), "w") as f:   # after every arm
+                for ln in lines:
+                    f.write(json.dumps(ln) + "\n")
         del nets, opts
         torch.cuda.empty_cache()
-    if rank == 0:
-        with open(os.path.join(args.out, f"cotrain_{args.config}_n{world}.jsonl"), "w") as f:
-            for ln in lines:
-                f.write(json.dumps(ln) + "\n")
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
