@@ -212,7 +212,7 @@ def run_ours(args, wl):
     # kernel pushes them into every rank's mailbox over NVLink peer memory (distributed.PeerExchange) -- no collective
     # launch; "nccl": one all-reduce per step on a side stream (the baseline this replaces, kept for A/B).
     px, exchange = None, "none"
-    if world > 1:
+    if world > 1 or args.exchange == "p2p":   # (p2p at N = 1: loopback on the own mailbox, for A/B of the fused kernel)
         exchange = args.exchange
         if exchange in ("p2p", "auto"):
             try:
@@ -224,7 +224,8 @@ def run_ours(args, wl):
                     raise
                 print(f"[bench rank {rank}] peer exchange unavailable ({e}); using NCCL", file=sys.stderr)
                 ok = torch.zeros(1, device=dev)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if world > 1:
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             if ok.item() == 0:
                 px = None
             exchange = "p2p" if px is not None else "nccl"
@@ -308,7 +309,8 @@ def run_ours(args, wl):
         q = px.published()
         got = px.read(q)
         last = sets[(args.steps - 1) % R].sums.clone()
-        dist.all_reduce(last)
+        if world > 1:
+            dist.all_reduce(last)
         err = float((got - last[:4]).abs().max().item()) / max(float(last[:4].abs().max().item()), 1e-30)
         assert err <= 1e-12, f"peer exchange disagrees with the NCCL all-reduce of the same sums (rel {err:.2e})"
         exchange_check = {"publications": q, "rel_err_vs_nccl_allreduce": err}

@@ -22,6 +22,13 @@ MAX_PEERS, PUB_ROW_WORDS, PUB_MAX_VALUES, IPC_HANDLE_BYTES = 8, 16, 8, 64
 
 _p, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
+
+class PeerPub(C.Structure):
+    """``dct_peer_pub`` of include/dct_b200.h (host struct; device pointers inside)."""
+    _fields_ = [("src", C.c_void_p), ("seq", C.c_void_p), ("n", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
+                ("nslots", C.c_int32), ("mailbox", C.c_void_p * 8)]
+
+
 # name -> argtypes (restype is int unless listed in _RESTYPES); must match include/dct_b200.h
 _SIGNATURES = {
     "dct_abi_version": [],
@@ -52,6 +59,7 @@ _SIGNATURES = {
     "dct_ce_fwd_f32": [_p, _p, _i, _i64, _i64, _p, _i64, _p, _p, _p, _p, _p],
     "dct_ce_bwd_f32": [_p, _p, _i, _i64, _i64, _p, _i64, _p, _p, _f, _p, _p, _p],
     "dct_ce_fwdbwd_f32": [_p, _p, _i, _i64, _i64, _p, _i64, _p, _f, _p, _p, _p, _p, _p, _p, _p],
+    "dct_ce_fwdbwd_conf_f32": [_p, _p, _i, _i64, _i64, _p, _i64, _p, _f, _p, _p, _p, _p, _p, _p, _p],
     "dct_classmap_f32": [_p, _i, _i64, _i64, _i, _p, _p, _p, _p, _p],
     "dct_onehot_from_labels_i64": [_p, _i, _i64, _i64, _p, _p, _p],
     "dct_onehot_dice_counts_i32": [_p, _p, _i, _i64, _i64, _p, _p, _p],
@@ -64,7 +72,8 @@ _SIGNATURES = {
     "dct_mailbox_create": [C.c_size_t, _p, _p],
     "dct_mailbox_open": [_p, _p],
     "dct_mailbox_close": [_p, _i],
-    "dct_exchange_arm": [_p, _p, _p],
+    "dct_exchange_publish": [_p, _p],
+    "dct_kl_from_logits_fwdbwd_pub_f32": [_p, _p, _i, _i64, _i64, _f, _f, _p, _p, _p, _p, _p, _p, _p],
 }
 _RESTYPES = {"dct_error_string": C.c_char_p, "dct_last_cuda_error": C.c_char_p, "dct_workspace_bytes": C.c_size_t,
              "dct_peer_pub_bytes": C.c_size_t}

@@ -87,13 +87,30 @@ extern "C" int dct_mailbox_close(void* dev_ptr, int owned) {
 }
 
 namespace dct {
-__global__ void exchange_arm_kernel(Workspace* ws, PeerPub* desc) { ws->pub = desc; }
+__global__ void exchange_publish_kernel(const PeerPub pub) {
+    PeerVals pv;
+    peer_prefetch(pub, pv);
+    peer_publish(pub, pv, nullptr, 0.0);
+}
+int check_pub(const dct_peer_pub* d) {
+    if (d == nullptr || d->src == nullptr || d->seq == nullptr) return DCT_ERR_BAD_ARG;
+    if (d->n < 1 || d->n > DCT_PUB_MAX_VALUES || d->world < 1 || d->world > DCT_MAX_PEERS || d->rank < 0 ||
+        d->rank >= d->world || d->nslots < 1)
+        return DCT_ERR_BAD_ARG;
+    for (int p = 0; p < d->world; ++p) {
+        if (d->mailbox[p] == nullptr) return DCT_ERR_BAD_ARG;
+        if (!aligned(d->mailbox[p], 16)) return DCT_ERR_MISALIGNED;
+    }
+    if (!aligned(d->src, 8) || !aligned(d->seq, 8)) return DCT_ERR_MISALIGNED;
+    return DCT_OK;
+}
 }  // namespace dct
 
-extern "C" int dct_exchange_arm(void* workspace, const void* desc_dev, void* stream) {
-    if (workspace == nullptr) return DCT_ERR_BAD_ARG;
-    if (!aligned(workspace, 8) || !aligned(desc_dev, 8)) return DCT_ERR_MISALIGNED;
-    exchange_arm_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<Workspace*>(workspace), static_cast<PeerPub*>(const_cast<void*>(desc_dev)));
+extern "C" int dct_exchange_publish(const dct_peer_pub* desc, void* stream) {
+    int rc = check_pub(desc);
+    if (rc != DCT_OK) return rc;
+    PeerPub pub;
+    std::memcpy(&pub, desc, sizeof(pub));
+    exchange_publish_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(pub);
     return check_launch();
 }

@@ -18,12 +18,13 @@ template <> struct lanes_of<f2> { static constexpr int value = 2; };
 __device__ __forceinline__ float vfrom(const float (&w)[1]) { return w[0]; }
 __device__ __forceinline__ f2 vfrom(const float (&w)[2]) { return mk2(w[0], w[1]); }
 
-// GRAD: x[0][c] <- g * w * (p_c - onehot_c);  DICEF: the tile kernel also counts Dice (I,G,P) of the same logits
-template <bool GRAD, bool DICEF, bool GMAPV>
+// GRAD: x[0][c] <- g * w * (p_c - onehot_c);  DICEF: the tile kernel also counts Dice (I,G,P) of the same logits;
+// CONFV: it also counts the confusion matrix of arg-max(logits) against the labels (the Cityscapes trainers' IoU meter)
+template <bool GRAD, bool DICEF, bool GMAPV, bool CONFV = false>
 struct CeOp {
     static constexpr int NIN = 1, NOUT = GRAD ? 1 : 0;
     static constexpr int NDICE = DICEF ? 1 : 0;
-    static constexpr bool GMAP = GMAPV, LABELS = true;
+    static constexpr bool GMAP = GMAPV, LABELS = true, CONF = CONFV;
     static constexpr bool HAS_MAP = true, USES_UP = GRAD, CHECKS_SIMPLEX = false;
     template <int CM, class T>
     static __device__ __forceinline__ T apply(T (&)[1][CM], int, T, float, bool&) { return vset<T>(0.0f); }  // unused
@@ -133,9 +134,11 @@ __global__ void __launch_bounds__(256) ce_kernel_rt(const CeArgs a) {
 }
 
 template <class Op, class ET = float>
-static int ce_tile(const CeArgs& c, int64_t B, unsigned long long* counts, cudaStream_t stream, bool& done) {
+static int ce_tile(const CeArgs& c, int64_t B, unsigned long long* counts, cudaStream_t stream, bool& done,
+                   unsigned long long* conf = nullptr) {
     done = false;
     TileArgs t{};
+    t.conf = conf;
     t.in[0] = c.x; t.out[0] = c.grad;
     t.HW = c.HW; t.map = c.map; t.sum = c.sum; t.up = c.up; t.eps = 0.0f; t.flags = c.flags; t.ws = c.ws;
     t.labels = c.labels; t.counts = counts; t.count_view_stride = B * c.C * 3;
@@ -263,6 +266,30 @@ extern "C" int dct_ce_fwdbwd_f32(const float* logits, const int64_t* labels, int
     if (dice_counts != nullptr)  // Dice counting of the same logits in its own launch (C > 4 or a non-tile shape)
         return dct_dice_counts_f32(logits, labels, C, B, HW, dice_counts, 1, flags, stream);
     return DCT_OK;
+}
+
+// Cityscapes flavour of the labeled loop (generalframework/trainer/cotraining_city.py:236-241, trainer_city.py:141):
+//   sup_loss = criterions['sup'](pred, gt.squeeze(1));  metrics[k].add(predicted=pred, target=gt)      (IoU meter)
+// One read of the logits + labels gives the loss, its gradient and conf[gt][argmax pred] (int64 [C,C], accumulated).
+extern "C" int dct_ce_fwdbwd_conf_f32(const float* logits, const int64_t* labels, int C, int64_t B, int64_t HW,
+                                      const float* class_weight, int64_t ignore_index, const float* gscalar, float gconst,
+                                      float* map, double* sum, float* grad_logits, int64_t* confusion, int32_t* flags,
+                                      void* workspace, void* stream) {
+    int rc = ce_check(logits, labels, C, B, HW);
+    if (rc != DCT_OK) return rc;
+    if (grad_logits == nullptr || confusion == nullptr || (sum != nullptr && workspace == nullptr)) return DCT_ERR_BAD_ARG;
+    if (!aligned(grad_logits, 4) || !aligned(confusion, 8) || (map != nullptr && !aligned(map, 4))) return DCT_ERR_MISALIGNED;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CeArgs c{logits, labels, class_weight, ignore_index, C, HW, map, sum, grad_logits, Upstream{nullptr, gscalar, gconst}, flags,
+             static_cast<Workspace*>(workspace)};
+    bool done = false;
+    rc = ce_tile<CeOp<true, false, false, true>>(c, B, nullptr, s, done, reinterpret_cast<unsigned long long*>(confusion));
+    if (rc != DCT_OK || done) return rc;
+    // not a tile shape: the loss kernels, then the counting kernel on the same tensors
+    rc = dct_ce_fwdbwd_f32(logits, labels, C, B, HW, class_weight, ignore_index, gscalar, gconst, map, sum, grad_logits,
+                           nullptr, flags, workspace, stream);
+    if (rc != DCT_OK) return rc;
+    return dct_confusion_f32(logits, labels, C, B, HW, confusion, stream);
 }
 
 // bf16 logits / gradients (fp32 math, fp32 map / sum): the tile pipeline only; DCT_ERR_UNSUPPORTED for other shapes

@@ -14,10 +14,9 @@ constexpr int kSMs = 148;             // B200: 2 dies x 74 SMs
 constexpr int kMaxPartials = 8192;    // per-launch CTA partial sums kept in the workspace
 constexpr float kEntEps = 1e-16f;     // Entropy / Entropy_2D epsilon (generalframework/loss/loss.py:64,81)
 
-// Peer publication descriptor ("dct_peer_pub" in include/dct_b200.h): where the last CTA of a launch pushes a step's
-// loss sums -- straight into every data-parallel rank's mailbox over NVLink (see peer_publish below).
+// Peer publication descriptor ("dct_peer_pub" in include/dct_b200.h): where the last CTA of a *_pub launch pushes a
+// step's loss sums -- straight into every data-parallel rank's mailbox over NVLink (see peer_publish below).
 struct PeerPub {
-    const double* trigger;                     // publish when the launch's `sum` output pointer equals this
     const double* src;                         // n doubles (local device memory) holding the step's sums
     unsigned long long* seq;                   // device counter of publications made so far (shared by the descriptors of a rank)
     int n, rank, world, nslots;
@@ -25,7 +24,7 @@ struct PeerPub {
 };
 static_assert(sizeof(PeerPub) == sizeof(dct_peer_pub), "PeerPub mirrors dct_peer_pub");
 
-// workspace layout: 64-byte header (all fields but `pub` zero between launches: the last CTA of a launch re-arms them)
+// workspace layout: 64-byte header (all fields zero between launches: the last CTA of a launch re-arms them)
 // followed by kMaxPartials double partials
 struct Workspace {
     unsigned int ticket;         // CTAs that have finished
@@ -34,8 +33,7 @@ struct Workspace {
     unsigned int pad0;
     unsigned long long fx_lo;    // order-independent loss sum in 2^-40 fixed point: sum of the low 32 bits ...
     long long fx_hi;             // ... and of the (signed) high bits of every partial
-    PeerPub* pub;                // null, or the armed publication descriptor (dct_exchange_arm); persistent
-    unsigned int pad[6];
+    unsigned int pad[8];
     double partials[kMaxPartials];
 };
 static_assert(offsetof(Workspace, partials) == 64, "workspace header is 64 bytes");
@@ -53,6 +51,7 @@ struct Views {
 };
 
 thread_local inline cudaError_t g_last_cuda_error = cudaSuccess;
+int check_pub(const dct_peer_pub* d);  // dct_abi.cu: validates a host-side publication descriptor
 
 inline int check_launch() {
     cudaError_t e = cudaGetLastError();
@@ -177,27 +176,44 @@ __device__ __forceinline__ float warp_sum(float v) {
 // two 8-byte words {32 data bits | 32-bit sequence number}: an aligned 8-byte store is single-copy atomic, so a
 // reader that sees the expected sequence number in a word also sees its data -- no fence, no flag round trip
 // (the "LL" scheme of NCCL's low-latency protocol).  Mailbox row: DCT_PUB_ROW_WORDS u64; slot = seq % nslots.
+// The descriptor travels BY VALUE in the kernel parameters and the older sums + the sequence counter are fetched
+// before the ticket atomic (peer_prefetch), so the publication adds no memory round trip to the kernel's tail.
+// Only the *_pub kernel variants contain this code (a compile-time switch): measured on B200, linking a hook into
+// every kernel's finisher cost 5.6 us per c2 step.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void peer_publish(PeerPub* pub) {
-    const unsigned long long q = __ldcg(pub->seq) + 1ull;
+struct PeerVals {
+    unsigned long long seq;
+    double v[DCT_PUB_MAX_VALUES];
+};
+__device__ __forceinline__ void peer_prefetch(const PeerPub& pub, PeerVals& pv) {
+    pv.seq = __ldcg(pub.seq);
+#pragma unroll
+    for (int j = 0; j < DCT_PUB_MAX_VALUES; ++j) pv.v[j] = j < pub.n ? __ldcg(pub.src + j) : 0.0;
+}
+// `fresh` / `fresh_ptr`: the sum this launch has just produced (it replaces the prefetched value of that slot)
+__device__ __forceinline__ void peer_publish(const PeerPub& pub, PeerVals& pv, const double* fresh_ptr, double fresh) {
+    const unsigned long long q = pv.seq + 1ull;
     const unsigned long long tag = (q & 0xffffffffull) << 32;
-    const int n = pub->n, world = pub->world;
-    const size_t row = ((size_t)(q % (unsigned long long)pub->nslots) * world + pub->rank) * DCT_PUB_ROW_WORDS;
-    for (int j = 0; j < n; ++j) {
-        const unsigned long long bits = (unsigned long long)__double_as_longlong(__ldcg(pub->src + j));
-        const unsigned long long w0 = tag | (bits & 0xffffffffull), w1 = tag | (bits >> 32);
-        for (int p = 0; p < world; ++p) {
-            unsigned long long* dst = pub->mailbox[p] + row + 2 * j;
-            asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(w0), "l"(w1) : "memory");
+    const size_t row = ((size_t)(q % (unsigned long long)pub.nslots) * pub.world + pub.rank) * DCT_PUB_ROW_WORDS;
+#pragma unroll
+    for (int j = 0; j < DCT_PUB_MAX_VALUES; ++j) {
+        if (j < pub.n) {
+            const double val = (pub.src + j == fresh_ptr) ? fresh : pv.v[j];
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(val);
+            const unsigned long long w0 = tag | (bits & 0xffffffffull), w1 = tag | (bits >> 32);
+#pragma unroll
+            for (int p = 0; p < DCT_MAX_PEERS; ++p) {
+                if (p < pub.world) {
+                    // volatile 8-byte stores = st.volatile (relaxed, system scope; SASS STG.E.64.STRONG.SYS); every word
+                    // carries its own tag
+                    volatile unsigned long long* vd = pub.mailbox[p] + row + 2 * j;
+                    vd[0] = w0;
+                    vd[1] = w1;
+                }
+            }
         }
     }
-    *pub->seq = q;
-}
-__device__ __forceinline__ void maybe_publish(Workspace* ws, const double* out) {
-#ifndef DCT_NO_PUBLISH  // developer A/B switch (a build without the hook; never defined in the product build)
-    PeerPub* pub = ws->pub;
-    if (pub != nullptr && out == pub->trigger) peer_publish(pub);
-#endif
+    *pub.seq = q;
 }
 
 // Deterministic grid-wide sum of one double per thread.  Every CTA writes its partial to the
@@ -236,7 +252,6 @@ __device__ __forceinline__ void grid_sum_to(double v, Workspace* ws, double* out
             t = warp_sum(t);
             if (lane == 0) {
                 *out = t;
-                maybe_publish(ws, out);
                 ws->ticket = 0u;
             }
         }
@@ -264,7 +279,9 @@ __device__ __forceinline__ long long warp_sum(long long v) {
 
 // Called by every thread of the CTA at the end of a tile-pipeline kernel.  `out` may be null.
 // Also re-arms the workspace header (ticket, tile counter, accumulators) when the last CTA is through.
-__device__ __forceinline__ void tile_grid_finish(long long acc_fx, bool nonfinite, Workspace* ws, double* out, int num_ctas) {
+template <bool PUB = false>
+__device__ __forceinline__ void tile_grid_finish(long long acc_fx, bool nonfinite, Workspace* ws, double* out, int num_ctas,
+                                                 const PeerPub* pub = nullptr) {
     if (ws == nullptr) return;
     __shared__ long long s_lo[20], s_hi[20];  // <= 17 warps per CTA
     __shared__ int s_nf;
@@ -280,6 +297,8 @@ __device__ __forceinline__ void tile_grid_finish(long long acc_fx, bool nonfinit
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+        PeerVals pv;
+        if constexpr (PUB) peer_prefetch(*pub, pv);  // in flight while the atomics below make their round trips
         if (out != nullptr) {
             long long lo = 0, hi = 0;
             for (int w = 0; w < nw; ++w) { lo += s_lo[w]; hi += s_hi[w]; }
@@ -296,8 +315,9 @@ __device__ __forceinline__ void tile_grid_finish(long long acc_fx, bool nonfinit
                 const long long hi = __ldcg(&ws->fx_hi);
                 const unsigned int nf = __ldcg(&ws->nonfinite);
                 const double total = ((double)hi * 4294967296.0 + (double)lo) * (1.0 / 1099511627776.0);
-                *out = nf ? __longlong_as_double(0x7ff8000000000000ll) : total;
-                maybe_publish(ws, out);
+                const double fin = nf ? __longlong_as_double(0x7ff8000000000000ll) : total;
+                *out = fin;
+                if constexpr (PUB) peer_publish(*pub, pv, out, fin);  // the step's sums -> every rank's mailbox (NVLink)
                 ws->fx_lo = 0ull;
                 ws->fx_hi = 0ll;
                 ws->nonfinite = 0u;

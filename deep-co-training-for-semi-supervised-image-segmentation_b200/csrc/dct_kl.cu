@@ -1,5 +1,7 @@
 // dct_kl.cu -- the adversarial branch's KL family, entropy and softmax as pixelwise ops
 // (dct_pixelwise.cuh) plus their C-ABI entry points (include/dct_b200.h).
+#include <cstring>
+
 #include "dct_pixelwise.cuh"
 
 namespace dct {
@@ -314,6 +316,39 @@ extern "C" int dct_kl_from_logits_fwdbwd_f32(const float* p_logit, const float* 
     PixArgs a = make_args(p_logit, y_prob, grad_p_logit, nullptr, C, HW, map, sum, Upstream{nullptr, nullptr, gconst},
                           eps, flags, workspace);
     return pix_launch<KlFromLogits>(a, B, static_cast<cudaStream_t>(stream));
+}
+
+// The adversarial KL is the LAST kernel of a consistency step (JSD -> VAT -> KL): this variant's last CTA also pushes the
+// step's loss sums into every data-parallel rank's mailbox over NVLink (include/dct_b200.h, "Fused cross-rank exchange").
+extern "C" int dct_kl_from_logits_fwdbwd_pub_f32(const float* p_logit, const float* y_prob, int C, int64_t B, int64_t HW,
+                                                 float eps, float gconst, float* map, double* sum, float* grad_p_logit,
+                                                 int32_t* flags, void* workspace, const dct_peer_pub* pub_desc,
+                                                 void* stream) {
+    if (sum == nullptr) return DCT_ERR_BAD_ARG;
+    int prc = check_pub(pub_desc);
+    if (prc != DCT_OK) return prc;
+    PixArgs a = make_args(p_logit, y_prob, grad_p_logit, nullptr, C, HW, map, sum, Upstream{nullptr, nullptr, gconst},
+                          eps, flags, workspace);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (C >= 1 && B >= 1 && HW >= 1 && p_logit != nullptr && y_prob != nullptr && workspace != nullptr && B <= 65535) {
+        TileArgs t{};
+        t.in[0] = a.in[0]; t.in[1] = a.in[1]; t.out[0] = a.out[0];
+        t.HW = a.HW; t.map = a.map; t.sum = a.sum; t.up = a.up; t.eps = a.eps; t.flags = a.flags; t.ws = a.ws;
+        std::memcpy(&t.pub, pub_desc, sizeof(t.pub));
+        if (tile_eligible<KlFromLogits>(t, B)) {
+            switch (C) {
+                case 2: return tile_launch_ct<KlFromLogits, 2, float, true>(t, B, st);
+                case 3: return tile_launch_ct<KlFromLogits, 3, float, true>(t, B, st);
+                case 4: return tile_launch_ct<KlFromLogits, 4, float, true>(t, B, st);
+                case 19: return tile_launch_ct<KlFromLogits, 19, float, true>(t, B, st);
+                default: break;
+            }
+        }
+    }
+    // shapes outside the tile pipeline: the plain kernels, then the stand-alone publication
+    int rc = pix_launch<KlFromLogits>(a, B, st);
+    if (rc != DCT_OK) return rc;
+    return dct_exchange_publish(pub_desc, stream);
 }
 
 extern "C" int dct_kl_div_fwd_f32(const float* p, const float* q, int C, int64_t B, int64_t HW, float eps, float* map,

@@ -24,6 +24,9 @@
 //   LABELS (optional) the op itself consumes the int64 label of every pixel (supervised cross-entropy): it then
 //                    provides apply_lab<CM>(x, C, g, cls[LW], w[LW], bad) instead, with cls = label in [0,C) or -1
 //                    (ignored / out of range) and w = class weight of the label (0 when cls < 0 or ignored)
+//   CONF (optional)  the kernel also counts the confusion matrix conf[gt][argmax x] of input tensor 0 against the labels
+//                    (IoU.add / ConfusionMatrix.add, generalframework/metrics/iou.py:43-69, confusionmatrix.py:32-85):
+//                    raw arg-max with torch.max semantics, labels outside [0,C) dropped (ignore-255 included)
 #pragma once
 #include <cuda_bf16.h>
 
@@ -90,6 +93,8 @@ struct TileArgs {
     const int64_t* labels;         // Dice: [B,HW] int64 (NDICE > 0 and non-null => count)
     unsigned long long* counts;    // Dice: [NDICE][B][C][3] (I,G,P), accumulated into
     int64_t count_view_stride;     // B*C*3
+    PeerPub pub;                   // *_pub launches (PUB kernels): publication descriptor of the step's sums, by value
+    unsigned long long* conf;      // CONF ops: [C][C] int64 (rows = ground truth), accumulated into; null = not counted
     const float* class_w;          // LABELS ops: per-class weight [C] (device) or null = 1
     int64_t ignore_index;          // LABELS ops: label value that contributes nothing (nn.NLLLoss ignore_index)
     int tiles_per_image;
@@ -104,8 +109,12 @@ template <class Op, class = void>
 struct op_labels : std::false_type {};
 template <class Op>
 struct op_labels<Op, std::enable_if_t<Op::LABELS>> : std::true_type {};
+template <class Op, class = void>
+struct op_conf : std::false_type {};
 template <class Op>
-constexpr bool op_label_row() { return Op::NDICE > 0 || op_labels<Op>::value; }
+struct op_conf<Op, std::enable_if_t<Op::CONF>> : std::true_type {};
+template <class Op>
+constexpr bool op_label_row() { return Op::NDICE > 0 || op_labels<Op>::value || op_conf<Op>::value; }
 
 // data rows + optional side rows: int64 labels (Dice / label ops) and the fp32 upstream-gradient map (backward ops);
 // in BYTES per pixel
@@ -148,14 +157,15 @@ struct TileCfg {
 //       No CTA-wide barrier in the tile loop: a fast warp runs ahead by up to STAGES-1 tiles.
 // Nothing depends on WHICH CTA processes a tile: Dice counts are integer atomics, the loss sum is accumulated in
 // exact fixed point (tile_grid_finish), so results are bit-reproducible under the dynamic part of the schedule.
-template <class Op, int CT, int PPT, int NCW, int STAGES, int MINB = 1, class ET = float>
+template <class Op, int CT, int PPT, int NCW, int STAGES, int MINB = 1, class ET = float, bool PUB = false>
 __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArgs a) {
     constexpr int CTHREADS = NCW * 32;
     using Cfg = TileCfg<Op, CT, PPT, CTHREADS, STAGES, ET>;
     constexpr int TP = Cfg::TP, ROWS = Cfg::ROWS, ES = Cfg::ES, NIN = Op::NIN, NOUT = Op::NOUT, C = CT;
     constexpr bool DICE = Op::NDICE > 0;
     constexpr bool LAB = op_labels<Op>::value;   // the op consumes the labels itself
-    constexpr bool LROW = DICE || LAB;           // the stage carries a label row
+    constexpr bool CONF = op_conf<Op>::value;    // confusion counts of tensor 0 vs the labels (CTA-shared histogram)
+    constexpr bool LROW = DICE || LAB || CONF;   // the stage carries a label row
     constexpr int LW = (PPT % 2 == 0) ? 2 : 1;   // pixels per math lane group: pairs use packed FP32x2
     constexpr int NG = PPT / LW;
     using T = typename std::conditional<LW == 2, f2, float>::type;
@@ -166,12 +176,17 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + Cfg::kStageBytes * STAGES);
     uint64_t* done = full + STAGES;
     __shared__ int s_tile[STAGES];  // tile index held by each stage; -1 = end of work
+    __shared__ unsigned int s_conf[CONF ? CT * CT : 1];   // this CTA's confusion counts (flushed once, at the end)
     const int tid = threadIdx.x, lane = tid & 31;
     const bool is_producer = tid >= CTHREADS;
     const int64_t HW = a.HW;
     const int tpi = a.tiles_per_image;
     const bool do_lab = LROW && a.labels != nullptr;
     const bool do_dice = DICE && do_lab;
+    const bool do_conf = CONF && do_lab && a.conf != nullptr;
+    if constexpr (CONF) {
+        for (int i = tid; i < CT * CT; i += (int)blockDim.x) s_conf[i] = 0u;
+    }
     const bool has_gmap = Op::GMAP && a.up.gmap != nullptr;
     const bool dynamic = a.ws != nullptr && !a.force_static;
 
@@ -373,6 +388,7 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
             unsigned char* st = stages + (size_t)stage * Cfg::kStageBytes;
             const int p0 = tid * PPT;
             const bool active = p0 < len;
+            const unsigned int amask = CONF ? __ballot_sync(0xffffffffu, active) : 0u;  // lanes that enter the block below
             unsigned int pk[DICE ? Op::NDICE : 1][2];  // this tile's packed 8-bit per-class counters: [view][I,P]
             unsigned int pkG = 0u;                     // |gt == c| is the same for every view
             if constexpr (DICE) {
@@ -437,6 +453,23 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
                                     pk[n][1] += hot;
                                     pk[n][0] += hot & gmask;
                                 }
+                            }
+                        }
+                    }
+                    if constexpr (CONF) {
+                        if (do_conf) {
+                            // lanes holding the same (gt, pred) cell elect a leader that adds their number to the CTA's
+                            // histogram: one shared-memory atomic per distinct cell and warp instead of one per pixel
+#pragma unroll
+                            for (int j = 0; j < LW; ++j) {
+                                const uint2 lb = lab[gi * LW + j];
+                                const bool valid = (lb.y == 0u) & (lb.x < (unsigned int)C);  // 0 <= int64 label < C
+                                float xs[C];
+#pragma unroll
+                                for (int c = 0; c < C; ++c) xs[c] = vget(x[0][c], j);
+                                const int key = valid ? (int)lb.x * C + raw_argmax<C>(xs) : -1;
+                                const unsigned int peers = __match_any_sync(amask, key);
+                                if (key >= 0 && lane == __ffs((int)peers) - 1) atomicAdd(&s_conf[key], (unsigned int)__popc(peers));
                             }
                         }
                     }
@@ -516,12 +549,21 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
     // this CTA's tiles are done: the next kernel in the stream may be scheduled onto the SMs that drain first and run
     // its prologue; its pdl_wait() still holds it until this whole grid (epilogue below included) has completed
     pdl_launch_dependents();
+    if constexpr (CONF) {
+        __syncthreads();  // every consumer warp's shared-memory atomics are done
+        if (do_conf) {
+            for (int i = tid; i < CT * CT; i += (int)blockDim.x) {
+                const unsigned int v = s_conf[i];
+                if (v != 0u) atomicAdd(a.conf + i, (unsigned long long)v);
+            }
+        }
+    }
     if constexpr (Op::CHECKS_SIMPLEX) {
         if (a.flags != nullptr && __syncthreads_or(bad)) {
             if (bad) atomicAdd(&a.flags[DCT_FLAG_SIMPLEX], 1);
         }
     }
-    tile_grid_finish(acc_fx, nonfinite, a.ws, Op::HAS_MAP ? a.sum : nullptr, gridDim.x);
+    tile_grid_finish<PUB>(acc_fx, nonfinite, a.ws, Op::HAS_MAP ? a.sum : nullptr, gridDim.x, &a.pub);
     if (a.trace != nullptr && tid == 0) a.trace[2 * blockIdx.x + 1] = globaltimer_ns();
 }
 
@@ -539,7 +581,7 @@ inline bool tile_eligible(const TileArgs& a, int64_t B) {
     return true;
 }
 
-template <class Op, int CT, class ET = float>
+template <class Op, int CT, class ET = float, bool PUB = false>
 int tile_launch_ct(TileArgs a, int64_t B, cudaStream_t stream) {
     constexpr int ROWS = Op::NIN * CT;
     static_assert(ROWS <= kTileMaxRows, "tile pipeline instantiations are for NIN*C <= 80");
@@ -561,7 +603,7 @@ int tile_launch_ct(TileArgs a, int64_t B, cudaStream_t stream) {
     // simply buy more stages
     constexpr int STAGES = tile_stages<tile_row_bytes<Op, CT, ET>(), PPT, NCW * 32, MINB, 1>();
     using Cfg = TileCfg<Op, CT, PPT, NCW * 32, STAGES, ET>;
-    auto kern = tile_kernel<Op, CT, PPT, NCW, STAGES, MINB, ET>;
+    auto kern = tile_kernel<Op, CT, PPT, NCW, STAGES, MINB, ET, PUB>;
     static bool configured[64] = {};  // per instantiation and device (the attribute is per device function)
     int devid = 0;
     cudaGetDevice(&devid);

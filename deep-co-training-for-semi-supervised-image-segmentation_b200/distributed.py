@@ -72,9 +72,9 @@ class PeerExchange:
     """Every rank's loss sums in every rank's HBM, written by the step's own last kernel.
 
     One process per GPU.  Each rank owns a small *mailbox* in device memory, shared with the other ranks of the
-    node through CUDA IPC; a workspace armed with :meth:`arm` makes the kernel that writes the step's last ``sum``
-    output push all ``n`` sums into row ``rank`` of EVERY mailbox with plain NVLink stores (sequence-tagged 8-byte
-    words, see ``peer_publish`` in csrc/dct_common.cuh).  There is no collective launch and no NCCL kernel
+    node through CUDA IPC; the step's last kernel (``dct_kl_from_logits_fwdbwd_pub_f32``, handed the descriptor
+    :meth:`descriptor` builds for the step's ``sums`` buffer) pushes all ``n`` sums into row ``rank`` of EVERY mailbox
+    with plain NVLink stores (sequence-tagged 8-byte words, see ``peer_publish`` in csrc/dct_common.cuh).  There is no collective launch and no NCCL kernel
     competing with the persistent CTAs of the next step; :meth:`read` sums the rows in rank order, so all ranks get
     bit-identical totals.  ``world == 1`` (no process group) is a loopback on the own mailbox.
 
@@ -111,40 +111,30 @@ class PeerExchange:
                     _lib.check(h.dct_mailbox_open(handles[r], C.byref(p)), "dct_mailbox_open")
                     self._ptrs[r] = p.value
         self.seq = torch.zeros(1, dtype=torch.int64, device=self.device)   # device-side publication counter
-        self._desc = {}      # workspace pointer -> (descriptor tensor, armed src pointer)
+        self._desc = {}      # sums pointer -> dct_peer_pub (host struct)
         self._mail = _as_int64_tensor(self._own, self.words, self.device)   # view of the own mailbox
-        assert int(h.dct_peer_pub_bytes()) == 8 * (5 + _lib.MAX_PEERS)
+        assert int(h.dct_peer_pub_bytes()) == 8 * (4 + _lib.MAX_PEERS)
 
-    def _descriptor(self, trigger_ptr: int, src_ptr: int) -> torch.Tensor:
-        """``dct_peer_pub`` as 13 int64 words: trigger, src, seq, {n, rank}, {world, nslots}, mailbox[8]."""
-        pack = lambda lo, hi: (hi << 32) | lo  # noqa: E731  (two int32 fields per word, little endian)
-        words = [trigger_ptr, src_ptr, self.seq.data_ptr(), pack(self.n, self.rank), pack(self.world, self.nslots)]
-        words += [p or 0 for p in self._ptrs] + [0] * (self._lib.MAX_PEERS - self.world)
-        return torch.tensor([_to_signed64(w) for w in words], dtype=torch.int64, device=self.device)
+    def descriptor(self, sums: torch.Tensor):
+        """``dct_peer_pub`` (a host-side ctypes struct, copied into the kernel parameters by the ``*_pub`` entry
+        points) publishing ``sums[:n]``; cached per ``sums`` buffer.  Pass ``ctypes.byref`` of it to the C ABI."""
+        assert sums.dtype == torch.float64 and sums.is_cuda and sums.numel() >= self.n and sums.is_contiguous()
+        key = sums.data_ptr()
+        desc = self._desc.get(key)
+        if desc is None:
+            desc = self._lib.PeerPub()
+            desc.src, desc.seq = key, self.seq.data_ptr()
+            desc.n, desc.rank, desc.world, desc.nslots = self.n, self.rank, self.world, self.nslots
+            for r, ptr in enumerate(self._ptrs):
+                desc.mailbox[r] = ptr
+            self._desc[key] = desc
+        return desc
 
-    def arm(self, workspace: torch.Tensor, sums: torch.Tensor, trigger_index: int) -> bool:
-        """Make launches on ``workspace`` whose ``sum`` output is ``&sums[trigger_index]`` publish ``sums[:n]``.
-        Returns True if an arming kernel was enqueued (False: this workspace is already armed for ``sums``)."""
-        assert sums.dtype == torch.float64 and sums.is_cuda and sums.numel() >= self.n
-        key = workspace.data_ptr()
-        src = sums.data_ptr()
-        trig = src + 8 * trigger_index
-        held = self._desc.get(key)
-        if held is not None and held[1] == (src, trig):
-            return False
-        desc = self._descriptor(trig, src)
-        keep = [] if held is None else held[2] + [held[0]]   # earlier descriptors stay alive (a kernel may still read them)
-        self._desc[key] = (desc, (src, trig), keep[-8:])
-        self._lib.check(self._lib.lib().dct_exchange_arm(workspace.data_ptr(), desc.data_ptr(),
-                                                         torch.cuda.current_stream(self.device).cuda_stream),
-                        "dct_exchange_arm")
-        return True
-
-    def disarm(self, workspace: torch.Tensor) -> None:
-        self._desc.pop(workspace.data_ptr(), None)
-        self._lib.check(self._lib.lib().dct_exchange_arm(workspace.data_ptr(), None,
-                                                         torch.cuda.current_stream(self.device).cuda_stream),
-                        "dct_exchange_arm")
+    def publish(self, sums: torch.Tensor) -> None:
+        """Stand-alone publication (one-thread kernel) for steps whose last kernel has no fused variant."""
+        self._lib.check(self._lib.lib().dct_exchange_publish(self._C.byref(self.descriptor(sums)),
+                                                             torch.cuda.current_stream(self.device).cuda_stream),
+                        "dct_exchange_publish")
 
     def published(self) -> int:
         """Publications this rank has made so far (host sync)."""

@@ -15,6 +15,7 @@ Where the step sits in the reference iteration (generalframework/trainer/cotrain
 The network forward/backward passes between those points stay in PyTorch/cuDNN; here their
 outputs are whatever tensors the caller binds (synthetic ones in bench.py).
 """
+import ctypes
 from dataclasses import dataclass
 from typing import List, Optional
 
@@ -88,7 +89,8 @@ class ConsistencyStep:
         self.exchange = exchange
         self._h = _lib.lib()
         # kernels launched per run(): the JSD kernel (Dice fused for C <= 4, else K counting launches) + 4 VAT/KL
-        self.launches_per_step = 1 + (0 if (not with_dice or (C <= 4 and K * C <= 16)) else K) + (4 if with_vat else 0)
+        self.launches_per_step = 1 + (0 if (not with_dice or (C <= 4 and K * C <= 16)) else K) + (4 if with_vat else 0) + \
+            (1 if (exchange is not None and not with_vat) else 0)
 
     # bytes that MUST move per step (algorithmic, fp32): see DESIGN.md "Algorithmic bytes"
     def algorithmic_bytes(self):
@@ -109,8 +111,6 @@ class ConsistencyStep:
         ws, s = st.workspace.data_ptr(), _runtime.stream_ptr(dev)
         fl = _runtime.flags_ptr(st)
         sums = bufs.sums.data_ptr()
-        if self.exchange is not None:  # (re-)arm only when this workspace last published another buffer set
-            self.exchange.arm(st.workspace, bufs.sums, 2 if self.with_vat else 0)
         if self.with_dice and zero_counts:
             bufs.dice_counts.zero_()  # the kernels accumulate into the counters
         _lib.check(h.dct_jsd_fwdbwd_f32(_lib.ptr_array(bufs.logits), K, C, B, HW, _lib.IN_LOGITS,
@@ -119,6 +119,8 @@ class ConsistencyStep:
                                         bufs.dice_counts.data_ptr() if self.with_dice else None, fl, ws, s),
                    "dct_jsd_fwdbwd_f32")
         if not self.with_vat:
+            if self.exchange is not None:   # JSD-only step: the sums leave through the one-thread publication kernel
+                self.exchange.publish(bufs.sums)
             return
         d = bufs.d.data_ptr()
         # d <- normalise(N(0,1));  d <- xi * normalise(d)                       (AEGenerator.py:97-98,103)
@@ -131,6 +133,14 @@ class ConsistencyStep:
         _lib.check(h.dct_l2_normalize_f32(bufs.d_grad.data_ptr(), bufs.r_adv.data_ptr(), B, self.M, 1, self.eps,
                                           bufs.img.data_ptr(), bufs.img_adv.data_ptr(), ws, s), "dct_l2_normalize_f32")
         # adv loss: KL_Divergence_2D(reduce=True)(softmax(adv_logits), real.detach()) + backward (cotraining :391-392)
+        if self.exchange is not None:
+            # the step's last kernel also stores the three sums into every data-parallel rank's mailbox (NVLink)
+            _lib.check(h.dct_kl_from_logits_fwdbwd_pub_f32(bufs.adv_logits.data_ptr(), bufs.real_probs.data_ptr(), C, B, HW,
+                                                           self.kl_eps, self.adv_weight / self.n, None, sums + 16,
+                                                           bufs.grad_adv.data_ptr(), fl, ws,
+                                                           ctypes.byref(self.exchange.descriptor(bufs.sums)), s),
+                       "dct_kl_from_logits_fwdbwd_pub_f32")
+            return
         _lib.check(h.dct_kl_from_logits_fwdbwd_f32(bufs.adv_logits.data_ptr(), bufs.real_probs.data_ptr(), C, B, HW,
                                                    self.kl_eps, self.adv_weight / self.n, None, sums + 16,
                                                    bufs.grad_adv.data_ptr(), fl, ws, s), "dct_kl_from_logits_fwdbwd_f32")

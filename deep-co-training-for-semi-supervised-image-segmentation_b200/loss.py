@@ -592,9 +592,9 @@ class _CEFn(torch.autograd.Function):
     map backward for reduction 'none'."""
 
     @staticmethod
-    def forward(ctx, logits, targets, weight, ignore_index: int, reduction: str, n_global, dice_counts):
+    def forward(ctx, logits, targets, weight, ignore_index: int, reduction: str, n_global, dice_counts, confusion=None):
         ctx.in_dtype = logits.dtype
-        lp = logits.dtype == torch.bfloat16 and reduction != "none" and ctx.needs_input_grad[0]
+        lp = logits.dtype == torch.bfloat16 and reduction != "none" and ctx.needs_input_grad[0] and confusion is None
         x = _prep_lp(logits, "CrossEntropyLoss2d") if lp else _prep(_promote(logits), "CrossEntropyLoss2d")
         assert x.dim() >= 2
         b, c, hw = _bchw(x)
@@ -610,6 +610,10 @@ class _CEFn(torch.autograd.Function):
             assert w.numel() == c, "weight must have one entry per class"
         if dice_counts is not None:
             assert dice_counts.dtype == torch.int64 and dice_counts.is_cuda and dice_counts.numel() == b * c * 3
+        if confusion is not None:
+            assert confusion.dtype == torch.int64 and confusion.is_cuda and confusion.is_contiguous() and \
+                confusion.numel() == c * c, "confusion must be a contiguous int64 [C,C] CUDA tensor"
+            assert dice_counts is None and reduction != "none", "confusion counting fuses with the mean / sum loss only"
         fl, ws, s = _runtime.flags_ptr(st), st.workspace.data_ptr(), _runtime.stream_ptr(dev)
         ctx.reduction, ctx.ignore_index = reduction, int(ignore_index)
         if reduction == "none":
@@ -629,7 +633,7 @@ class _CEFn(torch.autograd.Function):
         if reduction == "mean":
             if n_global is not None:
                 gconst = 1.0 / float(n_global)
-            elif w is None and dice_counts is not None:
+            elif w is None and dice_counts is not None and confusion is None:
                 # the fused meter asserts every label in [0,C) (class2one_hot, utils/utils.py:190; raised through
                 # the label flag), so no pixel is ignored and W is the pixel count: no histogram pass
                 gconst = 1.0 / float(b * hw)
@@ -647,6 +651,12 @@ class _CEFn(torch.autograd.Function):
                 ctx.grad = grad
         if lp:
             pass
+        elif ctx.needs_input_grad[0] and confusion is not None:
+            grad = torch.empty_like(x)
+            _lib.check(h.dct_ce_fwdbwd_conf_f32(x.data_ptr(), lab.data_ptr(), c, b, hw, _ptr(w), int(ignore_index),
+                                                _ptr(inv), gconst, None, total.data_ptr(), grad.data_ptr(),
+                                                confusion.data_ptr(), fl, ws, s), "dct_ce_fwdbwd_conf_f32")
+            ctx.grad = grad
         elif ctx.needs_input_grad[0]:
             grad = torch.empty_like(x)
             _lib.check(h.dct_ce_fwdbwd_f32(x.data_ptr(), lab.data_ptr(), c, b, hw, _ptr(w), int(ignore_index),
@@ -659,6 +669,9 @@ class _CEFn(torch.autograd.Function):
             if dice_counts is not None:
                 _lib.check(h.dct_dice_counts_f32(x.data_ptr(), lab.data_ptr(), c, b, hw, dice_counts.data_ptr(), 1, fl, s),
                            "dct_dice_counts_f32")
+            if confusion is not None:
+                _lib.check(h.dct_confusion_f32(x.data_ptr(), lab.data_ptr(), c, b, hw, confusion.data_ptr(), s),
+                           "dct_confusion_f32")
             ctx.grad = None
         _runtime.after_call(st)
         if inv is not None:
@@ -678,12 +691,12 @@ class _CEFn(torch.autograd.Function):
             _lib.check(h.dct_ce_bwd_f32(x.data_ptr(), lab.data_ptr(), c, b, hw, _ptr(w), ctx.ignore_index, g.data_ptr(),
                                         None, 1.0, grad.data_ptr(), None, _runtime.stream_ptr(x.device)),
                        "dct_ce_bwd_f32")
-            return grad.to(ctx.in_dtype), None, None, None, None, None, None
+            return grad.to(ctx.in_dtype), None, None, None, None, None, None, None
         grad = ctx.grad
         ctx.grad = None
         if grad is None:
             raise RuntimeError("CrossEntropyLoss2d: backward called twice or without grad-requiring logits")
-        return _finish_grads([grad], g, [ctx.in_dtype])[0], None, None, None, None, None, None
+        return _finish_grads([grad], g, [ctx.in_dtype])[0], None, None, None, None, None, None, None
 
 
 class CrossEntropyLoss2d(nn.Module):
@@ -703,12 +716,12 @@ class CrossEntropyLoss2d(nn.Module):
             self.weight = None
 
     def forward(self, outputs: torch.Tensor, targets: torch.Tensor):
-        return _CEFn.apply(outputs, targets, self.weight, int(self.ignore_index), self.reduction, None, None)
+        return _CEFn.apply(outputs, targets, self.weight, int(self.ignore_index), self.reduction, None, None, None)
 
 
 def supervised_from_logits(logits: torch.Tensor, gt: torch.Tensor, weight: Optional[torch.Tensor] = None,
                            ignore_index: int = 255, dice_counts: Optional[torch.Tensor] = None,
-                           n_global: Optional[int] = None) -> torch.Tensor:
+                           n_global: Optional[int] = None, confusion: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``CrossEntropyLoss2d(weight)(logits, gt.squeeze(1))`` and ``DiceMeter.add(logits, gt)`` in ONE pass.
 
     The two consecutive lines of the labeled loop (cotraining_totalloss.py:211-212) read the same
@@ -716,9 +729,14 @@ def supervised_from_logits(logits: torch.Tensor, gt: torch.Tensor, weight: Optio
     (upstream 1/W folded in) and, if ``dice_counts`` (int64 ``[B,C,3]``, accumulated into) is given,
     the (I, G, P) counts of ``argmax softmax(logits)`` against ``gt`` (feed them to
     ``DiceMeter.add_counts``).  ``n_global``: pixel count over all data-parallel ranks for the
-    unweighted global mean (defaults to the local denominator)."""
+    unweighted global mean (defaults to the local denominator).
+
+    ``confusion`` (int64 ``[C,C]``, accumulated into; instead of ``dice_counts``): the Cityscapes trainers keep an
+    ``IoU`` meter on the same line pair (cotraining_city.py:236-241: ``metrics[k].add(predicted=pred, target=gt)``);
+    the same launch then counts ``conf[gt][argmax logits]`` over the pixels with ``0 <= gt < C`` -- hand the tensor
+    to ``IoU.add_confusion`` / read it back at ``value()`` time."""
     w = None if weight is None else torch.as_tensor(weight, dtype=torch.float32)
-    return _CEFn.apply(logits, gt, w, int(ignore_index), "mean", n_global, dice_counts)
+    return _CEFn.apply(logits, gt, w, int(ignore_index), "mean", n_global, dice_counts, confusion)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -173,6 +173,11 @@ class ConfusionMatrix(Metric):
         _lib.check(_lib.lib().dct_confusion_f32(x.data_ptr(), g.data_ptr(), c, b, hw, conf.data_ptr(),
                                                 _runtime.stream_ptr(x.device)), "dct_confusion_f32")
 
+    def device_counts(self, device) -> torch.Tensor:
+        """The int64 ``[C,C]`` device accumulator itself: pass it as ``confusion=`` to ``supervised_from_logits`` and the
+        loss kernel counts straight into this meter (no second pass over the logits)."""
+        return self._device_conf(torch.device(device))
+
     def add(self, predicted, target):
         """predicted / target: integer class maps of equal shape (tensors or numpy arrays)."""
         if not torch.is_tensor(predicted):
@@ -229,6 +234,11 @@ class IoU(Metric):
 
     def reset(self):
         self.conf_metric.reset()
+
+    def device_counts(self, device) -> torch.Tensor:
+        """int64 ``[C,C]`` accumulator on ``device`` for the fused loss + meter launch (``supervised_from_logits(...,
+        confusion=meter.device_counts(dev))`` replaces ``meter.add(predicted=pred, target=gt)``)."""
+        return self.conf_metric.device_counts(device)
 
     def add(self, predicted, target):
         assert predicted.size(0) == target.size(0), 'number of targets and predicted outputs do not match'

@@ -83,9 +83,10 @@ DCT_API size_t dct_workspace_bytes(void);
  *
  * Under batch sharding the only cross-rank coupling of the path is a handful of scalars
  * (sum of the JSD map, of the KL maps).  Instead of a collective launched after the step, the
- * kernel that writes the step's LAST `sum` output also pushes all sums into every rank's
- * "mailbox" with plain stores through NVLink / NVSwitch peer mappings (one process per GPU;
- * mailboxes are shared with CUDA IPC).  No extra launch, no NCCL kernel competing for SMs.
+ * step's LAST kernel (dct_kl_from_logits_fwdbwd_pub_f32: the adversarial KL) also pushes all
+ * sums into every rank's "mailbox" with plain stores through NVLink / NVSwitch peer mappings
+ * (one process per GPU; mailboxes are shared with CUDA IPC).  No extra launch, no NCCL kernel
+ * competing for SMs.  Steps that end with another kernel use dct_exchange_publish (one thread).
  *
  *   mailbox (device memory of each rank):  uint64 [nslots][world][DCT_PUB_ROW_WORDS]
  *     publication number q (1, 2, ...) of rank r lands in slot q % nslots, row r, of EVERY
@@ -93,16 +94,16 @@ DCT_API size_t dct_workspace_bytes(void);
  *     {seq32 << 32 | high 32 data bits} with seq32 = q mod 2^32: a reader that finds seq32 in
  *     a word holds valid data (aligned 8-byte stores are single-copy atomic); summing the rows
  *     in rank order gives every rank the same bits.
- *   dct_peer_pub: the descriptor (DEVICE memory, 8-byte aligned) a workspace is armed with;
- *     a launch whose `sum` argument equals `trigger` publishes src[0..n) when it completes.
- *     `seq` points at a device counter the kernels increment (zero it once).
+ *   dct_peer_pub: the descriptor (a HOST struct, copied into the kernel parameters) handed to a
+ *     *_pub launch, which publishes src[0..n) when its last CTA has written the launch's own sum.
+ *     `src`, `seq`, `mailbox[]` are device pointers; `seq` is a device counter the kernels
+ *     increment (zero it once; shared by a rank's descriptors).
  * ------------------------------------------------------------------------------------------ */
 #define DCT_MAX_PEERS 8
 #define DCT_PUB_ROW_WORDS 16
 #define DCT_PUB_MAX_VALUES 8
 #define DCT_IPC_HANDLE_BYTES 64
 typedef struct dct_peer_pub {
-    const double* trigger;
     const double* src;
     unsigned long long* seq;
     int32_t n, rank, world, nslots;
@@ -116,8 +117,14 @@ DCT_API int dct_mailbox_create(size_t bytes, void** dev_ptr, void* ipc_handle);
 DCT_API int dct_mailbox_open(const void* ipc_handle, void** dev_ptr);
 /* owned != 0: cudaFree of a created mailbox; owned == 0: unmap an opened one */
 DCT_API int dct_mailbox_close(void* dev_ptr, int owned);
-/* arm (desc_dev != NULL) or disarm (NULL) `workspace`: enqueues on `stream`; the descriptor must outlive the launches */
-DCT_API int dct_exchange_arm(void* workspace, const void* desc_dev, void* stream);
+/* stand-alone publication of desc->src[0..n) (one thread): for steps whose last kernel has no *_pub variant */
+DCT_API int dct_exchange_publish(const dct_peer_pub* desc, void* stream);
+/* dct_kl_from_logits_fwdbwd_f32 (below) whose last CTA, after writing *sum, publishes the step's sums through
+ * `pub_desc` (host struct; sum must be non-NULL and is normally one of desc->src[0..n)). */
+DCT_API int dct_kl_from_logits_fwdbwd_pub_f32(const float* p_logit, const float* y_prob, int C, int64_t B, int64_t HW,
+                                              float eps, float gconst, float* map, double* sum, float* grad_p_logit,
+                                              int32_t* flags, void* workspace, const dct_peer_pub* pub_desc,
+                                              void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K-view Jensen-Shannon divergence.
@@ -283,6 +290,17 @@ DCT_API int dct_ce_fwdbwd_f32(const float* logits, const int64_t* labels, int C,
                               const float* class_weight, int64_t ignore_index, const float* gscalar, float gconst,
                               float* map, double* sum, float* grad_logits, int64_t* dice_counts, int32_t* flags,
                               void* workspace, void* stream);
+
+/* Cityscapes flavour of the labeled loop (generalframework/trainer/cotraining_city.py:236-241; trainer_city.py:141):
+ *   sup_loss = criterions['sup'](pred, gt.squeeze(1));   metrics[k].add(predicted=pred, target=gt)
+ * with metrics[k] = IoU(C, ignore_index=255) (generalframework/metrics/iou.py:43-69 -> confusionmatrix.py:32-85).
+ * Same loss / gradient arguments as dct_ce_fwdbwd_f32; `confusion` is int64 [C,C] (rows = ground truth), ACCUMULATED
+ * into: conf[t][argmax_c logits] += 1 for every pixel with 0 <= t < C (raw arg-max with torch.max semantics: first
+ * index on ties, NaN maximal; ignore-255 pixels fall outside [0,C) and are dropped).  One pass over logits + labels. */
+DCT_API int dct_ce_fwdbwd_conf_f32(const float* logits, const int64_t* labels, int C, int64_t B, int64_t HW,
+                                   const float* class_weight, int64_t ignore_index, const float* gscalar, float gconst,
+                                   float* map, double* sum, float* grad_logits, int64_t* confusion, int32_t* flags,
+                                   void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Class maps, one-hot tensors and the functional Dice on one-hot inputs (SURVEY.md 8a11 / 8b "Functional Dice").

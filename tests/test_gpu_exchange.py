@@ -1,8 +1,8 @@
 """GPU: the fused exchange of the step's loss sums (include/dct_b200.h "Fused cross-rank exchange").
 
 On one GPU the exchange is a loopback (world = 1: the own mailbox is the only peer), which exercises everything but
-the NVLink hop: arming a workspace, the publication from the last CTA of the step's last kernel (tile pipeline and
-register-tiled finishers), sequence tags, the ring, CUDA-graph replay.  The cross-rank hop is checked by
+the NVLink hop: the descriptor, the publication from the last CTA of the step's last kernel (the *_pub tile kernel,
+its non-tile fallback, the stand-alone publication kernel), sequence tags, the ring, CUDA-graph replay.  The cross-rank hop is checked by
 `bench.py --gpus N` itself (its result must equal an NCCL all-reduce of the same sums, or the run fails).
 """
 import pytest
@@ -77,39 +77,37 @@ def test_loopback_under_cuda_graph_and_jsd_only_trigger(dev):
         dct_b200.set_check_mode(old)
 
 
-def test_unarmed_and_foreign_sum_pointers_do_not_publish(dev):
+def test_fallback_shapes_and_plain_entry_points(dev):
     import dct_b200
     from dct_b200.distributed import PeerExchange
     from dct_b200.engine import StepBuffers
     old = dct_b200.set_check_mode("deferred")
     try:
         px = PeerExchange(dev, n=4, nslots=4)
-        K, C, B, H, W = 2, 2, 2, 32, 32
+        K, C, B = 2, 2, 2
         g = torch.Generator(device=dev).manual_seed(3)
-        bufs = StepBuffers.allocate(K, C, B, H, W, 1, dev, g)
-        armed = _step(K, C, B, H, W, px)
-        armed.run(bufs)
+        bufs = StepBuffers.allocate(K, C, B, 32, 32, 1, dev, g)
+        _step(K, C, B, 32, 32, px).run(bufs)
         torch.cuda.synchronize()
         assert px.published() == 1
-        # same workspace, public autograd API: its sum outputs are other buffers -> no publication
+        # the plain entry points never publish (public autograd API, a step without an exchange)
         z = [t.clone().requires_grad_() for t in bufs.logits]
         dct_b200.jsd_consistency_from_logits(z, weight=1.0).backward()
+        _step(K, C, B, 32, 32, None).run(bufs)
         torch.cuda.synchronize()
         assert px.published() == 1
-        # odd HW (register-tiled finisher) with an armed trigger publishes as well
-        Ho = 33
-        bo = StepBuffers.allocate(K, C, B, Ho, 31, 1, dev, g)
-        so = _step(K, C, B, Ho, 31, px, with_vat=False)
-        so.run(bo)
+        # odd HW: the *_pub entry point falls back to the non-tile kernels + the stand-alone publication
+        bo = StepBuffers.allocate(K, C, B, 33, 31, 1, dev, g)
+        _step(K, C, B, 33, 31, px).run(bo)
         torch.cuda.synchronize()
         assert px.published() == 2
         assert torch.equal(px.read(2), bo.sums[:4])
-        st = dct_b200._runtime.state(dev)
-        px.disarm(st.workspace)
-        armed.exchange = None
-        armed.run(bufs)
+        # 7 classes: no tile instantiation either
+        b7 = StepBuffers.allocate(K, 7, B, 32, 32, 1, dev, g)
+        _step(K, 7, B, 32, 32, px).run(b7)
         torch.cuda.synchronize()
-        assert px.published() == 2
+        assert px.published() == 3
+        assert torch.equal(px.read(3), b7.sums[:4])
         px.close()
     finally:
         dct_b200.set_check_mode(old)

@@ -127,6 +127,58 @@ def test_cross_entropy_vs_oracle(C, B, H, W, mode, dct, dev, oracle):
     assert loss2.item() == loss.item()
 
 
+@pytest.mark.parametrize("C,B,H,W", SHAPES)
+@pytest.mark.parametrize("variant", ["plain", "weighted_ignore_ties"])
+def test_cross_entropy_fused_with_confusion_vs_oracle(C, B, H, W, variant, dct, dev, oracle):
+    """cotraining_city.py:236-241: CE + IoU.add of the same (pred, gt) from one launch (dct_ce_fwdbwd_conf_f32): loss and
+    gradient within 1e-5, the confusion matrix bit-exact (raw arg-max, first index on ties, 255 dropped), accumulated."""
+    g = torch.Generator().manual_seed(4321 + 17 * C + W)
+    x = 3 * torch.randn(B, C, H, W, generator=g)
+    gt = torch.randint(0, C, (B, 1, H, W), generator=g)
+    weight = None
+    if variant == "weighted_ignore_ties":
+        x = torch.round(x)                                   # integer-valued logits: plenty of exact ties
+        gt[torch.rand(B, 1, H, W, generator=g) < 0.1] = 255
+        weight = (0.25 + torch.rand(C, generator=g))
+    meter = dct.IoU(C, ignore_index=255)
+    conf = meter.device_counts(dev)
+    z = x.to(dev).requires_grad_()
+    loss = dct.supervised_from_logits(z, gt.to(dev), weight=weight, confusion=conf)
+    loss.backward()
+    ol, og, bad = oracle.cross_entropy(x.numpy(), gt.numpy(), None if weight is None else weight.numpy(), 255, "mean")
+    assert bad == 0
+    assert_close(loss.item(), ol, floor=1.0, what="loss")
+    assert_close(N(z.grad), og, floor=float(np.abs(og).max()), what="grad")
+    oc = oracle.confusion(x.numpy(), gt.numpy())
+    assert np.array_equal(N(conf), oc), "fused confusion counts differ from the oracle"
+    # the meter reads the same accumulator; a second launch accumulates; the stand-alone kernel agrees
+    dct.supervised_from_logits(x.to(dev).requires_grad_(), gt.to(dev), weight=weight, confusion=conf)
+    assert np.array_equal(meter.conf_metric.conf64, 2 * oc)
+    ref_meter = dct.IoU(C, ignore_index=255)
+    ref_meter.add(predicted=x.to(dev), target=gt.to(dev))
+    assert np.array_equal(ref_meter.conf_metric.conf64, oc)
+    # evaluation (no gradient wanted): loss + counts through the forward kernels
+    conf2 = torch.zeros(C, C, dtype=torch.int64, device=dev)
+    with torch.no_grad():
+        l2 = dct.supervised_from_logits(x.to(dev), gt.to(dev), weight=weight, confusion=conf2)
+    assert_close(l2.item(), ol, floor=1.0, what="eval loss")
+    assert np.array_equal(N(conf2), oc)
+
+
+def test_fused_confusion_nan_scores_follow_torch_max(dct, dev, oracle):
+    g = torch.Generator().manual_seed(99)
+    C, B, H, W = 19, 2, 64, 128
+    x = 3 * torch.randn(B, C, H, W, generator=g)
+    x[torch.rand(B, C, H, W, generator=g) < 0.01] = float("nan")
+    gt = torch.randint(0, C, (B, 1, H, W), generator=g)
+    conf = torch.zeros(C, C, dtype=torch.int64, device=dev)
+    dct.supervised_from_logits(x.to(dev).requires_grad_(), gt.to(dev), confusion=conf)
+    assert np.array_equal(N(conf), oracle.confusion(x.numpy(), gt.numpy()))
+    pred = x.to(dev).max(1)[1]                               # the reference's own arg-max on the same device
+    want = torch.bincount((gt.to(dev).view(-1) * C + pred.view(-1)), minlength=C * C).view(C, C)
+    assert torch.equal(conf, want)
+
+
 def test_label_hist_and_bad_labels(dct, dev):
     import ctypes
     h = dct._lib.lib()
