@@ -208,19 +208,20 @@ def run_ours(args, wl):
     # CoTrainer_City keeps its IoU meters on the labeled branch only (trainer/cotraining_city.py:236-241 vs :250-257)
     with_dice = args.workload != "c4"
     n_local = B * H * W
-    # The path's only exchange: the loss sums of every step.  "p2p" (default at N > 1): the step's last
-    # kernel pushes them into every rank's mailbox over NVLink peer memory (distributed.PeerExchange) -- no collective
-    # launch; "nccl": one all-reduce per step on a side stream (the baseline this replaces, kept for A/B).
+    # The path's only exchange: the loss sums of every step.  "p2p" (default at N > 1): they are stored into
+    # every rank's mailbox over NVLink peer memory (distributed.PeerExchange) by a one-thread kernel chained to the step's
+    # last kernel -- no collective launch; "p2p-fused": by that last kernel itself (measured slower);
+    # "nccl": one all-reduce per step on a side stream (the baseline this replaces, kept for A/B).
     px, exchange = None, "none"
-    if world > 1 or args.exchange == "p2p":   # (p2p at N = 1: loopback on the own mailbox, for A/B of the fused kernel)
+    if world > 1 or args.exchange in ("p2p", "p2p-fused"):   # (at N = 1: loopback on the own mailbox, for A/B)
         exchange = args.exchange
-        if exchange in ("p2p", "auto"):
+        if exchange in ("p2p", "p2p-fused", "auto"):
             try:
                 from dct_b200.distributed import PeerExchange
                 px = PeerExchange(dev, n=4, nslots=64)
                 ok = torch.ones(1, device=dev)
             except Exception as e:  # IPC / peer mapping refused on this box
-                if args.exchange == "p2p":
+                if args.exchange != "auto":
                     raise
                 print(f"[bench rank {rank}] peer exchange unavailable ({e}); using NCCL", file=sys.stderr)
                 ok = torch.zeros(1, device=dev)
@@ -228,9 +229,10 @@ def run_ours(args, wl):
                 dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             if ok.item() == 0:
                 px = None
-            exchange = "p2p" if px is not None else "nccl"
+            exchange = ("p2p-fused" if args.exchange == "p2p-fused" else "p2p") if px is not None else "nccl"
     step = ConsistencyStep(K, C, B, H, W, cin=cin, jsd_weight=1.0, adv_weight=1.0, n_global=n_local * world,
-                           with_vat=with_vat, with_dice=with_dice, exchange=px)
+                           with_vat=with_vat, with_dice=with_dice, exchange=px,
+                           exchange_mode="fused" if exchange == "p2p-fused" else "chained")
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     # R independent buffer sets, rotated every step so that no step finds its inputs in the 126 MB L2
     per_set = sum(t.numel() * t.element_size() for t in StepBuffers.allocate(K, C, 1, H, W, cin, dev).input_tensors()) * B
@@ -372,8 +374,11 @@ def run_ours(args, wl):
                 "config": {"workload": f"{args.workload}: {desc}", "K": K, "C": C, "H": H, "W": W, "batch_per_gpu": B,
                            "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": bool(args.graph),
                            "exchange": {"none": "none (1 GPU)", "nccl": "NCCL all-reduce of the loss sums per step (side stream)",
-                                        "p2p": "fused: the step's last kernel stores the loss sums into every rank's "
-                                               "mailbox over NVLink peer memory (no collective launch)"}[exchange],
+                                        "p2p": "a one-thread kernel chained to the step's last kernel by programmatic dependent "
+                                               "launch stores the loss sums into every rank's mailbox over NVLink peer memory "
+                                               "(no collective, no NCCL kernel)",
+                                        "p2p-fused": "the step's last kernel itself stores the loss sums into every rank's "
+                                                     "mailbox over NVLink peer memory"}[exchange],
                            "exchange_check": exchange_check,
                            "l2": f"inputs larger than L2: {R} rotating buffer sets of {per_set / 2**20:.0f} MiB inputs"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": step.launches_per_step * args.steps,
@@ -485,7 +490,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--graph", type=int, default=1, help="replay the step as a CUDA graph (1) or launch eagerly (0)")
     ap.add_argument("--e2e-steps", type=int, default=50)
-    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "p2p-fused", "nccl"],
                     help="N > 1: how the loss sums cross ranks (auto = p2p, NCCL if peer mapping is refused)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -25,8 +25,8 @@ _p, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
 class PeerPub(C.Structure):
     """``dct_peer_pub`` of include/dct_b200.h (host struct; device pointers inside)."""
-    _fields_ = [("src", C.c_void_p), ("seq", C.c_void_p), ("n", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
-                ("nslots", C.c_int32), ("mailbox", C.c_void_p * 8)]
+    _fields_ = [("src", C.c_void_p), ("seq", C.c_void_p), ("mailbox_table", C.c_void_p), ("n", C.c_int32),
+                ("rank", C.c_int32), ("world", C.c_int32), ("nslots", C.c_int32)]
 
 
 # name -> argtypes (restype is int unless listed in _RESTYPES); must match include/dct_b200.h

@@ -37,9 +37,12 @@ class DeviceReport:
     keeps the per-image '2d' rows for the epoch-end ``DiceMeter`` statistics.  ``loss_sums``: float64 ``[K + 2]``
     (sup_0..sup_{K-1}, jsd, adv) and ``steps``.  ``reduce()`` is the only collective + host copy."""
 
-    def __init__(self, K: int, C: int, device, keep_rows: bool = False):
+    def __init__(self, K: int, C: int, device, keep_rows: bool = False, with_confusion: bool = False):
         self.K, self.C, self.device, self.keep_rows = K, C, device, keep_rows
         self.counts = {n: torch.zeros(K, C, 3, dtype=torch.int64, device=device) for n in ("lab", "unlab")}
+        # Cityscapes trainers (cotraining_city.py:212): one IoU meter per segmentator on the labeled branch; the fused
+        # loss kernel accumulates conf[gt][pred] straight into conf[k]
+        self.conf = torch.zeros(K, C, C, dtype=torch.int64, device=device) if with_confusion else None
         self.loss_sums = torch.zeros(K + 2, dtype=torch.float64, device=device)
         self.steps = 0
         self.rows = {n: [[] for _ in range(K)] for n in ("lab", "unlab")}
@@ -47,6 +50,8 @@ class DeviceReport:
     def reset(self):
         for c in self.counts.values():
             c.zero_()
+        if self.conf is not None:
+            self.conf.zero_()
         self.loss_sums.zero_()
         self.steps = 0
         self.rows = {n: [[] for _ in range(self.K)] for n in ("lab", "unlab")}
@@ -83,6 +88,11 @@ class DeviceReport:
                 i, s = c[..., 0].float(), (c[..., 1] + c[..., 2]).float()
                 dice = (2 * i + 1e-8) / (s + 1e-8)
             out[name + "_dice"] = dice.cpu()
+        if self.conf is not None:
+            conf = self.conf.clone()
+            if D.is_distributed():
+                D.all_reduce_counts(conf, group)
+            out["confusion"] = conf.cpu()                # [K,C,C] int64; IoU statistics: metrics.iou_from_confusion
         denom = max(self.steps, 1) * world
         out["losses"] = (sums / denom).cpu()
         return out
@@ -98,6 +108,8 @@ class CoTrainConfig:
     fgsm_eps: float = 0.05             # adv_training_dict['eplision'] (config/ACDC_config_cotraing.yaml)
     ignore_index: int = 255
     keep_rows: bool = False
+    meter: str = "dice"                # "dice": DiceMeter on both branches (CoTrainer); "iou": IoU meter on the labeled
+                                       # branch only (CoTrainer_City, trainer/cotraining_city.py:212,236-257)
 
 
 class CoTrainStep:
@@ -116,7 +128,9 @@ class CoTrainStep:
             nets = [DDP(n, device_ids=[idx], gradient_as_bucket_view=True, broadcast_buffers=False) for n in nets]
         self.nets = list(nets)
         self.optimizers = list(optimizers)
-        self.report = DeviceReport(self.K, cfg.num_classes, self.device, keep_rows=cfg.keep_rows)
+        assert cfg.meter in ("dice", "iou")
+        self.report = DeviceReport(self.K, cfg.num_classes, self.device, keep_rows=cfg.keep_rows,
+                                   with_confusion=cfg.meter == "iou")
 
     # ---- the adversarial branch (cotraining_totalloss.py:366-393) with the fused KL
     def _fgsm_adv(self, img_2: Tensor, gt_2: Tensor, unl_img: Tensor) -> Tensor:
@@ -140,19 +154,25 @@ class CoTrainStep:
         sup_losses, total = [], 0
         for k, (img, gt) in enumerate(labeled):
             logits = self.nets[k](img)
-            counts = torch.zeros(img.shape[0], C, 3, dtype=torch.int64, device=dev)
-            sup = supervised_from_logits(logits, gt, ignore_index=cfg.ignore_index, dice_counts=counts)
-            self.report.add_counts("lab", k, counts)
+            if cfg.meter == "iou":   # loss + gradient + confusion counts of the IoU meter from one launch
+                sup = supervised_from_logits(logits, gt, ignore_index=cfg.ignore_index, confusion=self.report.conf[k])
+            else:
+                counts = torch.zeros(img.shape[0], C, 3, dtype=torch.int64, device=dev)
+                sup = supervised_from_logits(logits, gt, ignore_index=cfg.ignore_index, dice_counts=counts)
+                self.report.add_counts("lab", k, counts)
             sup_losses.append(sup)
             total = total + sup
         jsd = adv = None
         if cfg.train_jsd and unlabeled is not None:
             uimg, ugt = unlabeled
             ulogits = [net(uimg) for net in self.nets]
-            ucounts = torch.zeros(self.K, uimg.shape[0], C, 3, dtype=torch.int64, device=dev)
-            jsd = jsd_consistency_from_logits(ulogits, weight=1.0, labels=ugt, dice_counts=ucounts)
-            for k in range(self.K):
-                self.report.add_counts("unlab", k, ucounts[k])
+            if cfg.meter == "iou":   # no meters on the unlabeled branch (cotraining_city.py:250-257)
+                jsd = jsd_consistency_from_logits(ulogits, weight=1.0)
+            else:
+                ucounts = torch.zeros(self.K, uimg.shape[0], C, 3, dtype=torch.int64, device=dev)
+                jsd = jsd_consistency_from_logits(ulogits, weight=1.0, labels=ugt, dice_counts=ucounts)
+                for k in range(self.K):
+                    self.report.add_counts("unlab", k, ucounts[k])
             total = total + cfg.cot_weight * jsd
         if cfg.train_adv and unlabeled is not None and self.K >= 2:
             adv = self._fgsm_adv(labeled[1][0], labeled[1][1], unlabeled[0])

@@ -88,20 +88,19 @@ extern "C" int dct_mailbox_close(void* dev_ptr, int owned) {
 
 namespace dct {
 __global__ void exchange_publish_kernel(const PeerPub pub) {
-    PeerVals pv;
-    peer_prefetch(pub, pv);
-    peer_publish(pub, pv, nullptr, 0.0);
+    // the counter is only ever written by publications of this stream, all of them long complete: fetch it (and the
+    // mailbox table, through the L2) while the previous launch is still draining
+    const unsigned long long seq_old = __ldcg(pub.seq);
+    pdl_wait();   // the previous launch of the stream has completed and its sums are visible
+    peer_publish(pub.src, pub.seq, seq_old, pub.n, pub.rank, pub.world, pub.nslots, pub.mailbox_table, nullptr, 0.0);
 }
 int check_pub(const dct_peer_pub* d) {
     if (d == nullptr || d->src == nullptr || d->seq == nullptr) return DCT_ERR_BAD_ARG;
     if (d->n < 1 || d->n > DCT_PUB_MAX_VALUES || d->world < 1 || d->world > DCT_MAX_PEERS || d->rank < 0 ||
         d->rank >= d->world || d->nslots < 1)
         return DCT_ERR_BAD_ARG;
-    for (int p = 0; p < d->world; ++p) {
-        if (d->mailbox[p] == nullptr) return DCT_ERR_BAD_ARG;
-        if (!aligned(d->mailbox[p], 16)) return DCT_ERR_MISALIGNED;
-    }
-    if (!aligned(d->src, 8) || !aligned(d->seq, 8)) return DCT_ERR_MISALIGNED;
+    if (d->mailbox_table == nullptr) return DCT_ERR_BAD_ARG;
+    if (!aligned(d->src, 8) || !aligned(d->seq, 8) || !aligned(d->mailbox_table, 8)) return DCT_ERR_MISALIGNED;
     return DCT_OK;
 }
 }  // namespace dct
@@ -111,6 +110,7 @@ extern "C" int dct_exchange_publish(const dct_peer_pub* desc, void* stream) {
     if (rc != DCT_OK) return rc;
     PeerPub pub;
     std::memcpy(&pub, desc, sizeof(pub));
-    exchange_publish_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(pub);
+    cudaError_t e = launch_pdl(exchange_publish_kernel, dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream), pub);
+    if (e != cudaSuccess) { g_last_cuda_error = e; return DCT_ERR_CUDA; }
     return check_launch();
 }

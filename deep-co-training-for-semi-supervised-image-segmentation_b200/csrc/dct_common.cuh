@@ -17,10 +17,10 @@ constexpr float kEntEps = 1e-16f;     // Entropy / Entropy_2D epsilon (generalfr
 // Peer publication descriptor ("dct_peer_pub" in include/dct_b200.h): where the last CTA of a *_pub launch pushes a
 // step's loss sums -- straight into every data-parallel rank's mailbox over NVLink (see peer_publish below).
 struct PeerPub {
-    const double* src;                         // n doubles (local device memory) holding the step's sums
-    unsigned long long* seq;                   // device counter of publications made so far (shared by the descriptors of a rank)
+    const double* src;                          // n doubles (local device memory) holding the step's sums
+    unsigned long long* seq;                    // device counter of publications made so far (shared by a rank's descriptors)
+    unsigned long long* const* mailbox_table;   // DEVICE array of `world` mailbox pointers (own one included), peer-mapped
     int n, rank, world, nslots;
-    unsigned long long* mailbox[DCT_MAX_PEERS];  // mailbox[r]: rank r's mailbox (own one included), peer-mapped
 };
 static_assert(sizeof(PeerPub) == sizeof(dct_peer_pub), "PeerPub mirrors dct_peer_pub");
 
@@ -176,44 +176,36 @@ __device__ __forceinline__ float warp_sum(float v) {
 // two 8-byte words {32 data bits | 32-bit sequence number}: an aligned 8-byte store is single-copy atomic, so a
 // reader that sees the expected sequence number in a word also sees its data -- no fence, no flag round trip
 // (the "LL" scheme of NCCL's low-latency protocol).  Mailbox row: DCT_PUB_ROW_WORDS u64; slot = seq % nslots.
-// The descriptor travels BY VALUE in the kernel parameters and the older sums + the sequence counter are fetched
-// before the ticket atomic (peer_prefetch), so the publication adds no memory round trip to the kernel's tail.
 // Only the *_pub kernel variants contain this code (a compile-time switch): measured on B200, linking a hook into
-// every kernel's finisher cost 5.6 us per c2 step.
+// every kernel's finisher cost 5.6 us per c2 step.  The mailbox pointer table lives in device memory next to the
+// sequence counter (`dct_peer_pub.mailbox_table`), so the descriptor is six scalars in the kernel parameters.
 // ---------------------------------------------------------------------------------------------
-struct PeerVals {
-    unsigned long long seq;
-    double v[DCT_PUB_MAX_VALUES];
-};
-__device__ __forceinline__ void peer_prefetch(const PeerPub& pub, PeerVals& pv) {
-    pv.seq = __ldcg(pub.seq);
-#pragma unroll
-    for (int j = 0; j < DCT_PUB_MAX_VALUES; ++j) pv.v[j] = j < pub.n ? __ldcg(pub.src + j) : 0.0;
-}
-// `fresh` / `fresh_ptr`: the sum this launch has just produced (it replaces the prefetched value of that slot)
-__device__ __forceinline__ void peer_publish(const PeerPub& pub, PeerVals& pv, const double* fresh_ptr, double fresh) {
-    const unsigned long long q = pv.seq + 1ull;
+// Out of line and fed scalars only.  Measured (profiles/r04/ab_publish.log, profiles/r05/ab_exchange_loopback.log):
+// with this code in a tile kernel -- inlined or called -- ptxas demotes the kernel's uniform registers (SASS: R2UR 7 -> 100,
+// PLOP3 230 -> 363 in the C=19 adversarial-KL kernel), the producer's bulk-copy issue loop slows down and the kernel
+// loses 9 % (C=4) to 19 % (C=19).  The product therefore chains the one-thread publication kernel behind the plain
+// kernel with programmatic dependent launch (+2.4 us per step); the fused *_pub variant stays available for A/B.  `fresh` is the sum the calling launch has just produced for slot `fresh_ptr`; the
+// other slots are read back from `src` (written by earlier kernels of the stream).
+static __device__ __noinline__ void peer_publish(const double* src, unsigned long long* seq, unsigned long long seq_old,
+                                                 int n, int rank, int world, int nslots,
+                                                 unsigned long long* const* mailbox_table, const double* fresh_ptr,
+                                                 double fresh) {
+    const unsigned long long q = seq_old + 1ull;
     const unsigned long long tag = (q & 0xffffffffull) << 32;
-    const size_t row = ((size_t)(q % (unsigned long long)pub.nslots) * pub.world + pub.rank) * DCT_PUB_ROW_WORDS;
-#pragma unroll
-    for (int j = 0; j < DCT_PUB_MAX_VALUES; ++j) {
-        if (j < pub.n) {
-            const double val = (pub.src + j == fresh_ptr) ? fresh : pv.v[j];
-            const unsigned long long bits = (unsigned long long)__double_as_longlong(val);
-            const unsigned long long w0 = tag | (bits & 0xffffffffull), w1 = tag | (bits >> 32);
-#pragma unroll
-            for (int p = 0; p < DCT_MAX_PEERS; ++p) {
-                if (p < pub.world) {
-                    // volatile 8-byte stores = st.volatile (relaxed, system scope; SASS STG.E.64.STRONG.SYS); every word
-                    // carries its own tag
-                    volatile unsigned long long* vd = pub.mailbox[p] + row + 2 * j;
-                    vd[0] = w0;
-                    vd[1] = w1;
-                }
-            }
+    const size_t row = ((size_t)(q % (unsigned long long)nslots) * world + rank) * DCT_PUB_ROW_WORDS;
+    for (int j = 0; j < n; ++j) {
+        const double val = (src + j == fresh_ptr) ? fresh : __ldcg(src + j);
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(val);
+        const unsigned long long w0 = tag | (bits & 0xffffffffull), w1 = tag | (bits >> 32);
+        for (int p = 0; p < world; ++p) {
+            // volatile 8-byte stores = st.volatile (relaxed, system scope; SASS STG.E.64.STRONG.SYS); every word
+            // carries its own tag
+            volatile unsigned long long* vd = mailbox_table[p] + row + 2 * j;
+            vd[0] = w0;
+            vd[1] = w1;
         }
     }
-    *pub.seq = q;
+    *seq = q;
 }
 
 // Deterministic grid-wide sum of one double per thread.  Every CTA writes its partial to the
@@ -297,8 +289,6 @@ __device__ __forceinline__ void tile_grid_finish(long long acc_fx, bool nonfinit
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        PeerVals pv;
-        if constexpr (PUB) peer_prefetch(*pub, pv);  // in flight while the atomics below make their round trips
         if (out != nullptr) {
             long long lo = 0, hi = 0;
             for (int w = 0; w < nw; ++w) { lo += s_lo[w]; hi += s_hi[w]; }
@@ -317,7 +307,9 @@ __device__ __forceinline__ void tile_grid_finish(long long acc_fx, bool nonfinit
                 const double total = ((double)hi * 4294967296.0 + (double)lo) * (1.0 / 1099511627776.0);
                 const double fin = nf ? __longlong_as_double(0x7ff8000000000000ll) : total;
                 *out = fin;
-                if constexpr (PUB) peer_publish(*pub, pv, out, fin);  // the step's sums -> every rank's mailbox (NVLink)
+                if constexpr (PUB)  // the step's sums -> every rank's mailbox (NVLink)
+                    peer_publish(pub->src, pub->seq, __ldcg(pub->seq), pub->n, pub->rank, pub->world, pub->nslots,
+                                 pub->mailbox_table, out, fin);
                 ws->fx_lo = 0ull;
                 ws->fx_hi = 0ll;
                 ws->nonfinite = 0u;

@@ -111,9 +111,10 @@ class PeerExchange:
                     _lib.check(h.dct_mailbox_open(handles[r], C.byref(p)), "dct_mailbox_open")
                     self._ptrs[r] = p.value
         self.seq = torch.zeros(1, dtype=torch.int64, device=self.device)   # device-side publication counter
+        self._table = torch.tensor([_to_signed64(p) for p in self._ptrs], dtype=torch.int64, device=self.device)
         self._desc = {}      # sums pointer -> dct_peer_pub (host struct)
         self._mail = _as_int64_tensor(self._own, self.words, self.device)   # view of the own mailbox
-        assert int(h.dct_peer_pub_bytes()) == 8 * (4 + _lib.MAX_PEERS)
+        assert int(h.dct_peer_pub_bytes()) == C.sizeof(_lib.PeerPub) == 40
 
     def descriptor(self, sums: torch.Tensor):
         """``dct_peer_pub`` (a host-side ctypes struct, copied into the kernel parameters by the ``*_pub`` entry
@@ -125,8 +126,7 @@ class PeerExchange:
             desc = self._lib.PeerPub()
             desc.src, desc.seq = key, self.seq.data_ptr()
             desc.n, desc.rank, desc.world, desc.nslots = self.n, self.rank, self.world, self.nslots
-            for r, ptr in enumerate(self._ptrs):
-                desc.mailbox[r] = ptr
+            desc.mailbox_table = self._table.data_ptr()
             self._desc[key] = desc
         return desc
 

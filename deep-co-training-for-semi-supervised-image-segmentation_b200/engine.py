@@ -79,7 +79,7 @@ class ConsistencyStep:
     """
 
     def __init__(self, K, C, B, H, W, cin=1, jsd_weight=1.0, adv_weight=1.0, xi=1e-6, eps=10.0, kl_eps=1e-10,
-                 n_global: Optional[int] = None, with_vat=True, with_dice=True, exchange=None):
+                 n_global: Optional[int] = None, with_vat=True, with_dice=True, exchange=None, exchange_mode="chained"):
         self.K, self.C, self.B, self.HW, self.M = K, C, B, H * W, cin * H * W
         self.n = B * H * W if n_global is None else int(n_global)
         self.jsd_weight, self.adv_weight, self.xi, self.eps, self.kl_eps = jsd_weight, adv_weight, xi, eps, kl_eps
@@ -87,10 +87,16 @@ class ConsistencyStep:
         # distributed.PeerExchange or None: the kernel that writes the step's last sum also pushes the sums into every
         # data-parallel rank's mailbox over NVLink (no collective launch)
         self.exchange = exchange
+        # "chained" (default): the plain kernel, then the one-thread publication kernel chained by programmatic dependent
+        #            launch (+2.4 us per step, measured);
+        # "fused":   the adversarial-KL kernel's own last CTA publishes (dct_kl_from_logits_fwdbwd_pub_f32) -- no extra
+        #            launch, but ptxas generates a slower tile loop for that kernel (+3.7 us at c2, +82 us at c4)
+        assert exchange_mode in ("fused", "chained")
+        self.exchange_mode = exchange_mode
         self._h = _lib.lib()
         # kernels launched per run(): the JSD kernel (Dice fused for C <= 4, else K counting launches) + 4 VAT/KL
         self.launches_per_step = 1 + (0 if (not with_dice or (C <= 4 and K * C <= 16)) else K) + (4 if with_vat else 0) + \
-            (1 if (exchange is not None and not with_vat) else 0)
+            (1 if (exchange is not None and (not with_vat or exchange_mode == "chained")) else 0)
 
     # bytes that MUST move per step (algorithmic, fp32): see DESIGN.md "Algorithmic bytes"
     def algorithmic_bytes(self):
@@ -133,7 +139,7 @@ class ConsistencyStep:
         _lib.check(h.dct_l2_normalize_f32(bufs.d_grad.data_ptr(), bufs.r_adv.data_ptr(), B, self.M, 1, self.eps,
                                           bufs.img.data_ptr(), bufs.img_adv.data_ptr(), ws, s), "dct_l2_normalize_f32")
         # adv loss: KL_Divergence_2D(reduce=True)(softmax(adv_logits), real.detach()) + backward (cotraining :391-392)
-        if self.exchange is not None:
+        if self.exchange is not None and self.exchange_mode == "fused":
             # the step's last kernel also stores the three sums into every data-parallel rank's mailbox (NVLink)
             _lib.check(h.dct_kl_from_logits_fwdbwd_pub_f32(bufs.adv_logits.data_ptr(), bufs.real_probs.data_ptr(), C, B, HW,
                                                            self.kl_eps, self.adv_weight / self.n, None, sums + 16,
@@ -144,6 +150,8 @@ class ConsistencyStep:
         _lib.check(h.dct_kl_from_logits_fwdbwd_f32(bufs.adv_logits.data_ptr(), bufs.real_probs.data_ptr(), C, B, HW,
                                                    self.kl_eps, self.adv_weight / self.n, None, sums + 16,
                                                    bufs.grad_adv.data_ptr(), fl, ws, s), "dct_kl_from_logits_fwdbwd_f32")
+        if self.exchange is not None:
+            self.exchange.publish(bufs.sums)
 
     def capture(self, bufs: StepBuffers) -> "torch.cuda.CUDAGraph":
         """Capture ``run(bufs)`` into a CUDA graph (replay with ``graph.replay()``)."""

@@ -96,7 +96,7 @@ DCT_API size_t dct_workspace_bytes(void);
  *     in rank order gives every rank the same bits.
  *   dct_peer_pub: the descriptor (a HOST struct, copied into the kernel parameters) handed to a
  *     *_pub launch, which publishes src[0..n) when its last CTA has written the launch's own sum.
- *     `src`, `seq`, `mailbox[]` are device pointers; `seq` is a device counter the kernels
+ *     `src`, `seq`, `mailbox_table` are device pointers; `seq` is a device counter the kernels
  *     increment (zero it once; shared by a rank's descriptors).
  * ------------------------------------------------------------------------------------------ */
 #define DCT_MAX_PEERS 8
@@ -104,10 +104,10 @@ DCT_API size_t dct_workspace_bytes(void);
 #define DCT_PUB_MAX_VALUES 8
 #define DCT_IPC_HANDLE_BYTES 64
 typedef struct dct_peer_pub {
-    const double* src;
-    unsigned long long* seq;
+    const double* src;                          /* device: the n sums to publish */
+    unsigned long long* seq;                    /* device: publication counter */
+    unsigned long long* const* mailbox_table;   /* device array of `world` mailbox pointers, mailbox_table[r] = rank r's */
     int32_t n, rank, world, nslots;
-    unsigned long long* mailbox[DCT_MAX_PEERS];
 } dct_peer_pub;
 DCT_API size_t dct_peer_pub_bytes(void);
 /* cudaMalloc + zero a mailbox of `bytes` on the current device; *dev_ptr receives it and ipc_handle
@@ -117,7 +117,8 @@ DCT_API int dct_mailbox_create(size_t bytes, void** dev_ptr, void* ipc_handle);
 DCT_API int dct_mailbox_open(const void* ipc_handle, void** dev_ptr);
 /* owned != 0: cudaFree of a created mailbox; owned == 0: unmap an opened one */
 DCT_API int dct_mailbox_close(void* dev_ptr, int owned);
-/* stand-alone publication of desc->src[0..n) (one thread): for steps whose last kernel has no *_pub variant */
+/* stand-alone publication of desc->src[0..n): a one-thread kernel chained to the previous launch of `stream` with
+ * programmatic dependent launch (its scheduling overlaps that kernel's tail) */
 DCT_API int dct_exchange_publish(const dct_peer_pub* desc, void* stream);
 /* dct_kl_from_logits_fwdbwd_f32 (below) whose last CTA, after writing *sum, publishes the step's sums through
  * `pub_desc` (host struct; sum must be non-NULL and is normally one of desc->src[0..n)). */

@@ -57,7 +57,7 @@ def test_exchange_descriptor_layout_matches_header():
     defs = {k: int(v) for k, v in re.findall(r"#define\s+(DCT_\w+)\s+(\d+)\s*$", txt, flags=re.M)}
     assert (defs["DCT_MAX_PEERS"], defs["DCT_PUB_ROW_WORDS"], defs["DCT_PUB_MAX_VALUES"], defs["DCT_IPC_HANDLE_BYTES"]) == \
         (L.MAX_PEERS, L.PUB_ROW_WORDS, L.PUB_MAX_VALUES, L.IPC_HANDLE_BYTES)
-    assert L.lib().dct_peer_pub_bytes() == 8 * (4 + L.MAX_PEERS)   # 2 pointers, 4 int32, MAX_PEERS pointers
+    assert L.lib().dct_peer_pub_bytes() == ctypes.sizeof(L.PeerPub) == 40   # 3 pointers + 4 int32
     assert 2 * L.PUB_MAX_VALUES <= L.PUB_ROW_WORDS                 # two tagged words per published double
 
 

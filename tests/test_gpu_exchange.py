@@ -17,9 +17,9 @@ def dev():
     return torch.device("cuda", 0)
 
 
-def _step(K, C, B, H, W, px, with_vat=True):
+def _step(K, C, B, H, W, px, with_vat=True, mode="fused"):  # fused: exercises the *_pub kernel; "chained" is the product default
     from dct_b200.engine import ConsistencyStep
-    return ConsistencyStep(K, C, B, H, W, cin=1, n_global=B * H * W, with_vat=with_vat, exchange=px)
+    return ConsistencyStep(K, C, B, H, W, cin=1, n_global=B * H * W, with_vat=with_vat, exchange=px, exchange_mode=mode)
 
 
 def test_loopback_publication_matches_local_sums(dev):
@@ -102,6 +102,15 @@ def test_fallback_shapes_and_plain_entry_points(dev):
         torch.cuda.synchronize()
         assert px.published() == 2
         assert torch.equal(px.read(2), bo.sums[:4])
+        # the chained mode: plain kernel + the one-thread publication kernel
+        _step(K, C, B, 32, 32, px, mode="chained").run(bufs)
+        torch.cuda.synchronize()
+        assert px.published() == 3
+        assert torch.equal(px.read(3), bufs.sums[:4])
+        px.seq.zero_()   # (restart the numbering for the checks below)
+        _step(K, C, B, 32, 32, px).run(bufs); _step(K, C, B, 33, 31, px).run(bo)
+        torch.cuda.synchronize()
+        assert px.published() == 2
         # 7 classes: no tile instantiation either
         b7 = StepBuffers.allocate(K, 7, B, 32, 32, 1, dev, g)
         _step(K, 7, B, 32, 32, px).run(b7)

@@ -262,13 +262,19 @@ def main():
         extra = {}
         if arm == "ours":
             step = CoTrainStep(nets, opts, CoTrainConfig(num_classes=C, train_jsd=True, train_adv=cfg["adv"], cot_weight=cfg["cot"],
-                                                         adv_weight=cfg["advw"], fgsm_eps=cfg["eps"]), dev)
+                                                         adv_weight=cfg["advw"], fgsm_eps=cfg["eps"],
+                                                         meter="iou" if args.config == "c4" else "dice"), dev)
             fn = lambda: step.step(lab, unlab)  # noqa: E731
             ms, wall = timed(fn)
             rep = step.report.reduce()
             dct_b200.raise_if_flagged()
             extra = {"losses": [round(float(v), 5) for v in rep["losses"]],
                      "unlab_dice_view0": [round(float(v), 4) for v in rep["unlab_dice"][0]]}
+            if "confusion" in rep:   # Cityscapes flavour: IoU meter on the labeled branch, counted by the loss kernel
+                conf0 = rep["confusion"][0].double()
+                iu = conf0.diag() / (conf0.sum(0) + conf0.sum(1) - conf0.diag()).clamp(min=1)
+                extra["lab_mean_iou_view0"] = round(float(iu.mean()), 4)
+                extra["lab_pixels_counted_view0"] = int(conf0.sum())
         elif arm == "aten":
             meters = [Aten.DiceMeter(C, axises) for _ in range(K)]
             umeters = [Aten.DiceMeter(C, axises) for _ in range(K)]
