@@ -209,13 +209,14 @@ def run_ours(args, wl):
     with_dice = args.workload != "c4"
     n_local = B * H * W
     # The path's only exchange: the loss sums of every step.  "p2p" (default at N > 1): they are stored into
-    # every rank's mailbox over NVLink peer memory (distributed.PeerExchange) by a one-thread kernel chained to the step's
-    # last kernel -- no collective launch; "p2p-fused": by that last kernel itself (measured slower);
+    # every rank's mailbox over NVLink peer memory (distributed.PeerExchange) by a one-CTA kernel chained to the step's
+    # last kernel -- no collective launch; "p2p-fused": by that last kernel itself, "p2p-deferred": one step late on a
+    # forked graph branch (both measured slower);
     # "nccl": one all-reduce per step on a side stream (the baseline this replaces, kept for A/B).
     px, exchange = None, "none"
-    if world > 1 or args.exchange in ("p2p", "p2p-fused"):   # (at N = 1: loopback on the own mailbox, for A/B)
+    if world > 1 or args.exchange in ("p2p", "p2p-fused", "p2p-deferred"):   # (at N = 1: loopback on the own mailbox, for A/B)
         exchange = args.exchange
-        if exchange in ("p2p", "p2p-fused", "auto"):
+        if exchange in ("p2p", "p2p-fused", "p2p-deferred", "auto"):
             try:
                 from dct_b200.distributed import PeerExchange
                 px = PeerExchange(dev, n=4, nslots=64)
@@ -229,17 +230,19 @@ def run_ours(args, wl):
                 dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             if ok.item() == 0:
                 px = None
-            exchange = ("p2p-fused" if args.exchange == "p2p-fused" else "p2p") if px is not None else "nccl"
+            exchange = (args.exchange if args.exchange in ("p2p-fused", "p2p-deferred") else "p2p") if px is not None else "nccl"
     step = ConsistencyStep(K, C, B, H, W, cin=cin, jsd_weight=1.0, adv_weight=1.0, n_global=n_local * world,
                            with_vat=with_vat, with_dice=with_dice, exchange=px,
-                           exchange_mode="fused" if exchange == "p2p-fused" else "chained")
+                           exchange_mode={"p2p-fused": "fused", "p2p-deferred": "deferred"}.get(exchange, "chained"))
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     # R independent buffer sets, rotated every step so that no step finds its inputs in the 126 MB L2
     per_set = sum(t.numel() * t.element_size() for t in StepBuffers.allocate(K, C, 1, H, W, cin, dev).input_tensors()) * B
     R = max(2, min(8, int(1.5e9 // max(per_set, 1)) or 2))
     sets = [StepBuffers.allocate(K, C, B, H, W, cin, dev, gen) for _ in range(R)]
     dct_b200.set_check_mode("deferred")  # no host sync inside the path; flags are read once at the end
-    graphs = [step.capture(s) for s in sets] if args.graph else None
+    deferred = px is not None and step.exchange_mode == "deferred"
+    prev_of = (lambda j: sets[(j - 1) % R]) if deferred else (lambda j: None)   # step i publishes step i-1's sums
+    graphs = [step.capture(s, publish_prev=prev_of(j)) for j, s in enumerate(sets)] if args.graph else None
     # the path's only exchange: the loss scalars of every step, all-reduced over NCCL on a side stream
     # so that the collective of step i overlaps the kernels of step i+1 (the gradients never depend on it: the
     # global 1/N is folded into the kernels through n_global)
@@ -258,7 +261,7 @@ def run_ours(args, wl):
         if graphs is not None:
             graphs[j].replay()
         else:
-            step.run(s)
+            step.run(s, publish_prev=prev_of(j))
         if use_nccl:
             done = torch.cuda.Event()
             done.record(main)
@@ -293,7 +296,9 @@ def run_ours(args, wl):
     e0.record()
     for i in range(args.steps):
         one(i)
-    drain()   # the timed region ends when the last step's all-reduce has completed
+    if deferred:
+        px.publish(sets[(args.steps - 1) % R].sums)   # the last step's sums (every earlier step was published by its successor)
+    drain()   # the timed region ends when the last step's exchange has completed
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -374,9 +379,11 @@ def run_ours(args, wl):
                 "config": {"workload": f"{args.workload}: {desc}", "K": K, "C": C, "H": H, "W": W, "batch_per_gpu": B,
                            "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": bool(args.graph),
                            "exchange": {"none": "none (1 GPU)", "nccl": "NCCL all-reduce of the loss sums per step (side stream)",
-                                        "p2p": "a one-thread kernel chained to the step's last kernel by programmatic dependent "
+                                        "p2p": "a one-CTA kernel chained to the step's last kernel by programmatic dependent "
                                                "launch stores the loss sums into every rank's mailbox over NVLink peer memory "
                                                "(no collective, no NCCL kernel)",
+                                        "p2p-deferred": "a one-CTA kernel on a forked graph branch stores step i-1's loss sums into "
+                                                        "every rank's mailbox next to step i's first kernel",
                                         "p2p-fused": "the step's last kernel itself stores the loss sums into every rank's "
                                                      "mailbox over NVLink peer memory"}[exchange],
                            "exchange_check": exchange_check,
@@ -490,7 +497,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--graph", type=int, default=1, help="replay the step as a CUDA graph (1) or launch eagerly (0)")
     ap.add_argument("--e2e-steps", type=int, default=50)
-    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "p2p-fused", "nccl"],
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "p2p-deferred", "p2p-fused", "nccl"],
                     help="N > 1: how the loss sums cross ranks (auto = p2p, NCCL if peer mapping is refused)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

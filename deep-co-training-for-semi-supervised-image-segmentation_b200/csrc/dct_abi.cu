@@ -87,12 +87,25 @@ extern "C" int dct_mailbox_close(void* dev_ptr, int owned) {
 }
 
 namespace dct {
-__global__ void exchange_publish_kernel(const PeerPub pub) {
-    // the counter is only ever written by publications of this stream, all of them long complete: fetch it (and the
-    // mailbox table, through the L2) while the previous launch is still draining
-    const unsigned long long seq_old = __ldcg(pub.seq);
+// One thread per (value j, peer p): everything that does not depend on the previous launch -- the sequence counter
+// (only ever written by publications of this stream, all long complete) and the mailbox pointers -- is fetched while
+// that launch is still draining; after griddepcontrol.wait one parallel round of loads (the sums) and the stores remain.
+__global__ void __launch_bounds__(DCT_PUB_MAX_VALUES * DCT_MAX_PEERS) exchange_publish_kernel(const PeerPub pub) {
+    const int t = threadIdx.x, j = t / DCT_MAX_PEERS, p = t % DCT_MAX_PEERS;
+    const bool on = j < pub.n && p < pub.world;
+    unsigned long long* mb = on ? pub.mailbox_table[p] : nullptr;
+    const unsigned long long q = __ldcg(pub.seq) + 1ull;
     pdl_wait();   // the previous launch of the stream has completed and its sums are visible
-    peer_publish(pub.src, pub.seq, seq_old, pub.n, pub.rank, pub.world, pub.nslots, pub.mailbox_table, nullptr, 0.0);
+    if (on) {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(__ldcg(pub.src + j));
+        const unsigned long long tag = (q & 0xffffffffull) << 32;
+        const size_t row = ((size_t)(q % (unsigned long long)pub.nslots) * pub.world + pub.rank) * DCT_PUB_ROW_WORDS;
+        volatile unsigned long long* vd = mb + row + 2 * j;   // st.volatile: relaxed, system scope; self-validating words
+        vd[0] = tag | (bits & 0xffffffffull);
+        vd[1] = tag | (bits >> 32);
+    }
+    __syncthreads();
+    if (t == 0) *pub.seq = q;
 }
 int check_pub(const dct_peer_pub* d) {
     if (d == nullptr || d->src == nullptr || d->seq == nullptr) return DCT_ERR_BAD_ARG;
@@ -110,7 +123,8 @@ extern "C" int dct_exchange_publish(const dct_peer_pub* desc, void* stream) {
     if (rc != DCT_OK) return rc;
     PeerPub pub;
     std::memcpy(&pub, desc, sizeof(pub));
-    cudaError_t e = launch_pdl(exchange_publish_kernel, dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream), pub);
+    cudaError_t e = launch_pdl(exchange_publish_kernel, dim3(1), dim3(DCT_PUB_MAX_VALUES * DCT_MAX_PEERS), 0,
+                               static_cast<cudaStream_t>(stream), pub);
     if (e != cudaSuccess) { g_last_cuda_error = e; return DCT_ERR_CUDA; }
     return check_launch();
 }

@@ -318,6 +318,7 @@ extern "C" int dct_kl_from_logits_fwdbwd_f32(const float* p_logit, const float* 
     return pix_launch<KlFromLogits>(a, B, static_cast<cudaStream_t>(stream));
 }
 
+#ifndef DCT_KBENCH  // (tools/kbench_tile.cu includes this file without dct_abi.cu)
 // The adversarial KL is the LAST kernel of a consistency step (JSD -> VAT -> KL): this variant's last CTA also pushes the
 // step's loss sums into every data-parallel rank's mailbox over NVLink (include/dct_b200.h, "Fused cross-rank exchange").
 extern "C" int dct_kl_from_logits_fwdbwd_pub_f32(const float* p_logit, const float* y_prob, int C, int64_t B, int64_t HW,
@@ -350,6 +351,8 @@ extern "C" int dct_kl_from_logits_fwdbwd_pub_f32(const float* p_logit, const flo
     if (rc != DCT_OK) return rc;
     return dct_exchange_publish(pub_desc, stream);
 }
+
+#endif  // DCT_KBENCH
 
 extern "C" int dct_kl_div_fwd_f32(const float* p, const float* q, int C, int64_t B, int64_t HW, float eps, float* map,
                                   double* sum, int32_t* flags, void* workspace, void* stream) {

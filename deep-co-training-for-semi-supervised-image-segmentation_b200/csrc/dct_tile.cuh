@@ -77,6 +77,11 @@ __device__ __forceinline__ void tile_st_row(unsigned char* row, int p0, const FV
     }
 }
 
+// stages with at least this many fp32 rows per pixel use an op's shared-memory-resident body, if it has one
+// (measured: K = 4, C = 19 gains, K = 3, C = 19 is faster register-resident; tools/kbench_tile.cu overrides it for A/B)
+#ifndef DCT_STREAM_MIN_ROWS
+#define DCT_STREAM_MIN_ROWS 61
+#endif
 constexpr int kTileMaxTensors = 8;
 constexpr int kTileMaxRows = 80;   // NIN*C rows per stage
 
@@ -113,6 +118,11 @@ template <class Op, class = void>
 struct op_conf : std::false_type {};
 template <class Op>
 struct op_conf<Op, std::enable_if_t<Op::CONF>> : std::true_type {};
+// does the op provide a shared-memory-resident ("streaming") body for stages too wide for registers?
+template <class Op, class = void>
+struct op_stream : std::false_type {};
+template <class Op>
+struct op_stream<Op, std::enable_if_t<Op::STREAM_CAPABLE>> : std::true_type {};
 template <class Op>
 constexpr bool op_label_row() { return Op::NDICE > 0 || op_labels<Op>::value || op_conf<Op>::value; }
 
@@ -164,6 +174,8 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
     constexpr int TP = Cfg::TP, ROWS = Cfg::ROWS, ES = Cfg::ES, NIN = Op::NIN, NOUT = Op::NOUT, C = CT;
     constexpr bool DICE = Op::NDICE > 0;
     constexpr bool LAB = op_labels<Op>::value;   // the op consumes the labels itself
+    // > 40 fp32 rows per pixel do not fit the register file as a pixel pair: ops that can, work on the stage in place
+    constexpr bool STREAM = op_stream<Op>::value && ROWS >= DCT_STREAM_MIN_ROWS && PPT <= 2 && std::is_same<ET, float>::value;
     constexpr bool CONF = op_conf<Op>::value;    // confusion counts of tensor 0 vs the labels (CTA-shared histogram)
     constexpr bool LROW = DICE || LAB || CONF;   // the stage carries a label row
     constexpr int LW = (PPT % 2 == 0) ? 2 : 1;   // pixels per math lane group: pairs use packed FP32x2
@@ -395,7 +407,18 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
 #pragma unroll
                 for (int n = 0; n < Op::NDICE; ++n) pk[n][0] = pk[n][1] = 0u;
             }
-            if (active) {
+            if constexpr (STREAM) {
+                if (active) {
+                    const T mv = Op::template stream<C, T>(st, Cfg::kRowBytes, p0, gs);
+                    acc_fx += to_fixed(vhsum(mv), nonfinite);
+                    if (a.map != nullptr) {
+                        FVec<PPT> mapv;
+#pragma unroll
+                        for (int v = 0; v < PPT; ++v) mapv.v[v] = vget(mv, v);
+                        st_stream<PPT>(a.map + (int64_t)b * HW + off + p0, mapv);
+                    }
+                }
+            } else if (active) {
                 FVec<PPT> gm;
 #pragma unroll
                 for (int v = 0; v < PPT; ++v) gm.v[v] = 1.0f;
@@ -596,8 +619,12 @@ int tile_launch_ct(TileArgs a, int64_t B, cudaStream_t stream) {
     //                    read-only ops: 8 warps, 1 CTA/SM, 2 stages
     //   rows <= 60       K = 3, C = 19: 5 warps, 1 CTA/SM, 3 stages (a pixel pair takes 255 registers)
     //   rows <= 80       one pixel/thread (a pixel pair would need > 255 registers), 8 warps
-    constexpr int PPT = ROWS <= 4 ? 4 : (ROWS <= 60 ? 2 : 1);
-    constexpr int NCW = ROWS <= 16 ? 8 : (ROWS <= 24 ? 4 : (ROWS <= 40 ? (Op::NOUT == 0 ? 8 : 3) : (ROWS <= 60 ? 5 : 8)));
+    //   rows > 40, ops with a shared-memory-resident body (K = 3, 4 JSD at C = 19): pixel pairs worked on in place in the
+    //                    stage (~100 registers), 58 KB stages (4 warps at 57 rows, 3 warps at 76 rows), 3 stages, 1 CTA/SM
+    constexpr bool STREAMK = op_stream<Op>::value && ROWS >= DCT_STREAM_MIN_ROWS && std::is_same<ET, float>::value;
+    constexpr int PPT = ROWS <= 4 ? 4 : ((ROWS <= 60 || STREAMK) ? 2 : 1);
+    constexpr int NCW = STREAMK ? (ROWS <= 60 ? 4 : 3)
+                                : (ROWS <= 16 ? 8 : (ROWS <= 24 ? 4 : (ROWS <= 40 ? (Op::NOUT == 0 ? 8 : 3) : (ROWS <= 60 ? 5 : 8))));
     constexpr int MINB = ROWS <= 24 ? 2 : (ROWS <= 40 ? (Op::NOUT == 0 ? 1 : 2) : 1);
     // bf16 tensors: same shapes (the register budget follows the number of rows, not their width); the 2-byte rows
     // simply buy more stages

@@ -131,7 +131,7 @@ class PeerExchange:
         return desc
 
     def publish(self, sums: torch.Tensor) -> None:
-        """Stand-alone publication (one-thread kernel) for steps whose last kernel has no fused variant."""
+        """Stand-alone publication (one small CTA) for steps whose last kernel has no fused variant."""
         self._lib.check(self._lib.lib().dct_exchange_publish(self._C.byref(self.descriptor(sums)),
                                                              torch.cuda.current_stream(self.device).cuda_stream),
                         "dct_exchange_publish")

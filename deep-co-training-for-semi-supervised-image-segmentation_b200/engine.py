@@ -87,16 +87,20 @@ class ConsistencyStep:
         # distributed.PeerExchange or None: the kernel that writes the step's last sum also pushes the sums into every
         # data-parallel rank's mailbox over NVLink (no collective launch)
         self.exchange = exchange
-        # "chained" (default): the plain kernel, then the one-thread publication kernel chained by programmatic dependent
+        # "chained" (default): the plain kernel, then the one-CTA publication kernel chained by programmatic dependent
         #            launch (+2.4 us per step, measured);
         # "fused":   the adversarial-KL kernel's own last CTA publishes (dct_kl_from_logits_fwdbwd_pub_f32) -- no extra
         #            launch, but ptxas generates a slower tile loop for that kernel (+3.7 us at c2, +82 us at c4)
-        assert exchange_mode in ("fused", "chained")
+        # "deferred": like "chained", but the publication of step i-1's sums runs on a forked branch next to step i's
+        #            first kernel (run(bufs, publish_prev=previous buffers)): nothing is added to the step's critical path;
+        #            the caller publishes the last step's sums itself (exchange.publish) when the loop ends
+        assert exchange_mode in ("fused", "chained", "deferred")
         self.exchange_mode = exchange_mode
+        self._pub_stream = None
         self._h = _lib.lib()
         # kernels launched per run(): the JSD kernel (Dice fused for C <= 4, else K counting launches) + 4 VAT/KL
         self.launches_per_step = 1 + (0 if (not with_dice or (C <= 4 and K * C <= 16)) else K) + (4 if with_vat else 0) + \
-            (1 if (exchange is not None and (not with_vat or exchange_mode == "chained")) else 0)
+            (1 if (exchange is not None and (not with_vat or exchange_mode != "fused")) else 0)
 
     # bytes that MUST move per step (algorithmic, fp32): see DESIGN.md "Algorithmic bytes"
     def algorithmic_bytes(self):
@@ -110,7 +114,34 @@ class ConsistencyStep:
                       "kl_from_logits_fwdbwd": n * 3 * C * 4})
         return b
 
-    def run(self, bufs: StepBuffers, zero_counts: bool = True) -> None:
+    def _publish_forked(self, prev: StepBuffers, dev) -> "torch.cuda.Event":
+        """Publication of ``prev.sums`` on a side branch of the current stream (a fork/join that CUDA-graph capture records
+        as such): it runs next to the kernels enqueued between this call and the join."""
+        cur = torch.cuda.current_stream(dev)
+        if self._pub_stream is None:
+            self._pub_stream = torch.cuda.Stream(device=dev)
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        self._pub_stream.wait_event(fork)
+        with torch.cuda.stream(self._pub_stream):
+            self.exchange.publish(prev.sums)
+            done = torch.cuda.Event()
+            done.record(self._pub_stream)
+        return done
+
+    def run(self, bufs: StepBuffers, zero_counts: bool = True, publish_prev: Optional[StepBuffers] = None) -> None:
+        h, K, C, B, HW = self._h, self.K, self.C, self.B, self.HW
+        dev = bufs.logits[0].device
+        joined = None
+        if self.exchange is not None and self.exchange_mode == "deferred" and publish_prev is not None:
+            joined = self._publish_forked(publish_prev, dev)
+        try:
+            self._run(bufs, zero_counts)
+        finally:
+            if joined is not None:
+                torch.cuda.current_stream(dev).wait_event(joined)
+
+    def _run(self, bufs: StepBuffers, zero_counts: bool) -> None:
         h, K, C, B, HW = self._h, self.K, self.C, self.B, self.HW
         dev = bufs.logits[0].device
         st = _runtime.state(dev)
@@ -125,8 +156,8 @@ class ConsistencyStep:
                                         bufs.dice_counts.data_ptr() if self.with_dice else None, fl, ws, s),
                    "dct_jsd_fwdbwd_f32")
         if not self.with_vat:
-            if self.exchange is not None:   # JSD-only step: the sums leave through the one-thread publication kernel
-                self.exchange.publish(bufs.sums)
+            if self.exchange is not None and self.exchange_mode != "deferred":
+                self.exchange.publish(bufs.sums)   # JSD-only step: the one-CTA publication kernel
             return
         d = bufs.d.data_ptr()
         # d <- normalise(N(0,1));  d <- xi * normalise(d)                       (AEGenerator.py:97-98,103)
@@ -150,21 +181,21 @@ class ConsistencyStep:
         _lib.check(h.dct_kl_from_logits_fwdbwd_f32(bufs.adv_logits.data_ptr(), bufs.real_probs.data_ptr(), C, B, HW,
                                                    self.kl_eps, self.adv_weight / self.n, None, sums + 16,
                                                    bufs.grad_adv.data_ptr(), fl, ws, s), "dct_kl_from_logits_fwdbwd_f32")
-        if self.exchange is not None:
+        if self.exchange is not None and self.exchange_mode == "chained":
             self.exchange.publish(bufs.sums)
 
-    def capture(self, bufs: StepBuffers) -> "torch.cuda.CUDAGraph":
-        """Capture ``run(bufs)`` into a CUDA graph (replay with ``graph.replay()``)."""
+    def capture(self, bufs: StepBuffers, publish_prev: Optional[StepBuffers] = None) -> "torch.cuda.CUDAGraph":
+        """Capture ``run(bufs, publish_prev=...)`` into a CUDA graph (replay with ``graph.replay()``)."""
         dev = bufs.logits[0].device
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            self.run(bufs)  # warm-up on the side stream (allocates the per-stream workspace)
+            self.run(bufs, publish_prev=publish_prev)  # warm-up on the side stream (allocates the per-stream workspace)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=side):
-            self.run(bufs)
+            self.run(bufs, publish_prev=publish_prev)
         return g
 
     def losses(self, bufs: StepBuffers):

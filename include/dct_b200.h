@@ -117,7 +117,7 @@ DCT_API int dct_mailbox_create(size_t bytes, void** dev_ptr, void* ipc_handle);
 DCT_API int dct_mailbox_open(const void* ipc_handle, void** dev_ptr);
 /* owned != 0: cudaFree of a created mailbox; owned == 0: unmap an opened one */
 DCT_API int dct_mailbox_close(void* dev_ptr, int owned);
-/* stand-alone publication of desc->src[0..n): a one-thread kernel chained to the previous launch of `stream` with
+/* stand-alone publication of desc->src[0..n): a one-CTA (64-thread) kernel chained to the previous launch of `stream` with
  * programmatic dependent launch (its scheduling overlaps that kernel's tail) */
 DCT_API int dct_exchange_publish(const dct_peer_pub* desc, void* stream);
 /* dct_kl_from_logits_fwdbwd_f32 (below) whose last CTA, after writing *sum, publishes the step's sums through

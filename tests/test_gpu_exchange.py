@@ -120,3 +120,41 @@ def test_fallback_shapes_and_plain_entry_points(dev):
         px.close()
     finally:
         dct_b200.set_check_mode(old)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_deferred_publication_runs_beside_the_next_step(dev, graph):
+    """exchange_mode='deferred': step i publishes step i-1's sums on a forked branch (eager and captured)."""
+    import dct_b200
+    from dct_b200.distributed import PeerExchange
+    from dct_b200.engine import ConsistencyStep, StepBuffers
+    old = dct_b200.set_check_mode("deferred")
+    try:
+        px = PeerExchange(dev, n=4, nslots=8)
+        K, C, B, H, W = 2, 4, 2, 64, 64
+        step = ConsistencyStep(K, C, B, H, W, cin=1, n_global=B * H * W, exchange=px, exchange_mode="deferred")
+        g = torch.Generator(device=dev).manual_seed(5)
+        sets = [StepBuffers.allocate(K, C, B, H, W, 1, dev, g) for _ in range(3)]
+        step.run(sets[2])                                    # produces the sums the first publication carries
+        torch.cuda.synchronize()
+        assert px.published() == 0                           # deferred: a step never publishes its own sums
+        want2 = sets[2].sums[:4].clone()
+        if graph:
+            graphs = [step.capture(sets[j], publish_prev=sets[(j - 1) % 3]) for j in range(3)]
+            torch.cuda.synchronize()
+            px.seq.zero_()                                   # (the captures' warm-up runs published too)
+            for j in range(3):
+                graphs[j].replay()
+        else:
+            for j in range(3):
+                step.run(sets[j], publish_prev=sets[(j - 1) % 3])
+        px.publish(sets[2].sums)                             # the loop's last step
+        torch.cuda.synchronize()
+        assert px.published() == 4
+        assert torch.equal(px.read(2), sets[0].sums[:4]) and torch.equal(px.read(3), sets[1].sums[:4])
+        assert torch.equal(px.read(4), sets[2].sums[:4])
+        if not graph:
+            assert torch.equal(px.read(1), want2)
+        px.close()
+    finally:
+        dct_b200.set_check_mode(old)

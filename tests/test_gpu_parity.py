@@ -456,3 +456,37 @@ def test_full_size_properties(K, C, B, H, W, dct, dev):
     assert float((nr - 1).abs().max()) <= 1e-5
     d2 = dct.l2_normalize(d1.clone())
     assert float((d2 - d1).abs().max()) <= 1e-6 * float(d1.abs().max())
+
+
+# ---------------------------------------------------------------------------------------------
+# K*C > 40 (K = 3, 4 at C = 19): the shared-memory-resident JSD body (jsd_stream_pair) -- ragged tails, saturated
+# logits whose exponentials underflow to zero, identical views, confident and agreeing inputs
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("K", [3, 4])
+@pytest.mark.parametrize("variant", ["plain", "confident", "agreeing", "saturated", "identical"])
+def test_wide_jsd_streaming_body_vs_oracle(K, variant, dct, dev, oracle):
+    C, B, H, W = 19, 2, 52, 100          # 5200 pixels per image: the last tile of every image is ragged
+    g = torch.Generator().manual_seed(77 + K)
+    z0 = torch.randn(B, C, H, W, generator=g)
+    if variant == "plain":
+        z = [3 * torch.randn(B, C, H, W, generator=g) for _ in range(K)]
+    elif variant == "confident":
+        z = [10 * torch.randn(B, C, H, W, generator=g) for _ in range(K)]
+    elif variant == "agreeing":
+        z = [3 * z0 + 0.1 * torch.randn(B, C, H, W, generator=g) for _ in range(K)]
+    elif variant == "saturated":
+        z = [80.0 * torch.sign(torch.randn(B, C, H, W, generator=g)) for _ in range(K)]   # exp underflows for the -80s
+    else:
+        z = [(3 * z0).clone() for _ in range(K)]
+    w = 0.7
+    n = B * H * W
+    mean, mp, gz = oracle.jsd_logits_fwdbwd([t.numpy() for t in z], w)
+    zd = [t.to(dev).requires_grad_() for t in z]
+    loss = dct.jsd_consistency_from_logits(zd, weight=w)
+    loss.backward()
+    got = np.stack([N(t.grad) for t in zd])
+    assert np.isfinite(got).all()
+    assert_close(loss.item(), w * mean, floor=w * lnK(K), what="loss")
+    assert_close(got, np.stack(gz), floor=w / n, what="grad")
+    if variant == "identical":
+        assert abs(loss.item()) <= 1e-6 and float(np.abs(got).max()) <= 1e-5 * w / n
