@@ -77,10 +77,12 @@ __device__ __forceinline__ void tile_st_row(unsigned char* row, int p0, const FV
     }
 }
 
-// stages with at least this many fp32 rows per pixel use an op's shared-memory-resident body, if it has one
-// (measured: K = 4, C = 19 gains, K = 3, C = 19 is faster register-resident; tools/kbench_tile.cu overrides it for A/B)
+// stages with at least this many fp32 rows per pixel use an op's shared-memory-resident body, if it has one.  Off in
+// the product: with the launch shapes below the register-resident body is as fast or faster at every measured shape
+// (profiles/r08/kbench_wide_{reg,stream}.log); tools/kbench_tile.cu builds with -DDCT_STREAM_MIN_ROWS=41 for the A/B,
+// and tests/test_gpu_parity.py covers the same inputs whichever body is compiled in.
 #ifndef DCT_STREAM_MIN_ROWS
-#define DCT_STREAM_MIN_ROWS 61
+#define DCT_STREAM_MIN_ROWS 1000
 #endif
 constexpr int kTileMaxTensors = 8;
 constexpr int kTileMaxRows = 80;   // NIN*C rows per stage
@@ -617,15 +619,17 @@ int tile_launch_ct(TileArgs a, int64_t B, cudaStream_t stream) {
     //   rows <= 24       one C = 19 tensor (cross-entropy): 4 warps, 2 CTAs/SM, 5 stages        (99% of the copy peak)
     //   rows <= 40       Cityscapes C = 19 with 2 tensors: 3 warps, 2 CTAs/SM, 3 stages           (JSD 4449 -> 5930 GB/s)
     //                    read-only ops: 8 warps, 1 CTA/SM, 2 stages
-    //   rows <= 60       K = 3, C = 19: 5 warps, 1 CTA/SM, 3 stages (a pixel pair takes 255 registers)
-    //   rows <= 80       one pixel/thread (a pixel pair would need > 255 registers), 8 warps
-    //   rows > 40, ops with a shared-memory-resident body (K = 3, 4 JSD at C = 19): pixel pairs worked on in place in the
-    //                    stage (~100 registers), 58 KB stages (4 warps at 57 rows, 3 warps at 76 rows), 3 stages, 1 CTA/SM
+    //   rows <= 60       K = 3, C = 19: one pixel/thread (a pixel pair takes 255 registers), 5 warps, 2 CTAs/SM, 3 stages
+    //                    (profiles/r08/kbench_wide_reg.log: 5244 GB/s against 4641 for the pixel-pair shape)
+    //   rows <= 80       K = 4, C = 19: one pixel/thread, 7 warps, 1 CTA/SM, 3 stages of 68 KB (the most that fits)
+    //                    (profiles/r09/kbench_wide_more.log: 4245 GB/s; 6 warps 3750, 2 x 3 warps 3744, 5 warps x 4 stages 3205)
+    //   DCT_STREAM_MIN_ROWS (off by default): ops with a shared-memory-resident body work on the stage in place; measured
+    //                    equal or slower than the register-resident body at every shape (profiles/r08/kbench_wide_stream.log)
     constexpr bool STREAMK = op_stream<Op>::value && ROWS >= DCT_STREAM_MIN_ROWS && std::is_same<ET, float>::value;
-    constexpr int PPT = ROWS <= 4 ? 4 : ((ROWS <= 60 || STREAMK) ? 2 : 1);
-    constexpr int NCW = STREAMK ? (ROWS <= 60 ? 4 : 3)
-                                : (ROWS <= 16 ? 8 : (ROWS <= 24 ? 4 : (ROWS <= 40 ? (Op::NOUT == 0 ? 8 : 3) : (ROWS <= 60 ? 5 : 8))));
-    constexpr int MINB = ROWS <= 24 ? 2 : (ROWS <= 40 ? (Op::NOUT == 0 ? 1 : 2) : 1);
+    constexpr int PPT = ROWS <= 4 ? 4 : (ROWS <= 40 ? 2 : 1);
+    constexpr int NCW = ROWS <= 16 ? 8 : (ROWS <= 24 ? 4 : (ROWS <= 40 ? (Op::NOUT == 0 ? 8 : 3) : (ROWS <= 60 ? 5 : 7)));
+    constexpr int MINB = ROWS <= 24 ? 2 : (ROWS <= 40 ? (Op::NOUT == 0 ? 1 : 2) : (ROWS <= 60 ? 2 : 1));
+    (void)STREAMK;
     // bf16 tensors: same shapes (the register budget follows the number of rows, not their width); the 2-byte rows
     // simply buy more stages
     constexpr int STAGES = tile_stages<tile_row_bytes<Op, CT, ET>(), PPT, NCW * 32, MINB, 1>();

@@ -262,6 +262,19 @@ int main(int argc, char** argv) {
         run_auto<J3, 19, 1, 4, 2>("jsd K3 C19", B, HWc, reps, 456, false);
         run_auto<J3, 19, 1, 5, 2>("jsd K3 C19", B, HWc, reps, 456, false);
     }
+    if (which == 7) {  // K = 4, C = 19: remaining shapes around the r08 winner (one pixel/thread, 6 warps, 3 stages)
+        const int64_t HWc = 512 * 1024;
+        using J4 = JsdOp<4, true, kFwdBwd, false>;
+        run_auto<J4, 19, 1, 6, 1>("jsd K4 C19", B, HWc, reps, 608, false);
+        run_auto<J4, 19, 1, 3, 2>("jsd K4 C19", B, HWc, reps, 608, false);
+        run_auto<J4, 19, 1, 5, 1>("jsd K4 C19", B, HWc, reps, 608, false);
+        run_auto<J4, 19, 1, 7, 1>("jsd K4 C19", B, HWc, reps, 608, false);
+        using J3 = JsdOp<3, true, kFwdBwd, false>;
+        run_auto<J3, 19, 1, 5, 2>("jsd K3 C19", B, HWc, reps, 456, false);
+        run_auto<J3, 19, 1, 4, 2>("jsd K3 C19", B, HWc, reps, 456, false);
+        run_auto<J3, 19, 1, 6, 2>("jsd K3 C19", B, HWc, reps, 456, false);
+        run_auto<J3, 19, 1, 3, 3>("jsd K3 C19", B, HWc, reps, 456, false);
+    }
     if (which == 4) {
         // ACDC-sized cross-entropy + Dice (C = 4, 256x256) and the plain variant
         using CED = CeOp<true, true, false>;
