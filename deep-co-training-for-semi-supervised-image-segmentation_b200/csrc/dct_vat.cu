@@ -127,42 +127,90 @@ l2_cluster_kernel(const L2Args a) {
     cluster.sync();  // no CTA may exit (and free s_wsum) while a peer can still be reading it
 }
 
-// fallback pass 1: per-(sample, CTA) sum of squares -> workspace partials[b * gx + x] (double)
-__global__ void __launch_bounds__(256) l2_sumsq_kernel(const float* d, int64_t M, Workspace* ws) {
-    __shared__ double s_warp[32];
-    const int64_t base = (int64_t)blockIdx.y * M;
-    double ss = 0.0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (int64_t)gridDim.x * blockDim.x) {
-        float v = d[base + i];
-        ss += (double)v * (double)v;
-    }
-    ss = warp_sum(ss);
+// ---- large / odd samples: grid-wide passes through the workspace ------------------------------------------------------
+// Workspace layout of this path: sample b owns kL2Stride(gx) = gx + 2 doubles: [0, gx) one partial per CTA of its row of the
+// grid, [gx] and [gx + 1] two norm slots (a double holding the float `sqrtf((float)sum) + 1e-16f`).  Pass p reads slot
+// p & 1 and, when another normalisation follows, writes slot (p + 1) & 1: a CTA that starts late never sees the new norm.
+// The CTA that draws the last ticket of a launch adds every sample's partials in a fixed order (one warp per sample: lane l
+// takes partials l, l + 32, ...; shuffle tree) -- deterministic -- and re-arms the ticket.
+__device__ __forceinline__ void l2_finish_norms(double ss, Workspace* ws, int gx, int slot) {
+    __shared__ double s_warp[8];
+    __shared__ bool s_last;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    ss = warp_sum(ss);
     if (lane == 0) s_warp[wid] = ss;
     __syncthreads();
-    if (wid == 0) {
-        double t = lane < (blockDim.x >> 5) ? s_warp[lane] : 0.0;
-        t = warp_sum(t);
-        if (lane == 0) ws->partials[blockIdx.y * gridDim.x + blockIdx.x] = t;
-    }
-}
-
-// fallback pass 2: rescale (scalar accesses: serves any M / alignment)
-__global__ void __launch_bounds__(256) l2_scale_kernel(const L2Args a, int npart) {
-    __shared__ float s_nrm;
-    const int64_t base = (int64_t)blockIdx.y * a.M;
     if (threadIdx.x == 0) {
         double t = 0.0;
-        for (int j = 0; j < npart; ++j) t += a.ws->partials[blockIdx.y * npart + j];
-        s_nrm = sqrtf((float)t) + 1e-16f;
+        for (int w = 0; w < 8; ++w) t += s_warp[w];
+        ws->partials[(size_t)blockIdx.y * (gx + 2) + blockIdx.x] = t;
+        __threadfence();
+        const unsigned int ticket = atomicAdd(&ws->ticket, 1u);
+        s_last = ticket == gridDim.x * gridDim.y - 1u;
     }
     __syncthreads();
-    const float nrm = s_nrm;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.M; i += (int64_t)gridDim.x * blockDim.x) {
-        float o = a.scale * __fdiv_rn(a.d[base + i], nrm);  // scale == 1 on all but the last pass
-        a.out[base + i] = o;
-        if (a.img != nullptr) a.adv[base + i] = fminf(fmaxf(a.img[base + i] + o, 0.0f), 1.0f);
+    if (!s_last) return;
+    __threadfence();
+    for (int b = wid; b < (int)gridDim.y; b += 8) {
+        const double* part = ws->partials + (size_t)b * (gx + 2);
+        double t = 0.0;
+        for (int i = lane; i < gx; i += 32) t += __ldcg(part + i);
+        t = warp_sum(t);
+        if (lane == 0) ws->partials[(size_t)b * (gx + 2) + gx + slot] = (double)(sqrtf((float)t) + 1e-16f);
     }
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); ws->ticket = 0u; }
+}
+
+// pass A: sum of squares of d -> norms.  VEC = 4: 128-bit streaming loads (M % 4 == 0, 16-byte aligned rows)
+template <int VEC>
+__global__ void __launch_bounds__(256) l2_sumsq_kernel(const float* __restrict__ d, int64_t M, Workspace* ws, int gx) {
+    pdl_wait();
+    const float* x = d + (int64_t)blockIdx.y * M;
+    double ss = 0.0;
+    const int64_t n = M / VEC;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const FVec<VEC> v = ld_stream<VEC>(x + i * VEC);
+        float s = 0.0f;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) s = fmaf(v.v[e], v.v[e], s);
+        ss += (double)s;
+    }
+    pdl_launch_dependents();
+    l2_finish_norms(ss, ws, gx, 0);
+}
+
+// pass B: out = scale * (d / norm) [, adv = clamp(img + out, 0, 1)]; NEXT: also the sum of squares of (d / norm) -> the
+// norms of the next normalisation pass (normalise(normalise(d)), AEGenerator.py:98 + :103) without another read pass.
+template <int VEC, bool NEXT>
+__global__ void __launch_bounds__(256) l2_scale_kernel(const L2Args a, int gx, int slot) {
+    pdl_wait();
+    const int64_t base = (int64_t)blockIdx.y * a.M;
+    const float nrm = (float)__ldcg(&a.ws->partials[(size_t)blockIdx.y * (gx + 2) + gx + slot]);
+    double ss = 0.0;
+    const int64_t n = a.M / VEC;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t off = base + i * VEC;
+        FVec<VEC> v = ld_stream<VEC>(a.d + off), o;
+        float s = 0.0f;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const float q = __fdiv_rn(v.v[e], nrm);  // d /= norm (IEEE divide, as the reference)
+            s = fmaf(q, q, s);
+            o.v[e] = a.scale * q;                    // scale == 1 on all but the last pass
+        }
+        ss += (double)s;
+        st_stream<VEC>(a.out + off, o);
+        if (a.img != nullptr) {
+            const FVec<VEC> im = ld_stream<VEC>(a.img + off);
+            FVec<VEC> ad;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) ad.v[e] = fminf(fmaxf(im.v[e] + o.v[e], 0.0f), 1.0f);
+            st_stream<VEC>(a.adv + off, ad);
+        }
+    }
+    pdl_launch_dependents();
+    if constexpr (NEXT) l2_finish_norms(ss, a.ws, gx, slot ^ 1);
 }
 
 template <int VEC>
@@ -229,28 +277,36 @@ extern "C" int dct_l2_normalize_f32(const float* d, float* out, int64_t B, int64
         return check_launch();
     }
     if (workspace == nullptr) return DCT_ERR_BAD_ARG;
-    if (B > 65535) return DCT_ERR_UNSUPPORTED;
-    int64_t gx = (M + 256 * 16 - 1) / (256 * 16);
-    int64_t cap = kMaxPartials / B;
-    if (cap < 1) return DCT_ERR_UNSUPPORTED;
+    if (B > 65535 || B > kMaxPartials / 3) return DCT_ERR_UNSUPPORTED;
+    // CTAs per sample: about eight 256-thread CTAs per SM over the whole grid, grid-stride loops inside
+    const int vec = vec_ok ? 4 : 1;
+    int64_t gx = (kSMs * 8 + B - 1) / B;
+    const int64_t need = (M / vec + 255) / 256;
+    if (gx > need) gx = need;
+    const int64_t cap = kMaxPartials / B - 2;
     if (gx > cap) gx = cap;
-    if (gx > 1024) gx = 1024;
+    if (gx < 1) gx = 1;
+    const dim3 grid((unsigned)gx, (unsigned)B), block(256);
+    cudaError_t e = vec_ok ? launch_pdl(l2_sumsq_kernel<4>, grid, block, 0, s, d, M, a.ws, (int)gx)
+                           : launch_pdl(l2_sumsq_kernel<1>, grid, block, 0, s, d, M, a.ws, (int)gx);
+    if (e != cudaSuccess) { g_last_cuda_error = e; return DCT_ERR_CUDA; }
     for (int pass = 0; pass < passes; ++pass) {
-        // two launches per pass; intermediate passes write the unscaled result to `out` and continue from there
+        // one launch per pass; intermediate passes write the unscaled result to `out`, continue from there, and also
+        // produce the next pass's norms (no separate sum-of-squares read)
         const bool last = (pass == passes - 1);
         L2Args p = a;
         p.d = (pass == 0) ? d : out;
         p.scale = last ? scale : 1.0f;
         p.img = last ? img : nullptr;
         p.adv = last ? adv : nullptr;
-        l2_sumsq_kernel<<<dim3((unsigned)gx, (unsigned)B), 256, 0, s>>>(p.d, M, a.ws);
-        int rc = check_launch();
-        if (rc != DCT_OK) return rc;
-        l2_scale_kernel<<<dim3((unsigned)gx, (unsigned)B), 256, 0, s>>>(p, (int)gx);
-        rc = check_launch();
-        if (rc != DCT_OK) return rc;
+        const int slot = pass & 1;
+        if (vec_ok) e = last ? launch_pdl(l2_scale_kernel<4, false>, grid, block, 0, s, p, (int)gx, slot)
+                             : launch_pdl(l2_scale_kernel<4, true>, grid, block, 0, s, p, (int)gx, slot);
+        else e = last ? launch_pdl(l2_scale_kernel<1, false>, grid, block, 0, s, p, (int)gx, slot)
+                      : launch_pdl(l2_scale_kernel<1, true>, grid, block, 0, s, p, (int)gx, slot);
+        if (e != cudaSuccess) { g_last_cuda_error = e; return DCT_ERR_CUDA; }
     }
-    return DCT_OK;
+    return check_launch();
 }
 
 extern "C" int dct_fgsm_f32(const float* img, const float* grad, float eps, float* adv, float* noise, int64_t n,
