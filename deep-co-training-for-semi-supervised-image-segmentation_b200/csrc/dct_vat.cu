@@ -21,6 +21,7 @@ namespace dct {
 
 constexpr int kL2Threads = 256;
 constexpr int kL2Cluster = 8;       // portable maximum cluster size
+constexpr int kL2ClusterBig = 16;   // B200's non-portable maximum (opt-in per function): samples up to 1 MB stay one launch
 constexpr int kL2MaxVecPerThread = 16;  // float4 per thread held in registers (64 floats)
 
 struct L2Args {
@@ -57,10 +58,12 @@ __device__ __forceinline__ float block_sum_f(float v, float* s_warp) {
 // memory (2 per lane) and reduces them with the same shuffle tree (so all 2048 threads of the
 // cluster hold bit-identical norms).  Per-pass slots make a second barrier per pass unnecessary;
 // the image (for the clamp(img + r) tail) is prefetched before the first barrier.
-template <int NV, bool IMG>
-__global__ void __cluster_dims__(kL2Cluster, 1, 1) __launch_bounds__(kL2Threads)
+template <int NV, bool IMG, int CL = kL2Cluster>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(kL2Threads)
 l2_cluster_kernel(const L2Args a) {
-    static_assert(kL2Cluster * (kL2Threads / 32) == 64, "gather assumes 64 partials = 2 per lane");
+    constexpr int kL2Cluster = CL;   // (shadows the namespace constant: 8, or 16 for the large-sample instantiations)
+    constexpr int kWarps = kL2Threads / 32;
+    static_assert((CL * kWarps) % 32 == 0 && kWarps == 8, "gather: CL x 8 partials, CL / 4 per lane");
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ float s_wsum[2][kL2Threads / 32];  // [pass][warp], read by the cluster peers
     const unsigned int rank = cluster.block_rank();
@@ -89,8 +92,10 @@ l2_cluster_kernel(const L2Args a) {
         const float w = warp_sum(ss);
         if (lane == 0) s_wsum[pass][wid] = w;
         cluster.sync();
-        float t = *cluster.map_shared_rank(&s_wsum[pass][lane & 7], lane >> 3) +
-                  *cluster.map_shared_rank(&s_wsum[pass][lane & 7], 4 + (lane >> 3));
+        float t = 0.0f;
+#pragma unroll
+        for (int i = 0; i < CL / 4; ++i)   // lane l reads warp (l & 7) of CTAs (l >> 3) + 4 i, in a fixed order
+            t += *cluster.map_shared_rank(&s_wsum[pass][lane & 7], 4 * i + (lane >> 3));
         t = warp_sum(t);
         const float nrm = sqrtf(t) + 1e-16f;
         ss = 0.0f;
@@ -262,6 +267,22 @@ extern "C" int dct_l2_normalize_f32(const float* d, float* out, int64_t B, int64
     const bool vec_ok = (M % 4) == 0 && aligned(d, 16) && aligned(out, 16) && aligned(img, 16) && aligned(adv, 16);
     const int64_t per_wave = (int64_t)kL2Cluster * kL2Threads * 4;  // floats covered by one float4 per thread
     const int64_t nv = (M + per_wave - 1) / per_wave;
+    const int64_t nv_big = (nv + 1) / 2;   // float4 per thread with a cluster of 16
+    if (vec_ok && nv > kL2MaxVecPerThread && nv_big <= kL2MaxVecPerThread && B * kL2ClusterBig <= 0x7fffffff) {
+        // 512 KB < sample <= 1 MB (spleen 512 x 512 slices): one cluster of 16 CTAs per sample
+        dim3 grid((unsigned)(B * kL2ClusterBig));
+        auto go = [&](auto kern) -> cudaError_t {
+            // the opt-in is per function and device; setting it again is harmless and costs a host-side table lookup
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e != cudaSuccess) return e;
+            return launch_pdl(kern, grid, dim3(kL2Threads), 0, s, a);
+        };
+        cudaError_t e;
+        if (nv_big <= 8) e = img != nullptr ? go(l2_cluster_kernel<8, true, kL2ClusterBig>) : go(l2_cluster_kernel<8, false, kL2ClusterBig>);
+        else e = img != nullptr ? go(l2_cluster_kernel<16, true, kL2ClusterBig>) : go(l2_cluster_kernel<16, false, kL2ClusterBig>);
+        if (e == cudaSuccess) return check_launch();
+        (void)cudaGetLastError();   // cluster of 16 refused on this device / configuration: the grid-wide passes below
+    }
     if (vec_ok && nv <= kL2MaxVecPerThread && B * kL2Cluster <= 0x7fffffff) {
         dim3 grid((unsigned)(B * kL2Cluster));
         cudaError_t e;

@@ -186,7 +186,9 @@ def test_vat_vs_reference(case, dct, dev):
 def test_l2_normalize_paths_vs_oracle(dct, dev, oracle):
     g = torch.Generator().manual_seed(7)
     # cluster path (1..16 float4 per thread), the two-launch fallback (large / odd M), scale + clamp tail
-    for shape in [(32, 1, 256, 256), (3, 3, 128, 256), (2, 3, 512, 1024), (5, 1, 33, 7), (2, 1, 1, 1)]:
+    # ... and one cluster of 16 CTAs per sample for 512 KB < sample <= 1 MB (spleen 512 x 512 slices)
+    for shape in [(32, 1, 256, 256), (3, 3, 128, 256), (2, 3, 512, 1024), (5, 1, 33, 7), (2, 1, 1, 1), (4, 1, 512, 512),
+                  (3, 1, 384, 512)]:
         d = torch.randn(*shape, generator=g)
         img = torch.rand(*shape, generator=g)
         want = oracle.l2_normalize(d.numpy())
