@@ -84,6 +84,14 @@ __device__ __forceinline__ void tile_st_row(unsigned char* row, int p0, const FV
 #ifndef DCT_STREAM_MIN_ROWS
 #define DCT_STREAM_MIN_ROWS 1000
 #endif
+// Fused Dice counters (NDICE > 0).  1 (product): every consumer thread keeps its packed 8-bit counters in registers ACROSS
+// tiles and its warp reduces + adds them to the global int64 counters only when the image changes, before a field could
+// overflow, and at the end of the CTA's work -- nothing Dice-related is left in the tile loop but the per-pixel arg-max.
+// 0: the first scheme (per tile: 1 + 2*NDICE warp reductions into the stage's label row, folded by the producer warp),
+// kept for the A/B (tools/kbench_tile.cu -DDCT_DICE_LOCAL=0; profiles/r19/).
+#ifndef DCT_DICE_LOCAL
+#define DCT_DICE_LOCAL 1
+#endif
 constexpr int kTileMaxTensors = 8;
 constexpr int kTileMaxRows = 80;   // NIN*C rows per stage
 
@@ -175,6 +183,8 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
     using Cfg = TileCfg<Op, CT, PPT, CTHREADS, STAGES, ET>;
     constexpr int TP = Cfg::TP, ROWS = Cfg::ROWS, ES = Cfg::ES, NIN = Op::NIN, NOUT = Op::NOUT, C = CT;
     constexpr bool DICE = Op::NDICE > 0;
+    constexpr bool DICE_LOCAL = DICE && (DCT_DICE_LOCAL != 0);   // counters live in the consumers' registers across tiles
+    constexpr bool DICE_FOLD = DICE && !DICE_LOCAL;               // per-tile fold through the label row by the producer warp
     constexpr bool LAB = op_labels<Op>::value;   // the op consumes the labels itself
     // > 40 fp32 rows per pixel do not fit the register file as a pixel pair: ops that can, work on the stage in place
     constexpr bool STREAM = op_stream<Op>::value && ROWS >= DCT_STREAM_MIN_ROWS && PPT <= 2 && std::is_same<ET, float>::value;
@@ -287,12 +297,12 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
         };
         // Dice: producer lane r (and r + 32) keeps counter r = (view, class, kind) of the image being processed in a
         // register and adds it to the global int64 counters when the image changes (integer atomics: order-independent)
-        constexpr int kDiceCounters = DICE ? Op::NDICE * C * 3 : 0;
+        constexpr int kDiceCounters = DICE_FOLD ? Op::NDICE * C * 3 : 0;
         constexpr int kDiceRounds = (kDiceCounters + 31) / 32;
         unsigned int dacc[kDiceRounds > 0 ? kDiceRounds : 1] = {};
         int cur_b = -1;
         auto flush_dice = [&](int bb) {
-            if constexpr (DICE) {
+            if constexpr (DICE_FOLD) {
 #pragma unroll
                 for (int rr = 0; rr < kDiceRounds; ++rr) {
                     const int r = rr * 32 + lane;
@@ -323,7 +333,7 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
             // and, AFTER this iteration's copies have been issued, add it to their per-image registers (any global
             // atomics of an image change then never sit in front of the release of the refill's barrier arrive).
             unsigned int dsum[kDiceRounds > 0 ? kDiceRounds : 1];
-            if constexpr (DICE) {
+            if constexpr (DICE_FOLD) {
                 if (do_dice) {
                     const unsigned int* pkw = reinterpret_cast<const unsigned int*>(stages + (size_t)stage * Cfg::kStageBytes + Cfg::kLabelOffB);
 #pragma unroll
@@ -366,7 +376,7 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
                     try_issue();
                 }
             }
-            if constexpr (DICE) {
+            if constexpr (DICE_FOLD) {
                 if (do_dice) {
                     if (b != cur_b) {  // uniform across the warp
                         if (cur_b >= 0) flush_dice(cur_b);
@@ -378,7 +388,7 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
             }
             __syncwarp();
         }
-        if constexpr (DICE) {
+        if constexpr (DICE_FOLD) {
             if (do_dice && cur_b >= 0) flush_dice(cur_b);
         }
         if constexpr (NOUT > 0) {
@@ -389,6 +399,51 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
         float gs = 1.0f;
         if constexpr (Op::USES_UP) gs = upstream_scalar(a.up);
         int nbad_label = 0;
+        // Dice: packed 8-bit per-class counters of this thread, [view][I,P], and |gt == c| (the same for every view).
+        // DICE_LOCAL: they live across tiles (dice_b = the image they belong to) and are flushed by dice_flush();
+        // DICE_FOLD: they are this tile's only and go to the producer warp through the label row.
+        unsigned int pk[DICE ? Op::NDICE : 1][2] = {};
+        unsigned int pkG = 0u;
+        int dice_b = -1, dice_tiles = 0;
+        constexpr int kDiceMaxTiles = 255 / PPT;   // a field grows by at most PPT per tile
+        auto dice_flush = [&](int bb) {            // warp-uniform call sites only
+            if constexpr (DICE_LOCAL) {
+                // widen every packed word into two words of 16-bit fields (classes 0,2 and 1,3): 32 lanes * 255 < 2^16
+                constexpr int NW = 1 + 2 * Op::NDICE;
+                unsigned int red[NW][2];
+                red[0][0] = __reduce_add_sync(0xffffffffu, pkG & 0x00ff00ffu);
+                red[0][1] = __reduce_add_sync(0xffffffffu, (pkG >> 8) & 0x00ff00ffu);
+                pkG = 0u;
+#pragma unroll
+                for (int n = 0; n < Op::NDICE; ++n)
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        red[1 + 2 * n + k][0] = __reduce_add_sync(0xffffffffu, pk[n][k] & 0x00ff00ffu);
+                        red[1 + 2 * n + k][1] = __reduce_add_sync(0xffffffffu, (pk[n][k] >> 8) & 0x00ff00ffu);
+                        pk[n][k] = 0u;
+                    }
+                // lane r (and r + 32) owns counter r = (view, class, kind): one int64 atomic per non-zero counter
+                constexpr int kCnt = Op::NDICE * C * 3;
+#pragma unroll
+                for (int rr = 0; rr < (kCnt + 31) / 32; ++rr) {
+                    const int r = rr * 32 + lane;
+                    unsigned int val = 0u;
+#pragma unroll
+                    for (int R = rr * 32; R < rr * 32 + 32; ++R) {
+                        if (R < kCnt) {   // compile-time after unrolling: no dynamic register indexing
+                            const int n = R / (C * 3), rc = R - n * C * 3, c = rc / 3, kind = rc - c * 3;
+                            const int widx = kind == 1 ? 0 : (kind == 0 ? 1 + 2 * n : 2 + 2 * n);
+                            const unsigned int f = (red[widx][c & 1] >> (16 * (c >> 1))) & 0xffffu;
+                            if (r == R) val = f;
+                        }
+                    }
+                    if (r < kCnt && val != 0u) {
+                        const int n = r / (C * 3), rc = r - n * C * 3;
+                        atomicAdd(a.counts + (int64_t)n * a.count_view_stride + (int64_t)bb * C * 3 + rc, (unsigned long long)val);
+                    }
+                }
+            }
+        };
 #pragma unroll 1
         for (int i = 0;; ++i) {
             const int stage = i % STAGES;
@@ -396,6 +451,16 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
             const int tile = s_tile[stage];
             if (tile < 0) break;
             const int b = tile / tpi;
+            if constexpr (DICE_LOCAL) {
+                if (do_dice) {
+                    if (b != dice_b || dice_tiles == kDiceMaxTiles) {   // uniform across the warp
+                        if (dice_b >= 0) dice_flush(dice_b);
+                        dice_b = b;
+                        dice_tiles = 0;
+                    }
+                    ++dice_tiles;
+                }
+            }
             const int64_t off = (int64_t)(tile - b * tpi) * TP;
             const int64_t rem = HW - off;
             const int len = (int)(rem < TP ? rem : TP);
@@ -403,9 +468,8 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
             const int p0 = tid * PPT;
             const bool active = p0 < len;
             const unsigned int amask = CONF ? __ballot_sync(0xffffffffu, active) : 0u;  // lanes that enter the block below
-            unsigned int pk[DICE ? Op::NDICE : 1][2];  // this tile's packed 8-bit per-class counters: [view][I,P]
-            unsigned int pkG = 0u;                     // |gt == c| is the same for every view
-            if constexpr (DICE) {
+            if constexpr (DICE_FOLD) {
+                pkG = 0u;
 #pragma unroll
                 for (int n = 0; n < Op::NDICE; ++n) pk[n][0] = pk[n][1] = 0u;
             }
@@ -544,7 +608,7 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
             }
             if constexpr (NOUT > 0) tma::fence_proxy_async_smem();
             __syncwarp();
-            if constexpr (DICE) {
+            if constexpr (DICE_FOLD) {
                 if (do_dice) {
                     // every packed field is <= 32 lanes * PPT < 256, so the packed words are reduced across the warp as
                     // they are (REDUX); the warp's labels have all been read, so its slice of the label row is free
@@ -563,6 +627,9 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
                 }
             }
             if (lane == 0) tma::mbar_arrive(&done[stage]);
+        }
+        if constexpr (DICE_LOCAL) {
+            if (do_dice && dice_b >= 0) dice_flush(dice_b);
         }
         if constexpr (LROW) {
             if (do_lab) {

@@ -461,6 +461,42 @@ def test_full_size_properties(K, C, B, H, W, dct, dev):
 
 
 # ---------------------------------------------------------------------------------------------
+# Dice counters kept in registers across tiles (csrc/dct_tile.cuh, DCT_DICE_LOCAL): images so large that one CTA works
+# through hundreds of tiles of the SAME image, so the packed 8-bit fields must be flushed before they overflow
+# (every 255 / pixels-per-thread tiles), plus a ragged last tile and a batch of 1 (fewer flushes than warps)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("C,B,H,W", [(4, 2, 4096, 4096), (2, 1, 4096, 4100), (4, 3, 2048, 2052)])
+def test_dice_counters_long_runs_of_one_image(C, B, H, W, dct, dev):
+    g = torch.Generator(device=dev).manual_seed(99)
+    K = 2
+    z = [3 * torch.randn(B, C, H, W, generator=g, device=dev) for _ in range(K)]
+    gt = torch.randint(0, C, (B, 1, H, W), generator=g, device=dev)
+    gt[:, :, : H // 3] = 0  # unbalanced: class 0 alone would overflow an 8-bit field within 64 tiles
+
+    def want(zk):
+        pred = zk.argmax(1)  # random data: no ties, equals argmax softmax
+        lab = gt.squeeze(1)
+        return torch.stack([torch.stack([((pred == c) & (lab == c)).flatten(1).sum(1), (lab == c).flatten(1).sum(1),
+                                         (pred == c).flatten(1).sum(1)], 1) for c in range(C)], 1)   # [B,C,3]
+
+    ref = [want(t) for t in z]
+    # the Dice meter's own kernel (one tensor, 4 pixels per thread)
+    for k in range(K):
+        assert torch.equal(dct.dice_counts(z[k], gt), ref[k])
+    # fused into the JSD launch (K count sets, 2 pixels per thread)
+    counts = torch.zeros(K, B, C, 3, dtype=torch.int64, device=dev)
+    zr = [t.clone().requires_grad_() for t in z]
+    dct.jsd_consistency_from_logits(zr, weight=1.0, labels=gt, dice_counts=counts).backward()
+    for k in range(K):
+        assert torch.equal(counts[k], ref[k])
+    del zr
+    # fused into the cross-entropy launch
+    c1 = torch.zeros(B, C, 3, dtype=torch.int64, device=dev)
+    dct.supervised_from_logits(z[0].clone().requires_grad_(), gt, dice_counts=c1).backward()
+    assert torch.equal(c1, ref[0])
+
+
+# ---------------------------------------------------------------------------------------------
 # K*C > 40 (K = 3, 4 at C = 19): the shared-memory-resident JSD body (jsd_stream_pair) -- ragged tails, saturated
 # logits whose exponentials underflow to zero, identical views, confident and agreeing inputs
 # ---------------------------------------------------------------------------------------------
