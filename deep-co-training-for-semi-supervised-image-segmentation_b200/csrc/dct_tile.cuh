@@ -85,10 +85,14 @@ __device__ __forceinline__ void tile_st_row(unsigned char* row, int p0, const FV
 #define DCT_STREAM_MIN_ROWS 1000
 #endif
 // Fused Dice counters (NDICE > 0).  1 (product): every consumer thread keeps its packed 8-bit counters in registers ACROSS
-// tiles and its warp reduces + adds them to the global int64 counters only when the image changes, before a field could
-// overflow, and at the end of the CTA's work -- nothing Dice-related is left in the tile loop but the per-pixel arg-max.
-// 0: the first scheme (per tile: 1 + 2*NDICE warp reductions into the stage's label row, folded by the producer warp),
-// kept for the A/B (tools/kbench_tile.cu -DDCT_DICE_LOCAL=0; profiles/r19/).
+// tiles.  The producer marks the tiles after which they must be handed over (the CTA's next tile belongs to another image
+// or does not exist, or a field could overflow); only on a marked tile do the consumer warps reduce their counters into
+// their slice of the stage's label row, and the producer warp adds the 8 warps' numbers to the global int64 counters --
+// a handful of times per CTA, nothing Dice-related in the other tiles but the per-pixel arg-max.
+// 0: the first scheme (EVERY tile: 1 + 2*NDICE warp reductions into the label row, folded into registers by the producer),
+// kept for the A/B (tools/kbench_tile.cu -DDCT_DICE_LOCAL=0).  Measured (profiles/r19, r20): per-tile fold 41.9 us at c2;
+// consumer warps adding to global memory themselves 41.6 us at c2 but +1 us at c1 / +2.7 us at c3-sized inputs (8x the
+// atomics on a few dozen addresses at the kernel's end); marked tiles: see profiles/r20/kbench_dice_ab.log.
 #ifndef DCT_DICE_LOCAL
 #define DCT_DICE_LOCAL 1
 #endif
@@ -200,6 +204,7 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + Cfg::kStageBytes * STAGES);
     uint64_t* done = full + STAGES;
     __shared__ int s_tile[STAGES];  // tile index held by each stage; -1 = end of work
+    __shared__ int s_mark[STAGES];  // DICE_LOCAL: 1 = hand the Dice counters over after this tile (written with s_tile)
     __shared__ unsigned int s_conf[CONF ? CT * CT : 1];   // this CTA's confusion counts (flushed once, at the end)
     const int tid = threadIdx.x, lane = tid & 31;
     const bool is_producer = tid >= CTHREADS;
@@ -257,6 +262,8 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
             ++draws;
             return t;
         };
+        int run_b = -1, run_len = 0;               // DICE_LOCAL: image and length of the current run of tiles (lane 0)
+        constexpr int kDiceMaxTiles = 255 / PPT;   // a packed 8-bit field grows by at most PPT per tile
         int issued = 0;        // loads issued so far; the k-th goes to stage k % STAGES
         bool more = true;
         int pending = 0;       // drawn one ahead of its use
@@ -272,6 +279,14 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
             pending = draw();
             s_tile[stage] = tile;
             const int b = tile / tpi;
+            if constexpr (DICE_LOCAL) {
+                // last tile of a run of one image (or of this CTA's work), or the run is as long as an 8-bit field allows
+                run_len = (b == run_b) ? run_len + 1 : 1;
+                run_b = b;
+                const bool mark = pending >= a.num_tiles || pending / tpi != b || run_len == kDiceMaxTiles;
+                if (mark) run_b = -1;
+                s_mark[stage] = mark ? 1 : 0;
+            }
             const int64_t off = (int64_t)(tile - b * tpi) * TP;
             const int64_t rem = HW - off;
             const uint32_t npix = (uint32_t)(rem < TP ? rem : TP);
@@ -297,7 +312,7 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
         };
         // Dice: producer lane r (and r + 32) keeps counter r = (view, class, kind) of the image being processed in a
         // register and adds it to the global int64 counters when the image changes (integer atomics: order-independent)
-        constexpr int kDiceCounters = DICE_FOLD ? Op::NDICE * C * 3 : 0;
+        constexpr int kDiceCounters = DICE ? Op::NDICE * C * 3 : 0;
         constexpr int kDiceRounds = (kDiceCounters + 31) / 32;
         unsigned int dacc[kDiceRounds > 0 ? kDiceRounds : 1] = {};
         int cur_b = -1;
@@ -333,6 +348,27 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
             // and, AFTER this iteration's copies have been issued, add it to their per-image registers (any global
             // atomics of an image change then never sit in front of the release of the refill's barrier arrive).
             unsigned int dsum[kDiceRounds > 0 ? kDiceRounds : 1];
+            bool hand_over = false;
+            if constexpr (DICE_LOCAL) {
+                // marked tile: every consumer warp left 2 * (1 + 2*NDICE) words of 16-bit fields (classes 0,2 / 1,3 of
+                // |gt==c|, then I / P of every view) in its slice of the label row; lane r sums counter r over the warps
+                hand_over = do_dice && s_mark[stage] != 0;   // written by lane 0 at issue time (a __syncwarp() ago)
+                if (hand_over) {
+                    const unsigned int* pkw = reinterpret_cast<const unsigned int*>(stages + (size_t)stage * Cfg::kStageBytes + Cfg::kLabelOffB);
+#pragma unroll
+                    for (int rr = 0; rr < kDiceRounds; ++rr) {
+                        const int r = rr * 32 + lane;
+                        unsigned int sum = 0u;
+                        if (r < kDiceCounters) {
+                            const int n = r / (C * 3), rc = r - n * C * 3, c = rc / 3, kind = rc - c * 3;
+                            const int widx = kind == 1 ? 0 : (kind == 0 ? 1 + 2 * n : 2 + 2 * n);
+#pragma unroll
+                            for (int w = 0; w < NCW; ++w) sum += (pkw[w * 64 * PPT + 2 * widx + (c & 1)] >> (16 * (c >> 1))) & 0xffffu;
+                        }
+                        dsum[rr] = sum;
+                    }
+                }
+            }
             if constexpr (DICE_FOLD) {
                 if (do_dice) {
                     const unsigned int* pkw = reinterpret_cast<const unsigned int*>(stages + (size_t)stage * Cfg::kStageBytes + Cfg::kLabelOffB);
@@ -376,6 +412,18 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
                     try_issue();
                 }
             }
+            if constexpr (DICE_LOCAL) {
+                if (hand_over) {   // uniform across the warp; after this iteration's copies have been issued
+#pragma unroll
+                    for (int rr = 0; rr < kDiceRounds; ++rr) {
+                        const int r = rr * 32 + lane;
+                        if (r < kDiceCounters && dsum[rr] != 0u) {
+                            const int n = r / (C * 3), rc = r - n * C * 3;
+                            atomicAdd(a.counts + (int64_t)n * a.count_view_stride + (int64_t)b * C * 3 + rc, (unsigned long long)dsum[rr]);
+                        }
+                    }
+                }
+            }
             if constexpr (DICE_FOLD) {
                 if (do_dice) {
                     if (b != cur_b) {  // uniform across the warp
@@ -400,50 +448,9 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
         if constexpr (Op::USES_UP) gs = upstream_scalar(a.up);
         int nbad_label = 0;
         // Dice: packed 8-bit per-class counters of this thread, [view][I,P], and |gt == c| (the same for every view).
-        // DICE_LOCAL: they live across tiles (dice_b = the image they belong to) and are flushed by dice_flush();
-        // DICE_FOLD: they are this tile's only and go to the producer warp through the label row.
+        // DICE_LOCAL: they live across tiles until the producer marks a tile (s_mark); DICE_FOLD: they are one tile's.
         unsigned int pk[DICE ? Op::NDICE : 1][2] = {};
         unsigned int pkG = 0u;
-        int dice_b = -1, dice_tiles = 0;
-        constexpr int kDiceMaxTiles = 255 / PPT;   // a field grows by at most PPT per tile
-        auto dice_flush = [&](int bb) {            // warp-uniform call sites only
-            if constexpr (DICE_LOCAL) {
-                // widen every packed word into two words of 16-bit fields (classes 0,2 and 1,3): 32 lanes * 255 < 2^16
-                constexpr int NW = 1 + 2 * Op::NDICE;
-                unsigned int red[NW][2];
-                red[0][0] = __reduce_add_sync(0xffffffffu, pkG & 0x00ff00ffu);
-                red[0][1] = __reduce_add_sync(0xffffffffu, (pkG >> 8) & 0x00ff00ffu);
-                pkG = 0u;
-#pragma unroll
-                for (int n = 0; n < Op::NDICE; ++n)
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        red[1 + 2 * n + k][0] = __reduce_add_sync(0xffffffffu, pk[n][k] & 0x00ff00ffu);
-                        red[1 + 2 * n + k][1] = __reduce_add_sync(0xffffffffu, (pk[n][k] >> 8) & 0x00ff00ffu);
-                        pk[n][k] = 0u;
-                    }
-                // lane r (and r + 32) owns counter r = (view, class, kind): one int64 atomic per non-zero counter
-                constexpr int kCnt = Op::NDICE * C * 3;
-#pragma unroll
-                for (int rr = 0; rr < (kCnt + 31) / 32; ++rr) {
-                    const int r = rr * 32 + lane;
-                    unsigned int val = 0u;
-#pragma unroll
-                    for (int R = rr * 32; R < rr * 32 + 32; ++R) {
-                        if (R < kCnt) {   // compile-time after unrolling: no dynamic register indexing
-                            const int n = R / (C * 3), rc = R - n * C * 3, c = rc / 3, kind = rc - c * 3;
-                            const int widx = kind == 1 ? 0 : (kind == 0 ? 1 + 2 * n : 2 + 2 * n);
-                            const unsigned int f = (red[widx][c & 1] >> (16 * (c >> 1))) & 0xffffu;
-                            if (r == R) val = f;
-                        }
-                    }
-                    if (r < kCnt && val != 0u) {
-                        const int n = r / (C * 3), rc = r - n * C * 3;
-                        atomicAdd(a.counts + (int64_t)n * a.count_view_stride + (int64_t)bb * C * 3 + rc, (unsigned long long)val);
-                    }
-                }
-            }
-        };
 #pragma unroll 1
         for (int i = 0;; ++i) {
             const int stage = i % STAGES;
@@ -451,16 +458,7 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
             const int tile = s_tile[stage];
             if (tile < 0) break;
             const int b = tile / tpi;
-            if constexpr (DICE_LOCAL) {
-                if (do_dice) {
-                    if (b != dice_b || dice_tiles == kDiceMaxTiles) {   // uniform across the warp
-                        if (dice_b >= 0) dice_flush(dice_b);
-                        dice_b = b;
-                        dice_tiles = 0;
-                    }
-                    ++dice_tiles;
-                }
-            }
+            const bool hand_over = DICE_LOCAL && do_dice && s_mark[stage] != 0;   // uniform across the CTA's consumers
             const int64_t off = (int64_t)(tile - b * tpi) * TP;
             const int64_t rem = HW - off;
             const int len = (int)(rem < TP ? rem : TP);
@@ -608,6 +606,29 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
             }
             if constexpr (NOUT > 0) tma::fence_proxy_async_smem();
             __syncwarp();
+            if constexpr (DICE_LOCAL) {
+                if (hand_over) {
+                    // widen every packed word into two words of 16-bit fields (classes 0,2 and 1,3; 32 lanes * 255 < 2^16),
+                    // reduce them across the warp (REDUX) and leave them in the warp's slice of the label row (its labels
+                    // have all been read); the producer warp adds the warps' numbers once `done` has completed
+                    constexpr int NW = 1 + 2 * Op::NDICE;
+                    unsigned int mine = 0u;
+#pragma unroll
+                    for (int j = 0; j < NW; ++j) {
+                        const unsigned int w = j == 0 ? pkG : pk[(j - 1) >> 1][(j - 1) & 1];
+                        const unsigned int lo = __reduce_add_sync(0xffffffffu, w & 0x00ff00ffu);
+                        const unsigned int hi = __reduce_add_sync(0xffffffffu, (w >> 8) & 0x00ff00ffu);
+                        if (lane == 2 * j) mine = lo;
+                        if (lane == 2 * j + 1) mine = hi;
+                    }
+                    static_assert(2 * NW <= 32, "one lane per reduced word");
+                    if (lane < 2 * NW) reinterpret_cast<unsigned int*>(st + Cfg::kLabelOffB)[(tid >> 5) * 64 * PPT + lane] = mine;
+                    pkG = 0u;
+#pragma unroll
+                    for (int n = 0; n < Op::NDICE; ++n) pk[n][0] = pk[n][1] = 0u;
+                    __syncwarp();
+                }
+            }
             if constexpr (DICE_FOLD) {
                 if (do_dice) {
                     // every packed field is <= 32 lanes * PPT < 256, so the packed words are reduced across the warp as
@@ -627,9 +648,6 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
                 }
             }
             if (lane == 0) tma::mbar_arrive(&done[stage]);
-        }
-        if constexpr (DICE_LOCAL) {
-            if (do_dice && dice_b >= 0) dice_flush(dice_b);
         }
         if constexpr (LROW) {
             if (do_lab) {
