@@ -174,8 +174,9 @@ struct TileCfg {
 //   producer: lane 0 owns the tile schedule (a contiguous range per CTA whose last fifth is shared through an
 //       atomic counter, see draw() below), publishes each tile index in the stage's shared-memory slot, issues every
 //       bulk load / store, and recycles a stage when its `done` mbarrier (NCW arrivals) has completed and, for ops
-//       with outputs, when the bulk store group that drains it has finished reading shared memory.  All 32 lanes
-//       fold the consumers' per-tile Dice counters into per-image registers (global int64 atomics on image change).
+//       with outputs, when the bulk store group that drains it has finished reading shared memory.  Fused Dice: lane 0
+//       marks the last tile of every run of one image (s_mark); on those tiles all 32 lanes add the counters the
+//       consumer warps hand over through the label row to the global int64 counters (see DCT_DICE_LOCAL above).
 //   consumers: wait on the stage's `full` mbarrier (transaction bytes), read the tile index (-1 = no more work),
 //       compute in registers, write results back in place, fence to the async proxy, arrive on `done`.
 //       No CTA-wide barrier in the tile loop: a fast warp runs ahead by up to STAGES-1 tiles.
@@ -310,8 +311,10 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
             }
             ++issued;
         };
-        // Dice: producer lane r (and r + 32) keeps counter r = (view, class, kind) of the image being processed in a
-        // register and adds it to the global int64 counters when the image changes (integer atomics: order-independent)
+        // Dice: producer lane r (and r + 32) owns counter r = (view, class, kind).  DICE_LOCAL: it adds what the consumer
+        // warps hand over on a marked tile straight to the global int64 counters; DICE_FOLD: it keeps the counter of the
+        // image being processed in a register, fed on every tile, and adds it to the global counter when the image changes
+        // (integer atomics either way: order-independent)
         constexpr int kDiceCounters = DICE ? Op::NDICE * C * 3 : 0;
         constexpr int kDiceRounds = (kDiceCounters + 31) / 32;
         unsigned int dacc[kDiceRounds > 0 ? kDiceRounds : 1] = {};
