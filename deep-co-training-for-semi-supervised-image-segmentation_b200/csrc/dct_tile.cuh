@@ -96,6 +96,17 @@ __device__ __forceinline__ void tile_st_row(unsigned char* row, int p0, const FV
 #ifndef DCT_DICE_LOCAL
 #define DCT_DICE_LOCAL 1
 #endif
+// Developer experiment (off in the product): the LAST DCT_POOL_SPLIT_LEVELS levels of the dynamically scheduled
+// tail pool are handed out as DCT_POOL_SPLIT sub-tiles of TP / DCT_POOL_SPLIT pixels each, so that the CTAs' finishing times
+// spread over a fraction of a tile's service time instead of a whole one (measured end spread at c2: 4.5 us on a 41 us
+// kernel, profiles/r10/kbench_c2_family.log).  1 = whole tiles only: every change sits under #if DCT_POOL_SPLIT > 1, the
+// product's translation units compile to the SASS they had before (checked with cuobjdump).  Not yet run on hardware.
+#ifndef DCT_POOL_SPLIT
+#define DCT_POOL_SPLIT 1
+#endif
+#ifndef DCT_POOL_SPLIT_LEVELS
+#define DCT_POOL_SPLIT_LEVELS 1
+#endif
 constexpr int kTileMaxTensors = 8;
 constexpr int kTileMaxRows = 80;   // NIN*C rows per stage
 
@@ -167,7 +178,11 @@ struct TileCfg {
     static constexpr size_t kRowBytes = (size_t)TP * ES;            // one data row
     static constexpr size_t kLabelOffB = (size_t)ROWS * TP * ES;    // in bytes; labels are 8-byte, TP*8 bytes
     static constexpr size_t kGmapOffB = kLabelOffB + (op_label_row<Op>() ? (size_t)TP * 8 : 0);  // valid when Op::GMAP (fp32 row)
+#if DCT_POOL_SPLIT > 1
+    static constexpr size_t kSmemBytes = kStageBytes * STAGES + 16 * STAGES + 4 * STAGES;   // + the stages' sub-tile indices
+#else
     static constexpr size_t kSmemBytes = kStageBytes * STAGES + 16 * STAGES;
+#endif
 };
 
 // Warp-specialised persistent kernel: NCW consumer warps + 1 producer warp per CTA.
@@ -204,6 +219,23 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
     unsigned char* stages = smem_raw;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + Cfg::kStageBytes * STAGES);
     uint64_t* done = full + STAGES;
+#if DCT_POOL_SPLIT > 1
+    constexpr int SPLIT_S = DCT_POOL_SPLIT, TPS = NCW * 32 * PPT / SPLIT_S;   // sub-tiles per tile, pixels per sub-tile
+    static_assert((NCW * 32 * PPT) % SPLIT_S == 0 && (TPS * (int)sizeof(ET)) % 16 == 0, "sub-tile rows stay 16-byte multiples");
+    int* s_part = reinterpret_cast<int*>(done + STAGES);   // sub-tile index held by each stage, -1 = a whole tile
+    // pixel offset (inside image tile / tiles_per_image) and length of tile `tile`, or of its sub-tile `part` (len 0: empty)
+    auto tile_span = [&](int tile, int part, int64_t& off, int& len) {
+        const int bb = tile / a.tiles_per_image;
+        off = (int64_t)(tile - bb * a.tiles_per_image) * (NCW * 32 * PPT);
+        const int64_t rem = a.HW - off;
+        len = (int)(rem < NCW * 32 * PPT ? rem : NCW * 32 * PPT);
+        if (part >= 0) {
+            const int o = part * TPS;
+            off += o;
+            len = len - o < 0 ? 0 : (len - o < TPS ? len - o : TPS);
+        }
+    };
+#endif
     __shared__ int s_tile[STAGES];  // tile index held by each stage; -1 = end of work
     __shared__ int s_mark[STAGES];  // DICE_LOCAL: 1 = hand the Dice counters over after this tile (written with s_tile)
     __shared__ unsigned int s_conf[CONF ? CT * CT : 1];   // this CTA's confusion counts (flushed once, at the end)
@@ -248,8 +280,37 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
         const int pool_q = dynamic ? per / (a.pool_div > 0 ? a.pool_div : 5) : 0;             // pool tiles taken from the end of every CTA's range
         const int my_static = my_n - pool_q;
         int draws = 0;
+#if DCT_POOL_SPLIT > 1
+        int draw_part = -1;    // sub-tile index of the tile draw() has just returned (-1 = whole tile)
+#endif
         auto draw = [&]() -> int {  // next tile index for this CTA; >= num_tiles when there is no more work
             int t;
+#if DCT_POOL_SPLIT > 1
+            draw_part = -1;
+            if (draws >= my_static && pool_q != 0) {
+                // pool levels [0, whole) are whole tiles; the last `lv` levels come as SPLIT_S sub-tiles each (all CTAs'
+                // part 0 of a level first, then part 1, ...); empty sub-tiles of a ragged tile are skipped
+                const int lv = pool_q < DCT_POOL_SPLIT_LEVELS ? pool_q : DCT_POOL_SPLIT_LEVELS, whole = pool_q - lv;
+                const unsigned int g = gridDim.x, n_whole = (unsigned int)whole * g;
+                for (;;) {
+                    unsigned int got;
+                    asm volatile("atom.global.relaxed.gpu.add.u32 %0, [%1], 1;" : "=r"(got) : "l"(&a.ws->tile_counter) : "memory");
+                    int j, k, part = -1;
+                    if (got < n_whole) { j = (int)(got % g); k = (int)(got / g); }
+                    else {
+                        const unsigned int r = got - n_whole, w = r % (g * SPLIT_S);
+                        k = whole + (int)(r / (g * SPLIT_S)); j = (int)(w % g); part = (int)(w / g);
+                    }
+                    if (k >= pool_q) { t = a.num_tiles; break; }
+                    t = j * per + min(j, extra) + per + (j < extra ? 1 : 0) - pool_q + k;
+                    int64_t o; int len;
+                    tile_span(t, part, o, len);
+                    if (len > 0) { draw_part = part; break; }
+                }
+                ++draws;
+                return t;
+            }
+#endif
             if (draws < my_static) t = my_begin + draws;
             else if (pool_q == 0) t = a.num_tiles;
             else {
@@ -268,9 +329,15 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
         int issued = 0;        // loads issued so far; the k-th goes to stage k % STAGES
         bool more = true;
         int pending = 0;       // drawn one ahead of its use
+#if DCT_POOL_SPLIT > 1
+        int pending_part = -1;
+#endif
         auto try_issue = [&]() {  // lane 0 only
             if (!more) return;
             const int tile = pending, stage = issued % STAGES;
+#if DCT_POOL_SPLIT > 1
+            const int part = pending_part;
+#endif
             if (tile >= a.num_tiles) {  // publish "no more work" through the same barrier
                 more = false;
                 s_tile[stage] = -1;
@@ -278,6 +345,10 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
                 return;
             }
             pending = draw();
+#if DCT_POOL_SPLIT > 1
+            pending_part = draw_part;
+            s_part[stage] = part;
+#endif
             s_tile[stage] = tile;
             const int b = tile / tpi;
             if constexpr (DICE_LOCAL) {
@@ -288,9 +359,16 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
                 if (mark) run_b = -1;
                 s_mark[stage] = mark ? 1 : 0;
             }
+#if DCT_POOL_SPLIT > 1
+            int64_t off;
+            int len_px;
+            tile_span(tile, part, off, len_px);
+            const uint32_t npix = (uint32_t)len_px;
+#else
             const int64_t off = (int64_t)(tile - b * tpi) * TP;
             const int64_t rem = HW - off;
             const uint32_t npix = (uint32_t)(rem < TP ? rem : TP);
+#endif
             const uint32_t bytes = npix * (uint32_t)ES;   // one data row segment
             unsigned char* dst = stages + (size_t)stage * Cfg::kStageBytes;
             uint32_t total = bytes * ROWS;
@@ -334,6 +412,9 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
         };
         if (lane == 0) {
             pending = draw();
+#if DCT_POOL_SPLIT > 1
+            pending_part = draw_part;
+#endif
 #pragma unroll 1
             for (int s = 0; s < STAGES; ++s) try_issue();
         }
@@ -392,9 +473,16 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
             __syncwarp();
             if (lane == 0) {
                 if constexpr (NOUT > 0) {
+#if DCT_POOL_SPLIT > 1
+                    int64_t off;
+                    int len_px;
+                    tile_span(tile, s_part[stage], off, len_px);
+                    const uint32_t bytes = (uint32_t)len_px * (uint32_t)ES;
+#else
                     const int64_t off = (int64_t)(tile - b * tpi) * TP;
                     const int64_t rem = HW - off;
                     const uint32_t bytes = (uint32_t)(rem < TP ? rem : TP) * (uint32_t)ES;
+#endif
                     const unsigned char* st = stages + (size_t)stage * Cfg::kStageBytes;
 #pragma unroll
                     for (int n = 0; n < NOUT; ++n)
@@ -462,9 +550,15 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
             if (tile < 0) break;
             const int b = tile / tpi;
             const bool hand_over = DICE_LOCAL && do_dice && s_mark[stage] != 0;   // uniform across the CTA's consumers
+#if DCT_POOL_SPLIT > 1
+            int64_t off;
+            int len;
+            tile_span(tile, s_part[stage], off, len);
+#else
             const int64_t off = (int64_t)(tile - b * tpi) * TP;
             const int64_t rem = HW - off;
             const int len = (int)(rem < TP ? rem : TP);
+#endif
             unsigned char* st = stages + (size_t)stage * Cfg::kStageBytes;
             const int p0 = tid * PPT;
             const bool active = p0 < len;
