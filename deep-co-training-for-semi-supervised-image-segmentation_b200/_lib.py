@@ -45,6 +45,7 @@ _SIGNATURES = {
     "dct_kl_logit_f32": [_p, _p, _i, _i64, _i64, _p, _p, _i, _p, _p, _f, _p, _p, _p, _p],
     "dct_kl_from_logits_fwdbwd_f32": [_p, _p, _i, _i64, _i64, _f, _f, _p, _p, _p, _p, _p, _p],
     "dct_kl_div_fwd_f32": [_p, _p, _i, _i64, _i64, _f, _p, _p, _p, _p, _p],
+    "dct_kl_div_bwd_f32": [_p, _p, _i, _i64, _i64, _f, _p, _p, _f, _p, _p, _p],
     "dct_entropy_fwd_f32": [_p, _i, _i64, _i64, _p, _p, _p, _p, _p],
     "dct_entropy_bwd_f32": [_p, _i, _i64, _i64, _p, _p, _f, _p, _p],
     "dct_softmax_fwd_f32": [_p, _i, _i64, _i64, _p, _p],

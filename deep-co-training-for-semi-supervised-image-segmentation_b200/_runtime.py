@@ -44,6 +44,24 @@ def get_check_mode() -> str:
     return _mode
 
 
+class check_mode:
+    """``with check_mode('deferred'): ...`` -- scoped assertion policy ('off' is never overridden: under ``python -O``
+    the reference's asserts are gone too)."""
+
+    def __init__(self, mode):
+        self.mode, self.old = mode, None
+
+    def __enter__(self):
+        if self.mode is not None and _mode != "off":
+            self.old = set_check_mode(self.mode)
+        return self
+
+    def __exit__(self, *exc):
+        if self.old is not None:
+            set_check_mode(self.old)
+        return False
+
+
 class StreamState:
     __slots__ = ("workspace", "flags")
 

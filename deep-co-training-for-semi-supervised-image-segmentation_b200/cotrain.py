@@ -23,6 +23,7 @@ import torch
 import torch.distributed as dist
 from torch import Tensor, nn
 
+from . import _runtime
 from . import distributed as D
 from .generators import fgsm_perturb
 from .loss import jsd_consistency_from_logits, kl_consistency_from_logits, softmax_dim1, supervised_from_logits
@@ -71,7 +72,11 @@ class DeviceReport:
         self.steps += 1
 
     def reduce(self, group=None) -> Dict[str, object]:
-        """All-reduce the counters (int64 SUM) and loss sums over the data-parallel ranks, then ONE host copy."""
+        """All-reduce the counters (int64 SUM) and loss sums over the data-parallel ranks, then ONE host copy.
+        This is also where the kernels' contract flags (labels outside [0,C), non-simplex targets) are read back in
+        'deferred' check mode: the reference's AssertionError surfaces here, once per reporting interval."""
+        if self.device.type == "cuda":
+            _runtime.raise_if_flagged()
         lab, unlab = self.counts["lab"].clone(), self.counts["unlab"].clone()
         sums = self.loss_sums.clone()
         world = 1
@@ -116,8 +121,16 @@ class CoTrainStep:
     """The iteration above for K networks ``nets[k](img) -> logits [B,C,H,W]`` and their optimizers."""
 
     def __init__(self, nets: Sequence[nn.Module], optimizers: Sequence[torch.optim.Optimizer], cfg: CoTrainConfig,
-                 device, ddp: bool = True):
+                 device, ddp: bool = True, check_mode: Optional[str] = "deferred"):
+        """``check_mode``: the assertion policy this loop runs under (``_runtime.set_check_mode``).  The default
+        'deferred' is what "nothing is read back inside the loop" needs: in the drop-ins' default 'eager' mode every
+        fused call that carries labels reads its 16-byte flag word back (one host sync per call, so that the
+        reference's AssertionError fires at the reference's call site); here the flags stay on the device and are
+        raised by ``report.reduce()``.  The mode is scoped to ``step()`` / ``evaluate()``; None leaves the process-wide
+        mode in force."""
         assert len(nets) == len(optimizers) and len(nets) >= 1
+        assert check_mode in (None, "eager", "deferred", "off")
+        self.check_mode = check_mode
         self.device = torch.device(device)
         self.cfg = cfg
         self.K = len(nets)
@@ -150,6 +163,10 @@ class CoTrainStep:
         """labeled: K pairs (img [B,Cin,H,W], gt [B,1,H,W] int64) already on the device (this rank's shard);
         unlabeled: (img, gt) -- gt feeds the unlabeled Dice meters only, as in the reference.  Returns the total
         loss tensor (not synchronised)."""
+        with _runtime.check_mode(self.check_mode):
+            return self._step(labeled, unlabeled)
+
+    def _step(self, labeled, unlabeled):
         cfg, C, dev = self.cfg, self.cfg.num_classes, self.device
         sup_losses, total = [], 0
         for k, (img, gt) in enumerate(labeled):
@@ -191,8 +208,9 @@ class CoTrainStep:
         Returns int64 counts ``[K,B,C,3]``; '2d' rows / '3d' batch Dice follow from ``dice_from_counts``."""
         C = self.cfg.num_classes
         out = torch.zeros(self.K, img.shape[0], C, 3, dtype=torch.int64, device=self.device)
-        for k, net in enumerate(self.raw_nets):
-            supervised_from_logits(net(img), gt, ignore_index=self.cfg.ignore_index, dice_counts=out[k])
+        with _runtime.check_mode(self.check_mode):
+            for k, net in enumerate(self.raw_nets):
+                supervised_from_logits(net(img), gt, ignore_index=self.cfg.ignore_index, dice_counts=out[k])
         return out
 
 

@@ -87,15 +87,16 @@ extern "C" int dct_mailbox_close(void* dev_ptr, int owned) {
 }
 
 namespace dct {
-// One thread per (value j, peer p): everything that does not depend on the previous launch -- the sequence counter
-// (only ever written by publications of this stream, all long complete) and the mailbox pointers -- is fetched while
-// that launch is still draining; after griddepcontrol.wait one parallel round of loads (the sums) and the stores remain.
+// One thread per (value j, peer p): what cannot depend on the previous launch -- the mailbox pointers -- is fetched while
+// that launch is still draining; after griddepcontrol.wait one parallel round of loads (counter + sums) and the stores remain.
 __global__ void __launch_bounds__(DCT_PUB_MAX_VALUES * DCT_MAX_PEERS) exchange_publish_kernel(const PeerPub pub) {
     const int t = threadIdx.x, j = t / DCT_MAX_PEERS, p = t % DCT_MAX_PEERS;
     const bool on = j < pub.n && p < pub.world;
-    unsigned long long* mb = on ? pub.mailbox_table[p] : nullptr;
-    const unsigned long long q = __ldcg(pub.seq) + 1ull;
+    unsigned long long* mb = on ? pub.mailbox_table[p] : nullptr;   // immutable after PeerExchange.__init__
     pdl_wait();   // the previous launch of the stream has completed and its sums are visible
+    // the counter is read AFTER the wait: the previous launch may itself be a publication (two in a row, or the deferred
+    // plus the final one), and its `*pub.seq = q` is only guaranteed visible once that grid has completed
+    const unsigned long long q = __ldcg(pub.seq) + 1ull;
     if (on) {
         const unsigned long long bits = (unsigned long long)__double_as_longlong(__ldcg(pub.src + j));
         const unsigned long long tag = (q & 0xffffffffull) << 32;

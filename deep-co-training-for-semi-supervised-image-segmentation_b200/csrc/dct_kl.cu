@@ -171,6 +171,31 @@ struct KlDivFwd {
     }
 };
 
+// its derivative (what autograd builds for loss.py:105): with r = q/p and u = r + eps,
+//   d/dp_c = -(log u) + r/u        d/dq_c = -1/u
+// IEEE divide / libdevice logf like the forward (p == 0 gives the reference's NaN / inf pattern, not a fast-math variant)
+template <bool WANT_Q>
+struct KlDivBwd {
+    static constexpr int NIN = 2, NOUT = 2;
+    static constexpr int NDICE = 0;
+    static constexpr bool GMAP = true;
+    static constexpr bool HAS_MAP = false, USES_UP = true, CHECKS_SIMPLEX = false;
+    template <int CM, class T>
+    static __device__ __forceinline__ T apply(T (&x)[2][CM], int C, T g, float eps, bool&) {
+#pragma unroll
+        for (int c = 0; c < CM; ++c)
+            if (c < C) {
+                const T pv = x[0][c], qv = x[1][c];
+                const T r = vmap([](float q, float p) { return q / p; }, qv, pv);
+                const T u = vadds(r, eps);
+                const T dp = vmap([](float rr, float uu) { return rr / uu - logf(uu); }, r, u);
+                x[0][c] = vmul(g, dp);
+                if constexpr (WANT_Q) x[1][c] = vmul(g, vmap([](float uu, float) { return -1.0f / uu; }, u, u));
+            }
+        return vset<T>(0.0f);
+    }
+};
+
 // Entropy_2D / Entropy forward -- loss.py:53-84
 struct EntropyFwd {
     static constexpr int NIN = 1, NOUT = 0;
@@ -358,6 +383,15 @@ extern "C" int dct_kl_div_fwd_f32(const float* p, const float* q, int C, int64_t
                                   double* sum, int32_t* flags, void* workspace, void* stream) {
     PixArgs a = make_args(p, q, nullptr, nullptr, C, HW, map, sum, Upstream{nullptr, nullptr, 1.0f}, eps, flags, workspace);
     return pix_launch<KlDivFwd>(a, B, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dct_kl_div_bwd_f32(const float* p, const float* q, int C, int64_t B, int64_t HW, float eps,
+                                  const float* gmap, const float* gscalar, float gconst, float* grad_p, float* grad_q,
+                                  void* stream) {
+    if (grad_p == nullptr) return DCT_ERR_BAD_ARG;
+    PixArgs a = make_args(p, q, grad_p, grad_q, C, HW, nullptr, nullptr, Upstream{gmap, gscalar, gconst}, eps, nullptr, nullptr);
+    if (grad_q != nullptr) return pix_launch<KlDivBwd<true>>(a, B, static_cast<cudaStream_t>(stream));
+    return pix_launch<KlDivBwd<false>>(a, B, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int dct_entropy_fwd_f32(const float* p, int C, int64_t B, int64_t HW, float* map, double* sum,

@@ -140,18 +140,31 @@ class PeerExchange:
         """Publications this rank has made so far (host sync)."""
         return int(self.seq.item())
 
-    def read(self, seq: int, check: bool = True) -> torch.Tensor:
-        """Global sums ``[n]`` float64 (device) of publication number ``seq``: the rows of all ranks added in rank
-        order.  ``check`` (one host sync) verifies that every row of the slot carries ``seq``."""
+    def read(self, seq: int, check: bool = True, wait_s: float = 0.0) -> torch.Tensor:
+        """Global sums ``[n]`` float64 (device) of publication number ``seq`` (1-based, < 2**32: the tag is the low 32
+        bits and 0 is the freshly zeroed mailbox): the rows of all ranks added in rank order.
+
+        The slot is copied ONCE and both the tags and the values are taken from that copy, so a peer's store landing
+        in between cannot produce a validated-but-torn total.  ``check`` (one host sync per poll) verifies that every
+        word of the copy carries ``seq``; peers' rows arrive asynchronously, so with ``wait_s > 0`` the copy is
+        re-taken until they all have or the time is up (then, as with ``wait_s == 0``: RuntimeError)."""
+        import time
+        assert 1 <= seq < (1 << 32), "publication numbers are 1-based and the tag holds 32 bits"
         R = self._lib.PUB_ROW_WORDS
         slot = seq % self.nslots
-        rows = self._mail[slot * self.world * R:(slot + 1) * self.world * R].view(self.world, R)[:, :2 * self.n]
-        tags = (rows >> 32) & 0xffffffff
-        if check:
-            bad = int((tags != (seq & 0xffffffff)).sum().item())
-            if bad:
+        view = self._mail[slot * self.world * R:(slot + 1) * self.world * R].view(self.world, R)[:, :2 * self.n]
+        deadline = time.monotonic() + max(float(wait_s), 0.0)
+        while True:
+            rows = view.clone()                                   # one snapshot: validated and decoded below
+            if not check:
+                break
+            bad = int((((rows >> 32) & 0xffffffff) != seq).sum().item())
+            if bad == 0:
+                break
+            if time.monotonic() >= deadline:
                 raise RuntimeError(f"PeerExchange.read({seq}): {bad} word(s) of slot {slot} carry another sequence number "
                                    "(publication not arrived yet, or overwritten: ring of %d slots)" % self.nslots)
+            time.sleep(50e-6)
         lo = rows & 0xffffffff
         bits = lo[:, 0::2] | (lo[:, 1::2] << 32)
         vals = bits.contiguous().view(torch.float64)          # [world, n]

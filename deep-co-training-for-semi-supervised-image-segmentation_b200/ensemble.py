@@ -145,6 +145,14 @@ class KappaMetrics(Metric):
         return {f'kappa{i}': self.value()[i].item() for i in range(len(self.value()))}
 
 
+class KappaMetrics2(KappaMetrics):
+    """The ``metrics2`` flavour (generalframework/metrics2/kappa.py:31-32): ``value()`` is the plain mean over the
+    log (a NaN kappa -- an empty or single-class mask -- propagates instead of being skipped by ``nanmean``)."""
+
+    def value(self):
+        return torch.Tensor(self.kappa).mean(0)
+
+
 class Kappa2Annotator(KappaMetrics):
     """Drop-in for ``Kappa2Annotator`` (metrics/kappa.py:41-61): agreement of two predictions over the pixels
     whose ground truth is in ``considered_classes``."""

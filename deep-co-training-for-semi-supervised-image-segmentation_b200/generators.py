@@ -115,10 +115,15 @@ class VATGenerator(object):
     def kl_div_with_logit(q_logit, p_logit, *unused):
         return _kl_div_with_logit(q_logit, p_logit)
 
-    def __call__(self, img: Tensor, loss_name='kl') -> Tuple[Tensor, Tensor]:
+    def __call__(self, img: Tensor, loss_name='kl', d: Tensor = None) -> Tuple[Tensor, Tensor]:
+        """``d``: optional start direction replacing the N(0,1) draw of AEGenerator.py:97 (seeded parity tests; the
+        tensor is consumed -- normalised in place like the reference's own ``d``)."""
         with torch.no_grad():
             pred = self.net(img)
-        d = torch.randn(img.shape, dtype=torch.float32, device=img.device)
+        if d is None:
+            d = torch.randn(img.shape, dtype=torch.float32, device=img.device)
+        else:
+            assert d.shape == img.shape and d.device == img.device and d.dtype == torch.float32
         self.net.zero_grad()
         for it in range(self.ip):
             # first iteration: d = _l2_normalize(d) (:98) and xi * _l2_normalize(d) (:103) in one launch

@@ -10,6 +10,9 @@ their existing call sites:
   KL_Divergence_2D(reduce=True)(adv, real) -> trainer-module globals           (cotraining_totalloss.py:13,392)
   VATGenerator / FSGMGenerator             -> trainer-module globals           (cotraining_totalloss.py:15)
   DiceMeter / IoU / KappaMetrics           -> metrics package + trainer globals (cotraining_totalloss.py:18)
+  metrics2.DiceMeter / metrics2.KappaMetrics -> their own twins (metrics.DiceMeter2, ensemble.KappaMetrics2): the
+                                              fork used by trainer/mean_teacher_trainer.py:18 reports differently
+                                              (metrics2/dice_meter.py:43,82-84; metrics2/kappa.py:31-32)
   dice_coef / dice_batch / class2one_hot / probs2one_hot / pred2class / ... (the star-imported helpers of
   utils/utils.py:73-235)                   -> trainer-module globals ONLY      (trainer/trainer.py:171-175,222-227)
 The helper functions are rebound only inside ``<package>.trainer.*``: the dataset code calls ``class2one_hot`` on
@@ -29,9 +32,12 @@ _REBIND = {
     "DiceMeter": metrics.DiceMeter, "IoU": metrics.IoU, "ConfusionMatrix": metrics.ConfusionMatrix,
     "KappaMetrics": ensemble.KappaMetrics, "Kappa2Annotator": ensemble.Kappa2Annotator,
 }
+# classes DEFINED under <package>.metrics2 keep that fork's host-side semantics (same kernels underneath)
+_REBIND_METRICS2 = {"DiceMeter": metrics.DiceMeter2, "KappaMetrics": ensemble.KappaMetrics2}
 _REBIND_TRAINER_FUNCS = {name: getattr(utils, name) for name in (
     "simplex", "one_hot", "uniq", "sset", "intersection", "union", "pred2class", "probs2class", "class2one_hot",
     "probs2one_hot", "predlogit2one_hot", "meta_dice", "dice_coef", "dice_batch")}
+_OURS = set(_REBIND.values()) | set(_REBIND_METRICS2.values())
 _saved = []
 
 
@@ -40,6 +46,7 @@ def install(package: str = "generalframework") -> int:
     try:
         importlib.import_module(package + ".loss")
         importlib.import_module(package + ".metrics")
+        importlib.import_module(package + ".metrics2")
     except Exception:
         pass
     n = 0
@@ -48,7 +55,11 @@ def install(package: str = "generalframework") -> int:
             continue
         for name, repl in _REBIND.items():
             cur = mod.__dict__.get(name)
-            if cur is not None and cur is not repl and isinstance(cur, type):
+            if not isinstance(cur, type) or cur in _OURS:   # absent, not a class, or already ours (install() twice)
+                continue
+            if ".metrics2." in (getattr(cur, "__module__", "") or "") + ".":
+                repl = _REBIND_METRICS2.get(name, repl)   # dispatch on where the class was defined, not on its name
+            if cur is not repl:
                 _saved.append((mod, name, cur))
                 setattr(mod, name, repl)
                 n += 1

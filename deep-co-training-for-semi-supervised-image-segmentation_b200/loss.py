@@ -455,8 +455,50 @@ class KL_Divergence_2D_Logit(nn.Module):
         return _KLLogitFn.apply(y_logit, p_logit, bool(self.reduce))
 
 
+class _KLDivFn(torch.autograd.Function):
+    """KL_div's map / mean and, like the reference's autograd graph, its gradients w.r.t. both arguments."""
+
+    @staticmethod
+    def forward(ctx, p, q, reduce: bool, eps: float):
+        p = _prep(p, "KL_div"); q = _prep(q, "KL_div")
+        assert p.shape == q.shape
+        b, c, hw = _bchw(p)
+        dev = p.device
+        st = _runtime.state(dev)
+        out_map = None if reduce else torch.empty((b,) + tuple(p.shape[2:]), dtype=torch.float32, device=dev)
+        total = torch.empty(1, dtype=torch.float64, device=dev) if reduce else None
+        _lib.check(_lib.lib().dct_kl_div_fwd_f32(p.data_ptr(), q.data_ptr(), c, b, hw, float(eps), _ptr(out_map),
+                                                 _ptr(total), _runtime.flags_ptr(st), st.workspace.data_ptr(),
+                                                 _runtime.stream_ptr(dev)), "dct_kl_div_fwd_f32")
+        _runtime.after_call(st)
+        ctx.save_for_backward(p, q)
+        ctx.reduce, ctx.eps, ctx.n = reduce, float(eps), b * hw
+        if reduce:
+            return (total / float(b * hw)).to(torch.float32).reshape(())
+        return out_map
+
+    @staticmethod
+    def backward(ctx, g):
+        p, q = ctx.saved_tensors
+        b, c, hw = _bchw(p)
+        if not (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
+            return None, None, None, None
+        g = g.contiguous().to(torch.float32)
+        gp = torch.empty_like(p)
+        gq = torch.empty_like(q) if ctx.needs_input_grad[1] else None
+        if ctx.reduce:
+            gmap, gscalar, gconst = None, g, 1.0 / ctx.n
+        else:
+            gmap, gscalar, gconst = g, None, 1.0
+        _lib.check(_lib.lib().dct_kl_div_bwd_f32(p.data_ptr(), q.data_ptr(), c, b, hw, ctx.eps, _ptr(gmap), _ptr(gscalar),
+                                                 gconst, gp.data_ptr(), _ptr(gq), _runtime.stream_ptr(p.device)),
+                   "dct_kl_div_bwd_f32")
+        return (gp if ctx.needs_input_grad[0] else None), gq, None, None
+
+
 class KL_div(nn.Module):
-    """Drop-in for ``KL_div`` (loss.py:87-107), forward only (no trainer differentiates it)."""
+    """Drop-in for ``KL_div`` (loss.py:87-107): ``sum_c -p log(q/p + eps)``, map or mean (``reduce`` is the ctor's, the
+    call-time argument is ignored exactly as the reference ignores it), differentiable w.r.t. ``p`` and ``q``."""
 
     def __init__(self, reduce=True, eps=1e-10):
         super().__init__()
@@ -464,19 +506,7 @@ class KL_div(nn.Module):
         self.reduce = reduce
 
     def forward(self, p, q, reduce=False):
-        p = _prep(p, "KL_div"); q = _prep(q, "KL_div")
-        assert p.shape == q.shape
-        b, c, hw = _bchw(p)
-        st = _runtime.state(p.device)
-        out = torch.empty((b,) + tuple(p.shape[2:]), dtype=torch.float32, device=p.device)
-        total = torch.empty(1, dtype=torch.float64, device=p.device)
-        _lib.check(_lib.lib().dct_kl_div_fwd_f32(p.data_ptr(), q.data_ptr(), c, b, hw, float(self.eps), out.data_ptr(),
-                                                 total.data_ptr(), _runtime.flags_ptr(st), st.workspace.data_ptr(),
-                                                 _runtime.stream_ptr(p.device)), "dct_kl_div_fwd_f32")
-        _runtime.after_call(st)
-        if self.reduce:
-            return (total / float(b * hw)).to(torch.float32).reshape(())
-        return out
+        return _KLDivFn.apply(p, q, bool(self.reduce), self.eps)
 
 
 class _KLFromLogitsFn(torch.autograd.Function):
@@ -633,9 +663,11 @@ class _CEFn(torch.autograd.Function):
         if reduction == "mean":
             if n_global is not None:
                 gconst = 1.0 / float(n_global)
-            elif w is None and dice_counts is not None and confusion is None:
+            elif w is None and dice_counts is not None and confusion is None and _runtime.get_check_mode() != "off":
                 # the fused meter asserts every label in [0,C) (class2one_hot, utils/utils.py:190; raised through
-                # the label flag), so no pixel is ignored and W is the pixel count: no histogram pass
+                # the label flag in 'eager' / 'deferred' mode), so no pixel is ignored and W is the pixel count: no
+                # histogram pass.  In mode 'off' nothing would ever report an ignored / bad label, and NLLLoss' mean
+                # is sum / #kept: the histogram branch below counts the kept pixels instead.
                 gconst = 1.0 / float(b * hw)
             else:
                 inv64 = 1.0 / _ce_weight_sum(lab, c, ignore_index, w, st, dev)
@@ -729,7 +761,9 @@ def supervised_from_logits(logits: torch.Tensor, gt: torch.Tensor, weight: Optio
     (upstream 1/W folded in) and, if ``dice_counts`` (int64 ``[B,C,3]``, accumulated into) is given,
     the (I, G, P) counts of ``argmax softmax(logits)`` against ``gt`` (feed them to
     ``DiceMeter.add_counts``).  ``n_global``: pixel count over all data-parallel ranks for the
-    unweighted global mean (defaults to the local denominator).
+    unweighted global mean (defaults to the local denominator) -- valid ONLY without class weights and without
+    ignored pixels (it replaces NLLLoss' data-dependent denominator ``sum_i w[t_i]`` by a constant); with either,
+    leave it None and all-reduce the per-rank losses weighted by their kept weight instead.
 
     ``confusion`` (int64 ``[C,C]``, accumulated into; instead of ``dice_counts``): the Cityscapes trainers keep an
     ``IoU`` meter on the same line pair (cotraining_city.py:236-241: ``metrics[k].add(predicted=pred, target=gt)``);

@@ -134,6 +134,22 @@ class DiceMeter(Metric):
         return {f'mDSC': means.item(), 'mVars': var.item()}
 
 
+class DiceMeter2(DiceMeter):
+    """Drop-in for the ``metrics2`` flavour of ``DiceMeter`` (generalframework/metrics2/dice_meter.py:36-84; user:
+    trainer/mean_teacher_trainer.py:18).  Same ``add`` (same counting kernel); the host side differs in two places:
+    ``report_axises='all'`` becomes ``list(range(C))`` (:43) and ``summary()`` reports one ``DSC{i}`` per report axis
+    (:82-84) instead of ``mDSC`` / ``mVars``."""
+
+    def __init__(self, method='2d', report_axises='all', C=4) -> None:
+        super().__init__(method=method, report_axises=report_axises, C=C)
+        if isinstance(report_axises, str) and report_axises == 'all':
+            self.report_axis = list(range(C))
+
+    def summary(self) -> dict:
+        _, (means, _) = self.value()
+        return {f'DSC{i}': means[i].item() for i in self.report_axis}
+
+
 class ConfusionMatrix(Metric):
     """Drop-in for ``ConfusionMatrix`` (metrics/confusionmatrix.py:7-98).
 

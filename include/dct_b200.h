@@ -199,9 +199,13 @@ DCT_API int dct_entropy_fwd_f32(const float* p, int C, int64_t B, int64_t HW, fl
 DCT_API int dct_entropy_bwd_f32(const float* p, int C, int64_t B, int64_t HW, const float* gmap,
                                 const float* gscalar, float gconst, float* grad_p, void* stream);
 
-/* KL_div.forward (loss.py:87-107): out = sum_c -p*log(q/p + eps) (forward only; unused by the trainers) */
+/* KL_div.forward (loss.py:87-107): out = sum_c -p*log(q/p + eps) (unused by the trainers; differentiable like the
+ * reference's autograd graph: with r = q/p, u = r + eps: grad_p = up * (r/u - log u), grad_q = up * (-1/u); grad_q nullable) */
 DCT_API int dct_kl_div_fwd_f32(const float* p, const float* q, int C, int64_t B, int64_t HW, float eps,
                        float* map, double* sum, int32_t* flags, void* workspace, void* stream);
+DCT_API int dct_kl_div_bwd_f32(const float* p, const float* q, int C, int64_t B, int64_t HW, float eps,
+                       const float* gmap, const float* gscalar, float gconst, float* grad_p, float* grad_q,
+                       void* stream);
 
 /* F.softmax(x, 1) forward (segmentators.py:50) and its backward gx = p*(gp - sum_c p*gp) */
 DCT_API int dct_softmax_fwd_f32(const float* x, int C, int64_t B, int64_t HW, float* p, void* stream);

@@ -120,6 +120,13 @@ def entropy(p):
     return out
 
 
+def entropy_bwd(p, gout):
+    dt = _dt(p); p = _c(p, dt); gout = _c(gout, dt); b, c, hw = _bchw(p)
+    gp = np.empty_like(p)
+    getattr(lib(), "dcto_entropy_bwd" + _suf(dt))(_ptr(p), _ptr(gout), _ptr(gp), _i64(b), _int(c), _i64(hw))
+    return gp
+
+
 def jsd_fwd(probs):
     dt = _dt(probs[0]); ps = [_c(p, dt) for p in probs]; b, c, hw = _bchw(ps[0])
     out = np.empty((b,) + ps[0].shape[2:], dtype=dt)
@@ -185,6 +192,15 @@ def kl_div_fwd(p, q, eps=1e-10):
     out = np.empty((b,) + p.shape[2:], dtype=dt)
     getattr(lib(), "dcto_kl_div_fwd" + _suf(dt))(_ptr(p), _ptr(q), _i64(b), _int(c), _i64(hw), _real(dt, eps), _ptr(out))
     return out
+
+
+def kl_div_bwd(p, q, gout, eps=1e-10):
+    """Gradients of KL_div's map w.r.t. p and q under the upstream map ``gout``."""
+    dt = _dt(p); p = _c(p, dt); q = _c(q, dt); gout = _c(gout, dt); b, c, hw = _bchw(p)
+    gp = np.empty_like(p); gq = np.empty_like(p)
+    getattr(lib(), "dcto_kl_div_bwd" + _suf(dt))(_ptr(p), _ptr(q), _i64(b), _int(c), _i64(hw), _real(dt, eps),
+                                                _ptr(gout), _ptr(gp), _ptr(gq))
+    return gp, gq
 
 
 def l2_normalize(d):

@@ -12,6 +12,10 @@ Why each stub is needed (reference file:line):
   generalframework/utils/visualize.py:2,4,6,9 (tensorboardX, visdom, matplotlib, skimage)
   generalframework/trainer/cotraining_totalloss.py:6 (tensorboardX)
   generalframework/utils/utils.py:318,342 + dataset/augment.py:141 (collections.Mapping...)
+  generalframework/trainer/mean_teacher_trainer.py:10 (easydict; only when the package is absent)
+
+Where the reference is looked for: $DCT_REFERENCE_ROOT, else /root/reference (the build container), else
+<repo>/baseline/_ref (a staged copy that travels to the GPU box; tools/stage_reference.sh).
 """
 import collections
 import collections.abc
@@ -19,7 +23,18 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("DCT_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root() -> str:
+    cands = [os.environ.get("DCT_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "generalframework")):
+            return c
+    return cands[0] or "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available() -> bool:
@@ -31,6 +46,26 @@ def _stub(name, **attrs):
     m.__dict__.update(attrs)
     sys.modules.setdefault(name, m)
     return sys.modules[name]
+
+
+class _EasyDict(dict):
+    """Stand-in for easydict.EasyDict (attribute access to dict keys, nested dicts converted)."""
+
+    def __init__(self, d=None, **kw):
+        super().__init__()
+        for k, v in dict(d or {}, **kw).items():
+            self[k] = v
+
+    def __setitem__(self, k, v):
+        super().__setitem__(k, _EasyDict(v) if isinstance(v, dict) and not isinstance(v, _EasyDict) else v)
+
+    __setattr__ = __setitem__
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
 
 
 class _SummaryWriter:
@@ -51,6 +86,10 @@ def install():
     sk.data = None
     _stub("tensorboardX", SummaryWriter=_SummaryWriter)
     _stub("visdom", Visdom=object)
+    try:
+        import easydict  # noqa: F401
+    except ImportError:
+        _stub("easydict", EasyDict=_EasyDict)
     mpl = _stub("matplotlib")
     mpl.pyplot = _stub("matplotlib.pyplot")
     for n in ("Mapping", "MutableMapping", "Iterable"):

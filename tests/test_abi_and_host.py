@@ -142,3 +142,44 @@ def test_install_rebinds_reference_call_sites():
     finally:
         dct_b200.uninstall()
     assert gl.LOSS["jsd"] is orig and ct.DiceMeter is not dct_b200.DiceMeter
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/generalframework"), reason="reference tree not mounted")
+def test_install_keeps_the_metrics2_flavour():
+    """generalframework.metrics2.DiceMeter (user: trainer/mean_teacher_trainer.py:18) differs from metrics.DiceMeter on the
+    host side (metrics2/dice_meter.py:43,82-84); install() must hand each module its own flavour and uninstall() must
+    restore both (round-1 defect: both were replaced by the metrics/ flavour)."""
+    import ref_shim
+    ref_shim.install()
+    import generalframework.metrics as gm
+    import generalframework.metrics2 as gm2
+    import generalframework.metrics2.dice_meter as gm2d
+    import generalframework.trainer.mean_teacher_trainer as mt
+    import dct_b200
+    ref1, ref2, refk2 = gm.DiceMeter, gm2.DiceMeter, gm2.KappaMetrics
+    assert ref1 is not ref2
+    want1 = ref1(method="2d", C=4)
+    want2 = ref2(method="2d", C=4)
+    log = torch.tensor([[1.0, 0.5, 0.25, 0.75], [1.0, 0.0, 0.5, 0.25]])
+    want1.diceLog.append(log); want2.diceLog.append(log)
+    dct_b200.install()
+    try:
+        dct_b200.install()   # idempotent: a second call must not re-dispatch our own classes
+        assert gm.DiceMeter is dct_b200.DiceMeter and gm2.DiceMeter is dct_b200.DiceMeter2
+        assert gm2d.DiceMeter is dct_b200.DiceMeter2 and mt.DiceMeter is dct_b200.DiceMeter2
+        assert gm2.KappaMetrics is dct_b200.KappaMetrics2 and gm.KappaMetrics is dct_b200.KappaMetrics
+        a, b = gm.DiceMeter(method="2d", C=4), gm2.DiceMeter(method="2d", C=4)
+        assert a.report_axis == want1.report_axis == "all" and b.report_axis == want2.report_axis == [0, 1, 2, 3]
+        a.diceLog.append(log); b.diceLog.append(log)
+        assert a.summary() == want1.summary() and set(a.summary()) == {"mDSC", "mVars"}
+        assert b.summary() == want2.summary() and set(b.summary()) == {"DSC0", "DSC1", "DSC2", "DSC3"}
+        assert b.detailed_summary() == want2.detailed_summary()
+        c = gm2.DiceMeter(method="3d", C=4, report_axises=[1, 3])
+        c.diceLog.append(log)
+        w = ref2(method="3d", C=4, report_axises=[1, 3]); w.diceLog.append(log)
+        assert c.summary() == w.summary() and set(c.summary()) == {"DSC1", "DSC3"}
+        (rm, rs), _ = c.value(); (wm, ws), _ = w.value()
+        assert rm.item() == wm.item() and rs.item() == ws.item()
+    finally:
+        dct_b200.uninstall()
+    assert gm.DiceMeter is ref1 and gm2.DiceMeter is ref2 and gm2.KappaMetrics is refk2 and mt.DiceMeter is ref2
