@@ -326,30 +326,37 @@ def run_ours(args, wl):
     # launch duration over a timed region of back-to-back launches on the launching stream, CUDA events on that
     # stream, rotating over the R buffer sets (R x inputs+grads >> the 126 MB L2, so no launch finds its inputs cached)
     fused_dice = with_dice and C <= 4 and K * C <= 16
-    jsd_only = ConsistencyStep(K, C, B, H, W, cin=cin, n_global=n_local * world, with_vat=False, with_dice=fused_dice)
     side = torch.cuda.Stream(device=dev)
-    side.wait_stream(torch.cuda.current_stream(dev))
-    with torch.cuda.stream(side):
-        for i in range(2 * R):
-            jsd_only.run(sets[i % R], zero_counts=False)
-    torch.cuda.current_stream(dev).wait_stream(side)
-    torch.cuda.synchronize()
-    kgraph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(kgraph, stream=side):
-        for j in range(R):
-            jsd_only.run(sets[j], zero_counts=False)
+
+    def time_part(part, reps):
+        """Average duration of ONE launch sequence of `part` (a graph of R back-to-back runs rotating over the buffer
+        sets, replayed `reps` times), CUDA events on the launching stream."""
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for i in range(2 * R):
+                step.run_part(sets[i % R], part)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            for j in range(R):
+                step.run_part(sets[j], part)
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(reps):
+            g.replay()
+        t1.record()
+        torch.cuda.synchronize()
+        return t0.elapsed_time(t1) / (reps * R)
+
     rounds = max(3, min(args.steps, 400) // R)
-    for _ in range(3):
-        kgraph.replay()
-    torch.cuda.synchronize()
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0.record()
-    for _ in range(rounds):
-        kgraph.replay()
-    k1.record()
-    torch.cuda.synchronize()
-    k_ms = k0.elapsed_time(k1) / (rounds * R)
-    alg = jsd_only.algorithmic_bytes()["jsd_fwdbwd"]
+    part_ms = {p: time_part(p, rounds) for p in step.parts()}
+    k_ms = part_ms["jsd"]
+    jsd_only = step
+    alg = jsd_only.part_bytes()["jsd"]
     peak, peak_src = load_peaks()
     achieved = alg / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "tile_kernel<JsdOp<K,logits,fwd+bwd,%s>> via dct_jsd_fwdbwd_f32 "
@@ -361,6 +368,10 @@ def run_ours(args, wl):
                 "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms,
                 "traffic": (load_traffic(args.workload) or {}).get("bytes"), "traffic_detail": load_traffic(args.workload),
                 "step_algorithmic_bytes": step.algorithmic_bytes(),
+                # every launch of the step timed on its own the same way (back to back with itself, cold inputs)
+                "step_kernels": [{"part": p, "us": part_ms[p] * 1e3, "algorithmic_bytes": step.part_bytes()[p],
+                                  "GBps": step.part_bytes()[p] / (part_ms[p] * 1e-3) / 1e9,
+                                  "frac": step.part_bytes()[p] / (part_ms[p] * 1e-3) / 1e9 / peak} for p in step.parts()],
                 "step_achieved_GBps": sum(step.algorithmic_bytes().values()) / (ms_total * 1e-3 / args.steps) / 1e9}
 
     # ---- e2e: host buffers in pinned memory -> H2D -> the public autograd API -> D2H of losses + Dice rows
@@ -429,9 +440,10 @@ def run_e2e(args, dct, step, dev_set, dev, world, n_local, K, C, B, H, W, with_v
         t = slots[j]
         logits = [x.requires_grad_() for x in t[:K]]
         labels, d, d_grad, img, yhat, adv, real = t[K:K + 7]
-        counts = torch.zeros(K, B, C, 3, dtype=torch.int64, device=dev)
+        counts = torch.empty(K, B, C, 3, dtype=torch.int64, device=dev)
         if with_dice:
-            loss = dct.jsd_consistency_from_logits(logits, weight=1.0, labels=labels, dice_counts=counts, n_global=n_glob)
+            loss = dct.jsd_consistency_from_logits(logits, weight=1.0, labels=labels, dice_counts=counts, n_global=n_glob,
+                                                   accumulate=False)
         else:
             loss = dct.jsd_consistency_from_logits(logits, weight=1.0, n_global=n_glob)
         total = loss

@@ -16,6 +16,8 @@ _CSRC = os.path.join(_PKG, "csrc")
 OK = 0
 ERR_UNSUPPORTED = -2
 IN_PROBS, IN_LOGITS = 0, 1
+COUNTS_ACCUMULATE, COUNTS_OVERWRITE = 0, 1
+ABI_VERSION = 2
 FLAG_SIMPLEX, FLAG_LABEL, FLAG_PRED, FLAG_ONEHOT, NUM_FLAGS = 0, 1, 2, 3, 4
 MAX_VIEWS, MAX_CLASSES = 8, 64
 MAX_PEERS, PUB_ROW_WORDS, PUB_MAX_VALUES, IPC_HANDLE_BYTES = 8, 16, 8, 64
@@ -38,7 +40,7 @@ _SIGNATURES = {
     "dct_workspace_bytes": [],
     "dct_jsd_fwd_f32": [_p, _i, _i, _i64, _i64, _i, _p, _p, _p, _p, _p],
     "dct_jsd_bwd_f32": [_p, _i, _i, _i64, _i64, _i, _p, _p, _f, _p, _p],
-    "dct_jsd_fwdbwd_f32": [_p, _i, _i, _i64, _i64, _i, _f, _p, _p, _p, _p, _p, _p, _p, _p],
+    "dct_jsd_fwdbwd_f32": [_p, _i, _i, _i64, _i64, _i, _f, _p, _p, _p, _p, _p, _i, _p, _p, _p],
     "dct_scale_if_not_one_f32": [_p, _i64, _p, _p],
     "dct_kl_fwd_f32": [_p, _p, _i, _i64, _i64, _f, _p, _p, _p, _p, _p],
     "dct_kl_bwd_f32": [_p, _p, _i, _i64, _i64, _f, _p, _p, _f, _p, _p, _p],
@@ -65,10 +67,12 @@ _SIGNATURES = {
     "dct_onehot_from_labels_i64": [_p, _i, _i64, _i64, _p, _p, _p],
     "dct_onehot_dice_counts_i32": [_p, _p, _i, _i64, _i64, _p, _p, _p],
     "dct_vote_f32": [_p, _i, _i, _i64, _i64, _i, _p, _p, _p, _p],
-    "dct_jsd_fwdbwd_bf16": [_p, _i, _i, _i64, _i64, _f, _p, _p, _p, _p, _p, _p, _p, _p],
+    "dct_jsd_fwdbwd_bf16": [_p, _i, _i, _i64, _i64, _f, _p, _p, _p, _p, _p, _i, _p, _p, _p],
     "dct_kl_logit_bf16": [_p, _p, _i, _i64, _i64, _p, _p, _i, _p, _p, _f, _p, _p, _p, _p],
     "dct_kl_from_logits_fwdbwd_bf16": [_p, _p, _i, _i64, _i64, _f, _f, _p, _p, _p, _p, _p, _p],
     "dct_ce_fwdbwd_bf16": [_p, _p, _i, _i64, _i64, _p, _i64, _p, _f, _p, _p, _p, _p, _p, _p, _p],
+    "dct_dev_trace_begin": [_p, _i, _i],
+    "dct_dev_trace_end": [],
     "dct_peer_pub_bytes": [],
     "dct_mailbox_create": [C.c_size_t, _p, _p],
     "dct_mailbox_open": [_p, _p],
@@ -117,7 +121,7 @@ def lib():
                     fn = getattr(h, name)  # AttributeError == ABI mismatch: fail loudly
                     fn.argtypes = argtypes
                     fn.restype = _RESTYPES.get(name, C.c_int)
-                if h.dct_abi_version() != 1:
+                if h.dct_abi_version() != ABI_VERSION:
                     raise ImportError("libdct_b200.so ABI version mismatch; rebuild with build(force=True)")
                 _lib = h
     return _lib

@@ -186,8 +186,8 @@ class CoTrainStep:
             if cfg.meter == "iou":   # no meters on the unlabeled branch (cotraining_city.py:250-257)
                 jsd = jsd_consistency_from_logits(ulogits, weight=1.0)
             else:
-                ucounts = torch.zeros(self.K, uimg.shape[0], C, 3, dtype=torch.int64, device=dev)
-                jsd = jsd_consistency_from_logits(ulogits, weight=1.0, labels=ugt, dice_counts=ucounts)
+                ucounts = torch.empty(self.K, uimg.shape[0], C, 3, dtype=torch.int64, device=dev)
+                jsd = jsd_consistency_from_logits(ulogits, weight=1.0, labels=ugt, dice_counts=ucounts, accumulate=False)
                 for k in range(self.K):
                     self.report.add_counts("unlab", k, ucounts[k])
             total = total + cfg.cot_weight * jsd

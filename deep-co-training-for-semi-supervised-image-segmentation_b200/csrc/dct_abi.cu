@@ -12,9 +12,28 @@ bool pdl_enabled() {
     }();
     return on;
 }
+
+static unsigned long long* g_trace_buf = nullptr;
+static int g_trace_max_ctas = 0, g_trace_max_launches = 0, g_trace_launch = 0;
+unsigned long long* trace_next(int grid) {
+    if (g_trace_buf == nullptr || grid > g_trace_max_ctas || g_trace_launch >= g_trace_max_launches) return nullptr;
+    return g_trace_buf + (size_t)(g_trace_launch++) * g_trace_max_ctas * kTraceSlots;
+}
 }  // namespace dct
 
 using namespace dct;
+
+extern "C" int dct_dev_trace_begin(void* buf, int max_ctas, int max_launches) {
+    if (buf == nullptr || max_ctas < 1 || max_launches < 1) return DCT_ERR_BAD_ARG;
+    g_trace_buf = static_cast<unsigned long long*>(buf);
+    g_trace_max_ctas = max_ctas; g_trace_max_launches = max_launches; g_trace_launch = 0;
+    return DCT_OK;
+}
+extern "C" int dct_dev_trace_end(void) {
+    const int n = g_trace_launch;
+    g_trace_buf = nullptr; g_trace_launch = 0;
+    return n;
+}
 
 extern "C" int dct_abi_version(void) { return DCT_ABI_VERSION; }
 

@@ -30,13 +30,22 @@ struct Workspace {
     unsigned int ticket;         // CTAs that have finished
     unsigned int tile_counter;   // dynamic tile scheduler of the tile pipeline (dct_tile.cuh)
     unsigned int nonfinite;      // #CTAs that saw a NaN / inf / out-of-range per-thread partial sum
-    unsigned int pad0;
+    unsigned int counts_zeroed;  // DCT_COUNTS_OVERWRITE: set (release) by CTA 0 once the launch's counters are cleared
     unsigned long long fx_lo;    // order-independent loss sum in 2^-40 fixed point: sum of the low 32 bits ...
     long long fx_hi;             // ... and of the (signed) high bits of every partial
     unsigned int pad[8];
     double partials[kMaxPartials];
+    // per-sample exchange of the one-launch perturbation normalisation (dct_vat.cu, l2_ll_kernel): a launch counter that
+    // gives every launch fresh tags, its ticket, and kL2LLSamples x 2 passes x kL2LLSlots self-validating 8-byte words
+    // {32-bit tag | fp32 partial sum of squares}.  Zero between allocations; only that kernel writes here.
+    unsigned int l2_epoch;
+    unsigned int l2_ticket;
+    unsigned int pad2[14];
+    unsigned long long l2_slots[256 * 2 * 32];
 };
 static_assert(offsetof(Workspace, partials) == 64, "workspace header is 64 bytes");
+constexpr int kL2LLSamples = 256, kL2LLSlots = 32;
+static_assert(sizeof(((Workspace*)nullptr)->l2_slots) == (size_t)kL2LLSamples * 2 * kL2LLSlots * 8, "l2 exchange area");
 
 struct Upstream {          // see "dct_upstream" in include/dct_b200.h
     const float* gmap;     // [B,HW] or null
@@ -91,6 +100,12 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kern, args...);
 }
+
+// Developer tracing (dct_dev_trace_begin / _end, include/dct_b200.h): while a trace buffer is registered every launch of a
+// traced kernel gets the next kTraceSlots * max_ctas words of it and its CTAs stamp %globaltimer there:
+// [0] after griddepcontrol.wait, [1] / [2] kernel-specific mid points, [3] at the CTA's end.  Null in the product.
+constexpr int kTraceSlots = 4;
+unsigned long long* trace_next(int grid);   // dct_abi.cu; nullptr when tracing is off or the buffer is exhausted
 
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
@@ -315,6 +330,7 @@ __device__ __forceinline__ void tile_grid_finish(long long acc_fx, bool nonfinit
                 ws->nonfinite = 0u;
             }
             ws->tile_counter = 0u;
+            ws->counts_zeroed = 0u;
             __threadfence();
             ws->ticket = 0u;
         }

@@ -72,13 +72,16 @@ extern "C" int dct_jsd_bwd_f32(const float* const* views, int K, int C, int64_t 
 
 extern "C" int dct_jsd_fwdbwd_f32(const float* const* views, int K, int C, int64_t B, int64_t HW, int in_kind,
                                   float gconst, float* map, double* sum, float* const* grad_views,
-                                  const int64_t* labels, int64_t* counts, int32_t* flags, void* workspace,
-                                  void* stream) {
+                                  const int64_t* labels, int64_t* counts, int counts_mode, int32_t* flags,
+                                  void* workspace, void* stream) {
     if (labels != nullptr && counts == nullptr) return DCT_ERR_BAD_ARG;
+    if (counts_mode != DCT_COUNTS_ACCUMULATE && counts_mode != DCT_COUNTS_OVERWRITE) return DCT_ERR_BAD_ARG;
+    if (labels != nullptr && counts_mode == DCT_COUNTS_OVERWRITE && workspace == nullptr) return DCT_ERR_BAD_ARG;
     bool dice_done = false;
     JsdCall c{labels, counts, &dice_done, views, grad_views, K, C, B, HW, in_kind, kFwdBwd, map, sum,
               Upstream{nullptr, nullptr, gconst}, flags, static_cast<Workspace*>(workspace),
               static_cast<cudaStream_t>(stream)};
+    c.counts_overwrite = counts_mode == DCT_COUNTS_OVERWRITE;
     int rc = jsd_dispatch(c);
     if (rc != DCT_OK) return rc;
     if (labels != nullptr && !dice_done) {
@@ -86,7 +89,8 @@ extern "C" int dct_jsd_fwdbwd_f32(const float* const* views, int K, int C, int64
         // generalframework/trainer/cotraining_totalloss.py:224).  C <= 4 with aligned rows is fused
         // into the loss kernel itself (JsdOp<.., DICEF>); other shapes count in K extra launches.
         for (int k = 0; k < K; ++k) {
-            rc = dct_dice_counts_f32(views[k], labels, C, B, HW, counts + (int64_t)k * B * C * 3, 1, flags, stream);
+            rc = dct_dice_counts_f32(views[k], labels, C, B, HW, counts + (int64_t)k * B * C * 3,
+                                     counts_mode == DCT_COUNTS_OVERWRITE ? 0 : 1, flags, stream);
             if (rc != DCT_OK) return rc;
         }
     }
@@ -98,14 +102,17 @@ extern "C" int dct_jsd_fwdbwd_f32(const float* const* views, int K, int C, int64
 // (K*C > 80, C not in {2,3,4,19}, HW % 8 != 0, rows not 16-byte aligned): the caller converts to float32 then.
 extern "C" int dct_jsd_fwdbwd_bf16(const void* const* views, int K, int C, int64_t B, int64_t HW, float gconst,
                                    float* map, double* sum, void* const* grad_views, const int64_t* labels,
-                                   int64_t* counts, int32_t* flags, void* workspace, void* stream) {
+                                   int64_t* counts, int counts_mode, int32_t* flags, void* workspace, void* stream) {
     if (labels != nullptr && counts == nullptr) return DCT_ERR_BAD_ARG;
+    if (counts_mode != DCT_COUNTS_ACCUMULATE && counts_mode != DCT_COUNTS_OVERWRITE) return DCT_ERR_BAD_ARG;
+    if (labels != nullptr && counts_mode == DCT_COUNTS_OVERWRITE && workspace == nullptr) return DCT_ERR_BAD_ARG;
     if (labels != nullptr && (C > 4 || !aligned(labels, 16) || grad_views == nullptr)) return DCT_ERR_UNSUPPORTED;
     bool dice_done = false;
     JsdCall c{labels, counts, &dice_done, reinterpret_cast<const float* const*>(views),
               reinterpret_cast<float* const*>(grad_views), K, C, B, HW, DCT_IN_LOGITS, grad_views ? kFwdBwd : kFwd, map, sum,
               Upstream{nullptr, nullptr, gconst}, flags, static_cast<Workspace*>(workspace),
               static_cast<cudaStream_t>(stream), 1};
+    c.counts_overwrite = counts_mode == DCT_COUNTS_OVERWRITE;
     int rc = jsd_dispatch(c);
     if (rc == DCT_OK && labels != nullptr && !dice_done) return DCT_ERR_UNSUPPORTED;  // (not reachable: C <= 4 fuses)
     return rc;

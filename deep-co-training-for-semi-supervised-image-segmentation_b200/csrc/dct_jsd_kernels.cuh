@@ -456,6 +456,7 @@ struct JsdCall {
     Workspace* ws;
     cudaStream_t stream;
     int elem = 0;               // 0: float32 tensors; 1: bfloat16 tensors (views / grads point to bf16; tile pipeline only)
+    bool counts_overwrite = false;   // DCT_COUNTS_OVERWRITE: the fused launch clears `counts` itself
 };
 
 // returns DCT_ERR_UNSUPPORTED when (K,C) has no register-tiled instantiation
@@ -471,7 +472,7 @@ int jsd_launch_tile(const JsdCall& c) {
         a.out[k] = c.grads ? c.grads[k] : nullptr;
     }
     a.HW = c.HW; a.map = c.map; a.sum = c.sum; a.up = c.up; a.eps = 0.0f; a.flags = c.flags; a.ws = c.ws;
-    a.labels = nullptr; a.counts = nullptr; a.count_view_stride = c.B * C * 3;
+    a.labels = nullptr; a.counts = nullptr; a.count_view_stride = c.B * C * 3; a.counts_overwrite = c.counts_overwrite ? 1 : 0;
     const bool lg = c.in_kind == DCT_IN_LOGITS;
     if constexpr (!std::is_same<ET, float>::value) {
         // bf16 tensors: the one-pass-over-logits forms only (fused forward+backward [+ Dice], or forward for eval)

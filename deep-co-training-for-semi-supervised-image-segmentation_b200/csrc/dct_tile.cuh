@@ -123,6 +123,7 @@ struct TileArgs {
     const int64_t* labels;         // Dice: [B,HW] int64 (NDICE > 0 and non-null => count)
     unsigned long long* counts;    // Dice: [NDICE][B][C][3] (I,G,P), accumulated into
     int64_t count_view_stride;     // B*C*3
+    int counts_overwrite;          // Dice: 1 = this launch clears `counts` first (CTA 0; the others wait for ws->counts_zeroed)
     PeerPub pub;                   // *_pub launches (PUB kernels): publication descriptor of the step's sums, by value
     unsigned long long* conf;      // CONF ops: [C][C] int64 (rows = ground truth), accumulated into; null = not counted
     const float* class_w;          // LABELS ops: per-class weight [C] (device) or null = 1
@@ -131,7 +132,7 @@ struct TileArgs {
     int num_tiles;
     int pool_div;                  // developer knob: the tail pool is 1/pool_div of every CTA's range (0 = default 5)
     int force_static;              // developer switch (tools/kbench_tile.cu): 1 = no tail pool (purely static contiguous ranges) even with a workspace
-    unsigned long long* trace;     // developer tracing (tools/kbench_tile.cu): per CTA {t_start, t_end} in ns; null in the product
+    unsigned long long* trace;     // developer tracing: kTraceSlots words per CTA (start, first tile landed, -, end) in ns; null in the product
 };
 
 // does the op read the labels itself (Op::LABELS == true)?  Ops without the member do not.
@@ -262,7 +263,19 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
     }
     __syncthreads();
     pdl_wait();               // the previous grid has completed and its writes are visible (no-op without PDL)
-    if (a.trace != nullptr && tid == 0) a.trace[2 * blockIdx.x] = globaltimer_ns();
+    if (a.trace != nullptr && tid == 0) a.trace[kTraceSlots * blockIdx.x] = globaltimer_ns();
+    if constexpr (DICE) {
+        // DCT_COUNTS_OVERWRITE: the launch clears its own counters.  CTA 0 stores the zeros and releases a flag; every
+        // other CTA's producer warp acquires it before its first add (by then -- a whole run of tiles later -- it has long
+        // been set).  All CTAs of the persistent grid are co-resident and CTA 0 never waits on anybody: no deadlock.
+        if (do_dice && a.counts_overwrite && blockIdx.x == 0) {
+            const int64_t ncnt = (int64_t)Op::NDICE * a.count_view_stride;
+            for (int64_t i = tid; i < ncnt; i += (int64_t)blockDim.x) a.counts[i] = 0ull;
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&a.ws->counts_zeroed), "r"(1u) : "memory");
+        }
+    }
 
     long long acc_fx = 0;     // this thread's share of the map sum, 2^-40 fixed point
     bool nonfinite = false;
@@ -397,8 +410,19 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
         constexpr int kDiceRounds = (kDiceCounters + 31) / 32;
         unsigned int dacc[kDiceRounds > 0 ? kDiceRounds : 1] = {};
         int cur_b = -1;
+        bool counts_ready = !(DICE && do_dice && a.counts_overwrite) || blockIdx.x == 0;   // CTA 0 cleared them itself
+        auto await_counts = [&]() {   // all lanes; once per CTA, right before its first add to the global counters
+            if (!counts_ready) {
+                unsigned int z;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(z) : "l"(&a.ws->counts_zeroed) : "memory");
+                } while (z == 0u);
+                counts_ready = true;
+            }
+        };
         auto flush_dice = [&](int bb) {
             if constexpr (DICE_FOLD) {
+                await_counts();
 #pragma unroll
                 for (int rr = 0; rr < kDiceRounds; ++rr) {
                     const int r = rr * 32 + lane;
@@ -505,6 +529,7 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
             }
             if constexpr (DICE_LOCAL) {
                 if (hand_over) {   // uniform across the warp; after this iteration's copies have been issued
+                    await_counts();
 #pragma unroll
                     for (int rr = 0; rr < kDiceRounds; ++rr) {
                         const int r = rr * 32 + lane;
@@ -547,6 +572,7 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
             const int stage = i % STAGES;
             tma::mbar_wait(&full[stage], (uint32_t)(i / STAGES) & 1u);
             const int tile = s_tile[stage];
+            if (a.trace != nullptr && i == 0 && tid == 0) a.trace[kTraceSlots * blockIdx.x + 1] = globaltimer_ns();
             if (tile < 0) break;
             const int b = tile / tpi;
             const bool hand_over = DICE_LOCAL && do_dice && s_mark[stage] != 0;   // uniform across the CTA's consumers
@@ -771,7 +797,7 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
         }
     }
     tile_grid_finish<PUB>(acc_fx, nonfinite, a.ws, Op::HAS_MAP ? a.sum : nullptr, gridDim.x, &a.pub);
-    if (a.trace != nullptr && tid == 0) a.trace[2 * blockIdx.x + 1] = globaltimer_ns();
+    if (a.trace != nullptr && tid == 0) a.trace[kTraceSlots * blockIdx.x + 3] = globaltimer_ns();
 }
 
 // Host side: does this problem fit the tile pipeline?  (16-byte aligned rows and segments)
@@ -829,6 +855,7 @@ int tile_launch_ct(TileArgs a, int64_t B, cudaStream_t stream) {
     a.num_tiles = (int)(a.tiles_per_image * B);
     int grid = kSMs * MINB;
     if (grid > a.num_tiles) grid = a.num_tiles;
+    if (a.trace == nullptr) a.trace = trace_next(grid);
     cudaError_t e = launch_pdl(kern, dim3(grid), dim3(NCW * 32 + 32), Cfg::kSmemBytes, stream, a);
     if (e != cudaSuccess) { g_last_cuda_error = e; return DCT_ERR_CUDA; }
     return check_launch();

@@ -13,6 +13,8 @@
 // workspace, then rescale; the second read is served by the 126 MB L2).
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "dct_common.cuh"
 
 namespace cg = cooperative_groups;
@@ -33,6 +35,7 @@ struct L2Args {
     const float* img;  // nullable
     float* adv;        // nullable
     Workspace* ws;
+    unsigned long long* trace;   // developer tracing (dct_common.cuh, trace_next); null in the product
 };
 
 __device__ __forceinline__ float block_sum_f(float v, float* s_warp) {
@@ -75,6 +78,7 @@ l2_cluster_kernel(const L2Args a) {
     FVec<4> im[IMG ? NV : 1];
     float ss = 0.0f;
     pdl_wait();
+    if (a.trace != nullptr && threadIdx.x == 0) a.trace[kTraceSlots * blockIdx.x] = globaltimer_ns();
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
         const int64_t q = ((int64_t)j * kL2Cluster + rank) * kL2Threads + threadIdx.x;  // float4 index in sample
@@ -97,6 +101,7 @@ l2_cluster_kernel(const L2Args a) {
         for (int i = 0; i < CL / 4; ++i)   // lane l reads warp (l & 7) of CTAs (l >> 3) + 4 i, in a fixed order
             t += *cluster.map_shared_rank(&s_wsum[pass][lane & 7], 4 * i + (lane >> 3));
         t = warp_sum(t);
+        if (a.trace != nullptr && threadIdx.x == 0) a.trace[kTraceSlots * blockIdx.x + 1 + (pass == a.passes - 1 ? 1 : 0)] = globaltimer_ns();
         const float nrm = sqrtf(t) + 1e-16f;
         ss = 0.0f;
 #pragma unroll
@@ -130,6 +135,145 @@ l2_cluster_kernel(const L2Args a) {
     }
     pdl_launch_dependents();
     cluster.sync();  // no CTA may exit (and free s_wsum) while a peer can still be reading it
+    if (a.trace != nullptr && threadIdx.x == 0) a.trace[kTraceSlots * blockIdx.x + 3] = globaltimer_ns();
+}
+
+// ---- one launch without a cluster: co-resident CTAs, per-sample exchange through self-validating words in L2 ----------------
+// The cluster kernel above spends 35 % of its duration with no SM active (cluster launch / drain, profiles/r18).  Here a
+// sample is spread over `cps` ordinary CTAs of one co-resident grid.  Per normalisation pass every CTA reduces its slice's
+// sum of squares (shuffle tree -> one shared-memory word per warp -> warp 0) and stores it as ONE aligned 8-byte word
+// {tag | fp32 bits} into its slot of the sample's row in the workspace; lanes 0..cps-1 of warp 0 then poll the sample's cps
+// slots until each carries this launch's tag.  An aligned 8-byte store is single-copy atomic, so a matching tag implies the
+// data (the scheme of the mailbox exchange, dct_common.cuh): no fence, no atomic, no flag round trip on the critical path.
+// All CTAs add the cps partials with the same shuffle tree, so the whole sample sees one bit-identical norm.
+// Tags: (launch epoch + 1) * 2 + pass; the epoch lives in the workspace and is bumped by the launch's last CTA (ticket), i.e.
+// after every CTA has read it.  Co-residency (the polls would deadlock otherwise) is checked by the host: grid <= 148 x
+// the kernel's resident CTAs per SM; larger problems take the cluster / grid-wide paths.
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <int NV, bool IMG, int THREADS>
+__global__ void __launch_bounds__(THREADS) l2_ll_kernel(const L2Args a, int cps) {
+    constexpr int kWarps = THREADS / 32;
+    static_assert(kWarps <= 32, "one shared-memory word per warp, reduced by warp 0");
+    __shared__ float s_w[kWarps];
+    __shared__ float s_tot;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t b = blockIdx.x / cps;
+    const int rank = (int)(blockIdx.x - b * cps);
+    const int64_t base = b * a.M;
+    const int64_t nvec = a.M / 4;
+    FVec<4> v[NV];
+    FVec<4> im[IMG ? NV : 1];
+    pdl_wait();
+    if (a.trace != nullptr && threadIdx.x == 0) a.trace[kTraceSlots * blockIdx.x] = globaltimer_ns();
+    const unsigned int epoch = __ldcg(&a.ws->l2_epoch);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int64_t q = ((int64_t)j * cps + rank) * THREADS + threadIdx.x;  // float4 index in sample
+        if (q < nvec) {
+            v[j] = ld_stream<4>(a.d + base + q * 4);
+            if constexpr (IMG) im[j] = ld_stream<4>(a.img + base + q * 4);
+        }
+    }
+    float ss = 0.0f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int64_t q = ((int64_t)j * cps + rank) * THREADS + threadIdx.x;
+        if (q < nvec) ss += v[j].v[0] * v[j].v[0] + v[j].v[1] * v[j].v[1] + v[j].v[2] * v[j].v[2] + v[j].v[3] * v[j].v[3];
+    }
+    for (int pass = 0; pass < a.passes; ++pass) {
+        const float w = warp_sum(ss);
+        if (lane == 0) s_w[wid] = w;
+        __syncthreads();
+        if (wid == 0) {
+            float t = lane < kWarps ? s_w[lane] : 0.0f;
+            t = warp_sum(t);
+            const unsigned long long tag = (unsigned long long)((epoch + 1u) * 2u + (unsigned int)pass) << 32;
+            unsigned long long* row = a.ws->l2_slots + ((size_t)b * 2 + pass) * kL2LLSlots;
+            if (lane == 0) st_relaxed_u64(row + rank, tag | (unsigned long long)__float_as_uint(t));
+            float p = 0.0f;
+            if (lane < cps) {
+                unsigned long long got;
+                do { got = ld_relaxed_u64(row + lane); } while ((got & 0xffffffff00000000ull) != tag);
+                p = __uint_as_float((unsigned int)(got & 0xffffffffull));
+            }
+            __syncwarp();
+            p = warp_sum(p);   // the same tree in every CTA of the sample: one bit-identical sum
+            if (lane == 0) s_tot = p;
+        }
+        __syncthreads();
+        if (a.trace != nullptr && threadIdx.x == 0) a.trace[kTraceSlots * blockIdx.x + 1 + (pass == a.passes - 1 ? 1 : 0)] = globaltimer_ns();
+        const float nrm = sqrtf(s_tot) + 1e-16f;
+        ss = 0.0f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int64_t q = ((int64_t)j * cps + rank) * THREADS + threadIdx.x;
+            if (q < nvec) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    v[j].v[e] = __fdiv_rn(v[j].v[e], nrm);  // d /= norm (IEEE divide, as the reference)
+                    ss += v[j].v[e] * v[j].v[e];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int64_t q = ((int64_t)j * cps + rank) * THREADS + threadIdx.x;
+        if (q < nvec) {
+            const int64_t off = base + q * 4;
+            FVec<4> o;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o.v[e] = a.scale * v[j].v[e];
+            st_stream<4>(a.out + off, o);
+            if constexpr (IMG) {
+                FVec<4> ad;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) ad.v[e] = fminf(fmaxf(im[j].v[e] + o.v[e], 0.0f), 1.0f);
+                st_stream<4>(a.adv + off, ad);
+            }
+        }
+    }
+    pdl_launch_dependents();
+    if (threadIdx.x == 0) {   // the launch's last CTA retires this launch's tags (every CTA has read the epoch long ago)
+        const unsigned int ticket = atomicAdd(&a.ws->l2_ticket, 1u);
+        if (ticket == gridDim.x - 1u) {
+            a.ws->l2_ticket = 0u;
+            a.ws->l2_epoch = epoch + 1u;
+        }
+        if (a.trace != nullptr) a.trace[kTraceSlots * blockIdx.x + 3] = globaltimer_ns();
+    }
+}
+
+// host side of the kernel above: picks (cps, NV), checks co-residency once per instantiation; false = not served
+template <int NV, bool IMG>
+static bool l2_ll_try(const L2Args& a, int64_t B, int cps, cudaStream_t s, cudaError_t& err) {
+    constexpr int THREADS = 256;
+    auto kern = l2_ll_kernel<NV, IMG, THREADS>;
+    static int resident = -1;   // CTAs of this instantiation one SM holds
+    if (resident < 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, THREADS, 0) != cudaSuccess) n = 0;
+        resident = n;
+    }
+    if (B * cps > (int64_t)kSMs * resident) return false;
+    L2Args at = a;
+    at.trace = trace_next((int)(B * cps));
+    err = launch_pdl(kern, dim3((unsigned)(B * cps)), dim3(THREADS), 0, s, at, cps);
+    return true;
+}
+
+// 0 = product choice; 1 = cluster kernels only; 2 = prefer the cluster-free kernel wherever it is eligible (developer A/B)
+static int l2_variant() {
+    static const int v = [] { const char* e = std::getenv("DCT_L2_VARIANT"); return e ? std::atoi(e) : 0; }();
+    return v;
 }
 
 // ---- large / odd samples: grid-wide passes through the workspace ------------------------------------------------------
@@ -263,8 +407,33 @@ extern "C" int dct_l2_normalize_f32(const float* d, float* out, int64_t B, int64
     if ((img == nullptr) != (adv == nullptr)) return DCT_ERR_BAD_ARG;
     if (!aligned(d, 4) || !aligned(out, 4) || !aligned(img, 4) || !aligned(adv, 4)) return DCT_ERR_MISALIGNED;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    L2Args a{d, out, M, passes, scale, img, adv, static_cast<Workspace*>(workspace)};
+    L2Args a{d, out, M, passes, scale, img, adv, static_cast<Workspace*>(workspace), nullptr};
     const bool vec_ok = (M % 4) == 0 && aligned(d, 16) && aligned(out, 16) && aligned(img, 16) && aligned(adv, 16);
+    if (vec_ok && workspace != nullptr && B <= kL2LLSamples && l2_variant() != 1) {
+        // cluster-free one-launch kernel: cps CTAs of 256 threads per sample, <= 8 float4 per thread, and as many more CTAs
+        // (fewer float4 each) as still fit one co-resident wave
+        const int64_t nvec = M / 4;
+        int64_t cps = (nvec + 256 * 8 - 1) / (256 * 8);
+        int nvt = 8;
+        while (nvt > 1 && cps * 2 <= kL2LLSlots && B * cps * 2 <= 2 * kSMs && (nvec + cps * 2 * 256 - 1) / (cps * 2 * 256) <= nvt / 2) {
+            cps *= 2;
+            nvt /= 2;
+        }
+        if (cps <= kL2LLSlots) {
+            cudaError_t e = cudaSuccess;
+            bool served;
+#define DCT_L2_LL(NVV) (img != nullptr ? l2_ll_try<NVV, true>(a, B, (int)cps, s, e) : l2_ll_try<NVV, false>(a, B, (int)cps, s, e))
+            if (nvt == 8) served = DCT_L2_LL(8);
+            else if (nvt == 4) served = DCT_L2_LL(4);
+            else if (nvt == 2) served = DCT_L2_LL(2);
+            else served = DCT_L2_LL(1);
+#undef DCT_L2_LL
+            if (served) {
+                if (e != cudaSuccess) { g_last_cuda_error = e; return DCT_ERR_CUDA; }
+                return check_launch();
+            }
+        }
+    }
     const int64_t per_wave = (int64_t)kL2Cluster * kL2Threads * 4;  // floats covered by one float4 per thread
     const int64_t nv = (M + per_wave - 1) / per_wave;
     const int64_t nv_big = (nv + 1) / 2;   // float4 per thread with a cluster of 16
@@ -285,6 +454,7 @@ extern "C" int dct_l2_normalize_f32(const float* d, float* out, int64_t B, int64
     }
     if (vec_ok && nv <= kL2MaxVecPerThread && B * kL2Cluster <= 0x7fffffff) {
         dim3 grid((unsigned)(B * kL2Cluster));
+        a.trace = trace_next((int)grid.x);
         cudaError_t e;
 #define DCT_L2_GO(NVV) (img != nullptr ? launch_pdl(l2_cluster_kernel<NVV, true>, grid, dim3(kL2Threads), 0, s, a) \
                                        : launch_pdl(l2_cluster_kernel<NVV, false>, grid, dim3(kL2Threads), 0, s, a))

@@ -108,15 +108,7 @@ class ConsistencyStep:
 
     # bytes that MUST move per step (algorithmic, fp32): see DESIGN.md "Algorithmic bytes"
     def algorithmic_bytes(self):
-        K, C, n = self.K, self.C, self.B * self.HW
-        cin = self.M // self.HW
-        fused = self.with_dice and C <= 4 and K * C <= 16   # Dice counted inside the JSD kernel: + labels only
-        b = {"jsd_fwdbwd": n * (2 * K * C * 4) + (n * 8 if fused else 0),
-             "dice": (n * K * (C * 4 + 8)) if (self.with_dice and not fused) else 0}
-        if self.with_vat:
-            b.update({"l2_normalize_x3": n * cin * 4 * (2 + 2 + 4), "kl_logit_fwdbwd": n * 3 * C * 4,
-                      "kl_from_logits_fwdbwd": n * 3 * C * 4})
-        return b
+        return self.part_bytes()
 
     def _publish_forked(self, prev: StepBuffers, dev) -> "torch.cuda.Event":
         """Publication of ``prev.sums`` on a side branch of the current stream (a fork/join that CUDA-graph capture records
@@ -145,48 +137,77 @@ class ConsistencyStep:
             if joined is not None:
                 torch.cuda.current_stream(dev).wait_event(joined)
 
-    def _run(self, bufs: StepBuffers, zero_counts: bool) -> None:
+    # the step's launches by name, in stream order (bench.py times each one on its own as well)
+    PARTS = ("jsd", "l2_direction", "kl_logit", "l2_radv", "kl_adv")
+
+    def parts(self):
+        return self.PARTS if self.with_vat else self.PARTS[:1]
+
+    def part_bytes(self):
+        """Algorithmic bytes of every launch of :meth:`parts` (what MUST cross HBM)."""
+        K, C, n = self.K, self.C, self.B * self.HW
+        cin = self.M // self.HW
+        fused = self.with_dice and C <= 4 and K * C <= 16   # Dice counted inside the JSD kernel: + labels only
+        b = {"jsd": n * (2 * K * C * 4) + (n * 8 if fused else 0) +
+                    ((n * K * (C * 4 + 8)) if (self.with_dice and not fused) else 0)}
+        if self.with_vat:
+            b.update({"l2_direction": n * cin * 4 * 2,      # d read, xi * normalise(normalise(d)) written (one launch)
+                      "kl_logit": n * 3 * C * 4,            # two logits tensors read, one gradient written
+                      "l2_radv": n * cin * 4 * 4,           # d.grad + img read, r_adv + img_adv written
+                      "kl_adv": n * 3 * C * 4})
+        return b
+
+    def run_part(self, bufs: StepBuffers, part: str, zero_counts: bool = True) -> None:
         h, K, C, B, HW = self._h, self.K, self.C, self.B, self.HW
         dev = bufs.logits[0].device
         st = _runtime.state(dev)
         ws, s = st.workspace.data_ptr(), _runtime.stream_ptr(dev)
         fl = _runtime.flags_ptr(st)
         sums = bufs.sums.data_ptr()
-        if self.with_dice and zero_counts:
-            bufs.dice_counts.zero_()  # the kernels accumulate into the counters
-        _lib.check(h.dct_jsd_fwdbwd_f32(_lib.ptr_array(bufs.logits), K, C, B, HW, _lib.IN_LOGITS,
-                                        self.jsd_weight / self.n, None, sums, _lib.ptr_array(bufs.grad_logits),
-                                        bufs.labels.data_ptr() if self.with_dice else None,
-                                        bufs.dice_counts.data_ptr() if self.with_dice else None, fl, ws, s),
-                   "dct_jsd_fwdbwd_f32")
-        if not self.with_vat:
-            if self.exchange is not None and self.exchange_mode != "deferred":
-                self.exchange.publish(bufs.sums)   # JSD-only step: the one-CTA publication kernel
-            return
-        d = bufs.d.data_ptr()
-        # d <- normalise(N(0,1));  d <- xi * normalise(d)                       (AEGenerator.py:97-98,103)
-        _lib.check(h.dct_l2_normalize_f32(d, d, B, self.M, 2, self.xi, None, None, ws, s), "dct_l2_normalize_f32")
-        # delta_kl = kl_div_with_logit(pred.detach(), y_hat); delta_kl.mean().backward()       (:107-108)
-        _lib.check(h.dct_kl_logit_f32(bufs.logits[0].data_ptr(), bufs.yhat_logits.data_ptr(), C, B, HW, None, sums + 8,
-                                      1, None, None, 1.0 / self.n, bufs.grad_yhat.data_ptr(), None, ws, s),
-                   "dct_kl_logit_f32")
-        # r_adv = eps * normalise(d.grad); img_adv = clamp(img + r_adv, 0, 1)                  (:113-117)
-        _lib.check(h.dct_l2_normalize_f32(bufs.d_grad.data_ptr(), bufs.r_adv.data_ptr(), B, self.M, 1, self.eps,
-                                          bufs.img.data_ptr(), bufs.img_adv.data_ptr(), ws, s), "dct_l2_normalize_f32")
-        # adv loss: KL_Divergence_2D(reduce=True)(softmax(adv_logits), real.detach()) + backward (cotraining :391-392)
-        if self.exchange is not None and self.exchange_mode == "fused":
-            # the step's last kernel also stores the three sums into every data-parallel rank's mailbox (NVLink)
-            _lib.check(h.dct_kl_from_logits_fwdbwd_pub_f32(bufs.adv_logits.data_ptr(), bufs.real_probs.data_ptr(), C, B, HW,
+        if part == "jsd":
+            # counts_mode 1: the launch overwrites the counters (zeroed by its own first CTA) -- no fill launch per step
+            _lib.check(h.dct_jsd_fwdbwd_f32(_lib.ptr_array(bufs.logits), K, C, B, HW, _lib.IN_LOGITS,
+                                            self.jsd_weight / self.n, None, sums, _lib.ptr_array(bufs.grad_logits),
+                                            bufs.labels.data_ptr() if self.with_dice else None,
+                                            bufs.dice_counts.data_ptr() if self.with_dice else None,
+                                            _lib.COUNTS_OVERWRITE if zero_counts else _lib.COUNTS_ACCUMULATE, fl, ws, s),
+                       "dct_jsd_fwdbwd_f32")
+        elif part == "l2_direction":
+            # d <- normalise(N(0,1));  d <- xi * normalise(d)                       (AEGenerator.py:97-98,103)
+            d = bufs.d.data_ptr()
+            _lib.check(h.dct_l2_normalize_f32(d, d, B, self.M, 2, self.xi, None, None, ws, s), "dct_l2_normalize_f32")
+        elif part == "kl_logit":
+            # delta_kl = kl_div_with_logit(pred.detach(), y_hat); delta_kl.mean().backward()       (:107-108)
+            _lib.check(h.dct_kl_logit_f32(bufs.logits[0].data_ptr(), bufs.yhat_logits.data_ptr(), C, B, HW, None, sums + 8,
+                                          1, None, None, 1.0 / self.n, bufs.grad_yhat.data_ptr(), None, ws, s),
+                       "dct_kl_logit_f32")
+        elif part == "l2_radv":
+            # r_adv = eps * normalise(d.grad); img_adv = clamp(img + r_adv, 0, 1)                  (:113-117)
+            _lib.check(h.dct_l2_normalize_f32(bufs.d_grad.data_ptr(), bufs.r_adv.data_ptr(), B, self.M, 1, self.eps,
+                                              bufs.img.data_ptr(), bufs.img_adv.data_ptr(), ws, s), "dct_l2_normalize_f32")
+        elif part == "kl_adv":
+            # adv loss: KL_Divergence_2D(reduce=True)(softmax(adv_logits), real.detach()) + backward (cotraining :391-392)
+            if self.exchange is not None and self.exchange_mode == "fused":
+                # the step's last kernel also stores the three sums into every data-parallel rank's mailbox (NVLink)
+                _lib.check(h.dct_kl_from_logits_fwdbwd_pub_f32(bufs.adv_logits.data_ptr(), bufs.real_probs.data_ptr(), C, B, HW,
+                                                               self.kl_eps, self.adv_weight / self.n, None, sums + 16,
+                                                               bufs.grad_adv.data_ptr(), fl, ws,
+                                                               ctypes.byref(self.exchange.descriptor(bufs.sums)), s),
+                           "dct_kl_from_logits_fwdbwd_pub_f32")
+            else:
+                _lib.check(h.dct_kl_from_logits_fwdbwd_f32(bufs.adv_logits.data_ptr(), bufs.real_probs.data_ptr(), C, B, HW,
                                                            self.kl_eps, self.adv_weight / self.n, None, sums + 16,
-                                                           bufs.grad_adv.data_ptr(), fl, ws,
-                                                           ctypes.byref(self.exchange.descriptor(bufs.sums)), s),
-                       "dct_kl_from_logits_fwdbwd_pub_f32")
-            return
-        _lib.check(h.dct_kl_from_logits_fwdbwd_f32(bufs.adv_logits.data_ptr(), bufs.real_probs.data_ptr(), C, B, HW,
-                                                   self.kl_eps, self.adv_weight / self.n, None, sums + 16,
-                                                   bufs.grad_adv.data_ptr(), fl, ws, s), "dct_kl_from_logits_fwdbwd_f32")
+                                                           bufs.grad_adv.data_ptr(), fl, ws, s), "dct_kl_from_logits_fwdbwd_f32")
+        else:
+            raise ValueError(part)
+
+    def _run(self, bufs: StepBuffers, zero_counts: bool) -> None:
+        for part in self.parts():
+            self.run_part(bufs, part, zero_counts)
         if self.exchange is not None and self.exchange_mode == "chained":
-            self.exchange.publish(bufs.sums)
+            self.exchange.publish(bufs.sums)   # the one-CTA publication kernel behind the step's last kernel
+        elif self.exchange is not None and self.exchange_mode == "fused" and not self.with_vat:
+            self.exchange.publish(bufs.sums)   # JSD-only step: no fused variant of its last kernel
 
     def capture(self, bufs: StepBuffers, publish_prev: Optional[StepBuffers] = None) -> "torch.cuda.CUDAGraph":
         """Capture ``run(bufs, publish_prev=...)`` into a CUDA graph (replay with ``graph.replay()``)."""

@@ -171,8 +171,9 @@ class _FusedJSDFn(torch.autograd.Function):
     """weight * mean(JSD(softmax(logits))) and its gradient in ONE pass (dct_jsd_fwdbwd_f32)."""
 
     @staticmethod
-    def forward(ctx, weight: float, n_global: Optional[int], labels, counts, in_kind: int, *views):
+    def forward(ctx, weight: float, n_global: Optional[int], labels, counts, in_kind: int, accumulate: bool, *views):
         in_dtypes = [v.dtype for v in views]
+        cmode = _lib.COUNTS_ACCUMULATE if accumulate else _lib.COUNTS_OVERWRITE
         lp = in_kind == _lib.IN_LOGITS and _all_bf16(views)
         if in_kind == _lib.IN_LOGITS and not lp and any(d == torch.bfloat16 for d in in_dtypes):
             views = [_promote(v) for v in views]   # mixed precisions: promote
@@ -181,7 +182,7 @@ class _FusedJSDFn(torch.autograd.Function):
         dev = vs[0].device
         st = _runtime.state(dev)
         n = b * hw if n_global is None else int(n_global)
-        need_grad = any(ctx.needs_input_grad[5:])
+        need_grad = any(ctx.needs_input_grad[6:])
         ctx.in_dtypes = in_dtypes
         total = torch.empty(1, dtype=torch.float64, device=dev)
         h = _lib.lib()
@@ -200,7 +201,7 @@ class _FusedJSDFn(torch.autograd.Function):
             fuse_dice = lab is not None and need_grad and c <= 4
             rc = h.dct_jsd_fwdbwd_bf16(_lib.ptr_array(vs), len(vs), c, b, hw, float(weight) / n, None, _ptr(total),
                                        _lib.ptr_array(grads) if need_grad else None, _ptr(lab) if fuse_dice else None,
-                                       _ptr(counts) if fuse_dice else None, fl, st.workspace.data_ptr(),
+                                       _ptr(counts) if fuse_dice else None, cmode, fl, st.workspace.data_ptr(),
                                        _runtime.stream_ptr(dev))
             if rc == _lib.ERR_UNSUPPORTED:
                 lp = False
@@ -211,7 +212,7 @@ class _FusedJSDFn(torch.autograd.Function):
                     for k, v in enumerate(vs):
                         vf = v.float()
                         _lib.check(h.dct_dice_counts_f32(vf.data_ptr(), lab.data_ptr(), c, b, hw,
-                                                         counts.data_ptr() + k * b * c * 3 * 8, 1, fl,
+                                                         counts.data_ptr() + k * b * c * 3 * 8, int(accumulate), fl,
                                                          _runtime.stream_ptr(dev)), "dct_dice_counts_f32")
                 ctx.grads = grads
         if lp:
@@ -219,7 +220,7 @@ class _FusedJSDFn(torch.autograd.Function):
         elif need_grad:
             grads = [torch.empty_like(v) for v in vs]
             _lib.check(h.dct_jsd_fwdbwd_f32(_lib.ptr_array(vs), len(vs), c, b, hw, in_kind, float(weight) / n, None,
-                                            _ptr(total), _lib.ptr_array(grads), _ptr(lab), _ptr(counts), fl,
+                                            _ptr(total), _lib.ptr_array(grads), _ptr(lab), _ptr(counts), cmode, fl,
                                             st.workspace.data_ptr(), _runtime.stream_ptr(dev)), "dct_jsd_fwdbwd_f32")
             ctx.grads = grads
         else:
@@ -228,7 +229,7 @@ class _FusedJSDFn(torch.autograd.Function):
             if lab is not None:
                 for k, v in enumerate(vs):
                     _lib.check(h.dct_dice_counts_f32(v.data_ptr(), lab.data_ptr(), c, b, hw,
-                                                     counts.data_ptr() + k * b * c * 3 * 8, 1, fl,
+                                                     counts.data_ptr() + k * b * c * 3 * 8, int(accumulate), fl,
                                                      _runtime.stream_ptr(dev)), "dct_dice_counts_f32")
             ctx.grads = None
         if lab is not None or in_kind == _lib.IN_PROBS:
@@ -246,12 +247,12 @@ class _FusedJSDFn(torch.autograd.Function):
         h = _lib.lib()
         dev = grads[0].device
         grads = _finish_grads(grads, g, ctx.in_dtypes)
-        return (None, None, None, None, None) + tuple(grads)
+        return (None, None, None, None, None, None) + tuple(grads)
 
 
 def jsd_consistency_from_logits(logits: Sequence[torch.Tensor], weight: float = 1.0,
                                 labels: Optional[torch.Tensor] = None, dice_counts: Optional[torch.Tensor] = None,
-                                n_global: Optional[int] = None) -> torch.Tensor:
+                                n_global: Optional[int] = None, accumulate: bool = True) -> torch.Tensor:
     """``weight * JSD_2D([softmax(z,1) for z in logits]).mean()`` in one pass over the logits.
 
     The gradient w.r.t. every logits tensor is produced by the same kernel launch (upstream
@@ -260,8 +261,9 @@ def jsd_consistency_from_logits(logits: Sequence[torch.Tensor], weight: float = 
     given, the K views' Dice counts (I, G, P) against ``labels`` are produced as well
     (what ``unlabdiceMeters[k].add`` computes, cotraining_totalloss.py:224).
     ``n_global``: total pixel count over all data-parallel ranks (defaults to the local B*H*W).
+    ``accumulate=False``: the launch clears ``dice_counts`` itself (hand it ``torch.empty``: no fill launch per step).
     """
-    return _FusedJSDFn.apply(float(weight), n_global, labels, dice_counts, _lib.IN_LOGITS, *logits)
+    return _FusedJSDFn.apply(float(weight), n_global, labels, dice_counts, _lib.IN_LOGITS, bool(accumulate), *logits)
 
 
 class FusedJSDConsistency(nn.Module):
@@ -271,8 +273,8 @@ class FusedJSDConsistency(nn.Module):
         super().__init__()
         self.weight = weight
 
-    def forward(self, logits: List[torch.Tensor], labels=None, dice_counts=None, n_global=None):
-        return jsd_consistency_from_logits(logits, self.weight, labels, dice_counts, n_global)
+    def forward(self, logits: List[torch.Tensor], labels=None, dice_counts=None, n_global=None, accumulate=True):
+        return jsd_consistency_from_logits(logits, self.weight, labels, dice_counts, n_global, accumulate)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define DCT_ABI_VERSION 1
+#define DCT_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define DCT_API __attribute__((visibility("default")))
@@ -151,11 +151,16 @@ DCT_API int dct_jsd_bwd_f32(const float* const* views, int K, int C, int64_t B, 
  * known up front (e.g. cot_weight / N for `weight * JSD_2D(..).mean()`,
  * generalframework/trainer/cotraining_totalloss.py:225-226,246).
  * Optional fused Dice counting for the K views on the same read (unlabdiceMeters,
- * cotraining_totalloss.py:224): if `labels` != NULL, `counts` int64 [K][B][C][3] (I, G, P) is
- * ACCUMULATED into with pred_k = argmax softmax(views[k]) exactly as dct_dice_counts_f32. */
+ * cotraining_totalloss.py:224): if `labels` != NULL, `counts` int64 [K][B][C][3] (I, G, P) receives the counts with
+ * pred_k = argmax softmax(views[k]) exactly as dct_dice_counts_f32.  `counts_mode`: DCT_COUNTS_ACCUMULATE adds to what
+ * `counts` holds; DCT_COUNTS_OVERWRITE makes the launch itself clear the counters first (its first CTA zeroes them and
+ * releases a flag in the workspace that every other CTA acquires before its first add -- needs `workspace`), so a
+ * training loop needs no fill launch per step (ABI 2; ABI 1 always accumulated). */
+#define DCT_COUNTS_ACCUMULATE 0
+#define DCT_COUNTS_OVERWRITE 1
 DCT_API int dct_jsd_fwdbwd_f32(const float* const* views, int K, int C, int64_t B, int64_t HW, int in_kind,
                        float gconst, float* map, double* sum, float* const* grad_views,
-                       const int64_t* labels, int64_t* counts,
+                       const int64_t* labels, int64_t* counts, int counts_mode,
                        int32_t* flags, void* workspace, void* stream);
 
 /* grad[i] *= *gscalar for i < n, skipped entirely (no memory traffic) when *gscalar == 1.0f.
@@ -358,7 +363,7 @@ DCT_API int dct_vote_f32(const float* const* views, int K, int C, int64_t B, int
  * forward only (evaluation; `labels` must be NULL then).  Fused Dice counting needs C <= 4. */
 DCT_API int dct_jsd_fwdbwd_bf16(const void* const* views, int K, int C, int64_t B, int64_t HW, float gconst,
                                 float* map, double* sum, void* const* grad_views, const int64_t* labels,
-                                int64_t* counts, int32_t* flags, void* workspace, void* stream);
+                                int64_t* counts, int counts_mode, int32_t* flags, void* workspace, void* stream);
 
 /* dct_kl_logit_f32 (VATGenerator.kl_div_with_logit, AEGenerator.py:78-91) on bf16 logits; bf16 gradients. */
 DCT_API int dct_kl_logit_bf16(const void* q_logit, const void* p_logit, int C, int64_t B, int64_t HW, float* map,
@@ -375,6 +380,16 @@ DCT_API int dct_ce_fwdbwd_bf16(const void* logits, const int64_t* labels, int C,
                                const float* class_weight, int64_t ignore_index, const float* gscalar, float gconst,
                                float* map, double* sum, void* grad_logits, int64_t* dice_counts, int32_t* flags,
                                void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Developer tracing (tools/step_trace.py; not used by the product).  Between _begin and _end every launch of the tile
+ * pipeline and of the perturbation normalisation takes the next 4 * max_ctas uint64 words of `buf` (device memory, zeroed
+ * by the caller) and each of its CTAs stamps %globaltimer (ns) there: [0] after the programmatic-dependency wait,
+ * [1] first tile landed / after the first per-sample exchange, [2] after the last exchange, [3] at its end.  _end returns the
+ * number of launches recorded.  Process-global state: do not trace from two host threads at once.
+ * ------------------------------------------------------------------------------------------ */
+DCT_API int dct_dev_trace_begin(void* buf, int max_ctas, int max_launches);
+DCT_API int dct_dev_trace_end(void);
 
 #ifdef __cplusplus
 }

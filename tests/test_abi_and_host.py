@@ -41,7 +41,7 @@ def test_header_prototype_arity_matches_ctypes_table():
 def test_library_basics_without_gpu():
     import dct_b200
     h = dct_b200._lib.lib()
-    assert h.dct_abi_version() == 1
+    assert h.dct_abi_version() == 2
     assert h.dct_workspace_bytes() >= 8 * 8192
     assert h.dct_error_string(0) == b"ok"
     assert b"unsupported" in h.dct_error_string(-2)

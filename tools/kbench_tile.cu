@@ -16,7 +16,7 @@ namespace dct {
 static bool g_pdl = true;
 static int g_pool_div = 0;
 static bool g_static = false;  // 1: no workspace -> static round-robin tile schedule (and no loss sum)
-namespace dct { bool pdl_enabled() { return g_pdl; } }
+namespace dct { bool pdl_enabled() { return g_pdl; } unsigned long long* trace_next(int) { return nullptr; } }
 
 using namespace dct;
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
@@ -92,15 +92,15 @@ void run(const char* tag, int64_t B, int64_t HW, int reps, double bytes_per_px, 
     // in-kernel trace of a chain of 8 launches: CTA residency window vs launch-to-launch spacing
     {
         const int NL = 8;
-        unsigned long long* tr; CK(cudaMalloc(&tr, (size_t)NL * grid * 16));
-        for (int i = 0; i < NL; ++i) { TileArgs t = sets[i % R]; t.trace = tr + (size_t)i * grid * 2; launch_pdl(kern, dim3(grid), dim3(THREADS), Cfg::kSmemBytes, (cudaStream_t)0, t); }
+        unsigned long long* tr; CK(cudaMalloc(&tr, (size_t)NL * grid * 8 * kTraceSlots));
+        for (int i = 0; i < NL; ++i) { TileArgs t = sets[i % R]; t.trace = tr + (size_t)i * grid * kTraceSlots; launch_pdl(kern, dim3(grid), dim3(THREADS), Cfg::kSmemBytes, (cudaStream_t)0, t); }
         CK(cudaDeviceSynchronize());
-        std::vector<unsigned long long> h((size_t)NL * grid * 2);
+        std::vector<unsigned long long> h((size_t)NL * grid * kTraceSlots);
         CK(cudaMemcpy(h.data(), tr, h.size() * 8, cudaMemcpyDeviceToHost));
         double win = 0, gap = 0, cta = 0, spread_s = 0, spread_e = 0; unsigned long long prev_end = 0, prev_start = 0; double spacing = 0;
         for (int i = 0; i < NL; ++i) {
             unsigned long long s0 = ~0ull, s1 = 0, e0_ = ~0ull, e1_ = 0; double d = 0;
-            for (int c = 0; c < grid; ++c) { auto a0 = h[((size_t)i * grid + c) * 2], a1 = h[((size_t)i * grid + c) * 2 + 1]; s0 = std::min(s0, a0); s1 = std::max(s1, a0); e0_ = std::min(e0_, a1); e1_ = std::max(e1_, a1); d += (double)(a1 - a0); }
+            for (int c = 0; c < grid; ++c) { auto a0 = h[((size_t)i * grid + c) * kTraceSlots], a1 = h[((size_t)i * grid + c) * kTraceSlots + 3]; s0 = std::min(s0, a0); s1 = std::max(s1, a0); e0_ = std::min(e0_, a1); e1_ = std::max(e1_, a1); d += (double)(a1 - a0); }
             if (i >= 2) { win += (double)(e1_ - s0); gap += (double)(s0 - prev_end); cta += d / grid; spread_s += (double)(s1 - s0); spread_e += (double)(e1_ - e0_); spacing += (double)(s0 - prev_start); }
             prev_end = e1_; prev_start = s0;
         }

@@ -89,7 +89,7 @@ def main():
 
             def ours():
                 _lib.check(h.dct_jsd_fwdbwd_f32(_lib.ptr_array(z), K, C, Bc, H * W, _lib.IN_LOGITS, 1.0 / N, None,
-                                                total.data_ptr(), _lib.ptr_array(gr), None, None, None,
+                                                total.data_ptr(), _lib.ptr_array(gr), None, None, 0, None,
                                                 st.workspace.data_ptr(), _runtime.stream_ptr(dev)), "jsd")
             for _ in range(3):
                 ours()
