@@ -32,6 +32,7 @@
 
 #include "dct_common.cuh"
 #include "dct_tma.cuh"
+#include "dct_tmap.cuh"
 
 namespace dct {
 
@@ -96,16 +97,12 @@ __device__ __forceinline__ void tile_st_row(unsigned char* row, int p0, const FV
 #ifndef DCT_DICE_LOCAL
 #define DCT_DICE_LOCAL 1
 #endif
-// Developer experiment (off in the product): the LAST DCT_POOL_SPLIT_LEVELS levels of the dynamically scheduled
-// tail pool are handed out as DCT_POOL_SPLIT sub-tiles of TP / DCT_POOL_SPLIT pixels each, so that the CTAs' finishing times
-// spread over a fraction of a tile's service time instead of a whole one (measured end spread at c2: 4.5 us on a 41 us
-// kernel, profiles/r10/kbench_c2_family.log).  1 = whole tiles only: every change sits under #if DCT_POOL_SPLIT > 1, the
-// product's translation units compile to the SASS they had before (checked with cuobjdump).  Not yet run on hardware.
-#ifndef DCT_POOL_SPLIT
-#define DCT_POOL_SPLIT 1
-#endif
-#ifndef DCT_POOL_SPLIT_LEVELS
-#define DCT_POOL_SPLIT_LEVELS 1
+// (An experiment that handed the last level(s) of the tail pool out as 2 or 4 sub-tiles per tile -- to shrink the CTAs' end
+// spread below one tile's service time -- was measured and removed: the extra indirection in the tile loop cost far more
+// than the tail it saved: c2 step 106.2 -> 124.2 (2 sub-tiles) / 136.4 us (4), c4 1.385 -> 1.738 ms; profiles/r26/ab_split.log.)
+// 1 (product): stages of C > 4 shapes whose tile is one box are moved by tensor-map TMA; 0: row copies everywhere (A/B builds)
+#ifndef DCT_TMAP
+#define DCT_TMAP 1
 #endif
 constexpr int kTileMaxTensors = 8;
 constexpr int kTileMaxRows = 80;   // NIN*C rows per stage
@@ -135,6 +132,18 @@ struct TileArgs {
     unsigned long long* trace;     // developer tracing: kTraceSlots words per CTA (start, first tile landed, -, end) in ns; null in the product
 };
 
+// Tensor maps of a launch whose stages are filled / drained by tensor-map TMA (dct_tmap.cuh): second kernel parameter,
+// __grid_constant__ (the copy instructions take the descriptors' addresses in parameter space).  Empty otherwise.
+template <bool TMAP>
+struct TileMaps {
+    int unused;
+};
+template <>
+struct alignas(64) TileMaps<true> {
+    CUtensorMap in[kTileMaxTensors];
+    CUtensorMap out[kTileMaxTensors];
+};
+
 // does the op read the labels itself (Op::LABELS == true)?  Ops without the member do not.
 template <class Op, class = void>
 struct op_labels : std::false_type {};
@@ -161,29 +170,38 @@ constexpr int tile_row_bytes() {
 template <class Op, int CT>
 constexpr int tile_row_words() { return tile_row_bytes<Op, CT, float>() / 4; }
 
-template <int WORDS, int PPT, int CTHREADS, int MINB, int UNIT = 4>
+// one tensor's C rows of a tile; with tensor-map TMA every tensor's box starts on a 128-byte boundary of the stage
+template <int CT, int TP, class ET, bool TMAP>
+constexpr size_t tile_tensor_stride() {
+    constexpr size_t raw = (size_t)CT * TP * sizeof(ET);
+    return TMAP ? (raw + 127) / 128 * 128 : raw;
+}
+template <class Op, int CT, int TP, class ET, bool TMAP>
+constexpr size_t tile_stage_bytes() {
+    return Op::NIN * tile_tensor_stride<CT, TP, ET, TMAP>() + (op_label_row<Op>() ? (size_t)TP * 8 : 0) + (Op::GMAP ? (size_t)TP * 4 : 0);
+}
+
+template <size_t STAGE_BYTES, int MINB>
 constexpr int tile_stages() {
-    // as many stages as fit in this CTA's share of shared memory, between 2 and 8 (WORDS in units of UNIT bytes per pixel)
-    constexpr size_t stage = (size_t)WORDS * PPT * CTHREADS * UNIT;
+    // as many stages as fit in this CTA's share of shared memory, between 2 and 8
     // 228 KB per SM, 1 KB reserved per CTA, < 1 KB of static shared memory + barriers + alignment slack
-    constexpr size_t n = (233472 / MINB - 2048) / stage;
+    constexpr size_t n = (233472 / MINB - 2048) / STAGE_BYTES;
     return n < 2 ? 2 : (n > 8 ? 8 : (int)n);
 }
 
-template <class Op, int CT, int PPT, int CTHREADS, int STAGES, class ET = float>
+template <class Op, int CT, int PPT, int CTHREADS, int STAGES, class ET = float, bool TMAP = false>
 struct TileCfg {
     static constexpr int TP = CTHREADS * PPT;                       // pixels per tile
     static constexpr int ROWS = Op::NIN * CT;                       // data rows (element type ET)
     static constexpr int ES = (int)sizeof(ET);
-    static constexpr size_t kStageBytes = (size_t)tile_row_bytes<Op, CT, ET>() * TP;
+    static constexpr size_t kTensorStride = tile_tensor_stride<CT, TP, ET, TMAP>();   // tensor n's rows start at n * kTensorStride
+    static constexpr size_t kStageBytes = tile_stage_bytes<Op, CT, TP, ET, TMAP>();
     static constexpr size_t kRowBytes = (size_t)TP * ES;            // one data row
-    static constexpr size_t kLabelOffB = (size_t)ROWS * TP * ES;    // in bytes; labels are 8-byte, TP*8 bytes
+    static constexpr size_t kLabelOffB = Op::NIN * kTensorStride;   // in bytes; labels are 8-byte, TP*8 bytes
     static constexpr size_t kGmapOffB = kLabelOffB + (op_label_row<Op>() ? (size_t)TP * 8 : 0);  // valid when Op::GMAP (fp32 row)
-#if DCT_POOL_SPLIT > 1
-    static constexpr size_t kSmemBytes = kStageBytes * STAGES + 16 * STAGES + 4 * STAGES;   // + the stages' sub-tile indices
-#else
     static constexpr size_t kSmemBytes = kStageBytes * STAGES + 16 * STAGES;
-#endif
+    static_assert(!TMAP || (TP <= 256 && kStageBytes % 128 == 0), "tensor-map stages: one box per tensor, 128-byte aligned");
+    __host__ __device__ static constexpr size_t row_off(int n, int c) { return (size_t)n * kTensorStride + (size_t)c * kRowBytes; }
 };
 
 // Warp-specialised persistent kernel: NCW consumer warps + 1 producer warp per CTA.
@@ -198,17 +216,20 @@ struct TileCfg {
 //       No CTA-wide barrier in the tile loop: a fast warp runs ahead by up to STAGES-1 tiles.
 // Nothing depends on WHICH CTA processes a tile: Dice counts are integer atomics, the loss sum is accumulated in
 // exact fixed point (tile_grid_finish), so results are bit-reproducible under the dynamic part of the schedule.
-template <class Op, int CT, int PPT, int NCW, int STAGES, int MINB = 1, class ET = float, bool PUB = false>
-__global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArgs a) {
+// TMAP: the data rows move by tensor-map TMA, one copy per tensor and tile each way (dct_tmap.cuh); side rows (labels,
+// upstream map) stay 1-D bulk copies.  A ragged last tile of an image needs no special casing for the data rows then:
+// the box is filled with zeros beyond the image (the transaction count is always the whole box) and clipped on the way out.
+template <class Op, int CT, int PPT, int NCW, int STAGES, int MINB = 1, class ET = float, bool PUB = false, bool TMAP = false>
+__global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArgs a, const __grid_constant__ TileMaps<TMAP> maps) {
     constexpr int CTHREADS = NCW * 32;
-    using Cfg = TileCfg<Op, CT, PPT, CTHREADS, STAGES, ET>;
+    using Cfg = TileCfg<Op, CT, PPT, CTHREADS, STAGES, ET, TMAP>;
     constexpr int TP = Cfg::TP, ROWS = Cfg::ROWS, ES = Cfg::ES, NIN = Op::NIN, NOUT = Op::NOUT, C = CT;
     constexpr bool DICE = Op::NDICE > 0;
     constexpr bool DICE_LOCAL = DICE && (DCT_DICE_LOCAL != 0);   // counters live in the consumers' registers across tiles
     constexpr bool DICE_FOLD = DICE && !DICE_LOCAL;               // per-tile fold through the label row by the producer warp
     constexpr bool LAB = op_labels<Op>::value;   // the op consumes the labels itself
     // > 40 fp32 rows per pixel do not fit the register file as a pixel pair: ops that can, work on the stage in place
-    constexpr bool STREAM = op_stream<Op>::value && ROWS >= DCT_STREAM_MIN_ROWS && PPT <= 2 && std::is_same<ET, float>::value;
+    constexpr bool STREAM = op_stream<Op>::value && ROWS >= DCT_STREAM_MIN_ROWS && PPT <= 2 && std::is_same<ET, float>::value && !TMAP;
     constexpr bool CONF = op_conf<Op>::value;    // confusion counts of tensor 0 vs the labels (CTA-shared histogram)
     constexpr bool LROW = DICE || LAB || CONF;   // the stage carries a label row
     constexpr int LW = (PPT % 2 == 0) ? 2 : 1;   // pixels per math lane group: pairs use packed FP32x2
@@ -220,23 +241,6 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
     unsigned char* stages = smem_raw;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + Cfg::kStageBytes * STAGES);
     uint64_t* done = full + STAGES;
-#if DCT_POOL_SPLIT > 1
-    constexpr int SPLIT_S = DCT_POOL_SPLIT, TPS = NCW * 32 * PPT / SPLIT_S;   // sub-tiles per tile, pixels per sub-tile
-    static_assert((NCW * 32 * PPT) % SPLIT_S == 0 && (TPS * (int)sizeof(ET)) % 16 == 0, "sub-tile rows stay 16-byte multiples");
-    int* s_part = reinterpret_cast<int*>(done + STAGES);   // sub-tile index held by each stage, -1 = a whole tile
-    // pixel offset (inside image tile / tiles_per_image) and length of tile `tile`, or of its sub-tile `part` (len 0: empty)
-    auto tile_span = [&](int tile, int part, int64_t& off, int& len) {
-        const int bb = tile / a.tiles_per_image;
-        off = (int64_t)(tile - bb * a.tiles_per_image) * (NCW * 32 * PPT);
-        const int64_t rem = a.HW - off;
-        len = (int)(rem < NCW * 32 * PPT ? rem : NCW * 32 * PPT);
-        if (part >= 0) {
-            const int o = part * TPS;
-            off += o;
-            len = len - o < 0 ? 0 : (len - o < TPS ? len - o : TPS);
-        }
-    };
-#endif
     __shared__ int s_tile[STAGES];  // tile index held by each stage; -1 = end of work
     __shared__ int s_mark[STAGES];  // DICE_LOCAL: 1 = hand the Dice counters over after this tile (written with s_tile)
     __shared__ unsigned int s_conf[CONF ? CT * CT : 1];   // this CTA's confusion counts (flushed once, at the end)
@@ -260,6 +264,14 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
             tma::mbar_init(&done[s], NCW);
         }
         tma::fence_barrier_init();
+    }
+    if constexpr (TMAP) {   // descriptor fetch overlaps the previous grid's tail (before the dependency wait)
+        if (tid == CTHREADS) {
+#pragma unroll
+            for (int n = 0; n < NIN; ++n) tma::prefetch_tensormap(&maps.in[n]);
+#pragma unroll
+            for (int n = 0; n < NOUT; ++n) tma::prefetch_tensormap(&maps.out[n]);
+        }
     }
     __syncthreads();
     pdl_wait();               // the previous grid has completed and its writes are visible (no-op without PDL)
@@ -293,37 +305,8 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
         const int pool_q = dynamic ? per / (a.pool_div > 0 ? a.pool_div : 5) : 0;             // pool tiles taken from the end of every CTA's range
         const int my_static = my_n - pool_q;
         int draws = 0;
-#if DCT_POOL_SPLIT > 1
-        int draw_part = -1;    // sub-tile index of the tile draw() has just returned (-1 = whole tile)
-#endif
         auto draw = [&]() -> int {  // next tile index for this CTA; >= num_tiles when there is no more work
             int t;
-#if DCT_POOL_SPLIT > 1
-            draw_part = -1;
-            if (draws >= my_static && pool_q != 0) {
-                // pool levels [0, whole) are whole tiles; the last `lv` levels come as SPLIT_S sub-tiles each (all CTAs'
-                // part 0 of a level first, then part 1, ...); empty sub-tiles of a ragged tile are skipped
-                const int lv = pool_q < DCT_POOL_SPLIT_LEVELS ? pool_q : DCT_POOL_SPLIT_LEVELS, whole = pool_q - lv;
-                const unsigned int g = gridDim.x, n_whole = (unsigned int)whole * g;
-                for (;;) {
-                    unsigned int got;
-                    asm volatile("atom.global.relaxed.gpu.add.u32 %0, [%1], 1;" : "=r"(got) : "l"(&a.ws->tile_counter) : "memory");
-                    int j, k, part = -1;
-                    if (got < n_whole) { j = (int)(got % g); k = (int)(got / g); }
-                    else {
-                        const unsigned int r = got - n_whole, w = r % (g * SPLIT_S);
-                        k = whole + (int)(r / (g * SPLIT_S)); j = (int)(w % g); part = (int)(w / g);
-                    }
-                    if (k >= pool_q) { t = a.num_tiles; break; }
-                    t = j * per + min(j, extra) + per + (j < extra ? 1 : 0) - pool_q + k;
-                    int64_t o; int len;
-                    tile_span(t, part, o, len);
-                    if (len > 0) { draw_part = part; break; }
-                }
-                ++draws;
-                return t;
-            }
-#endif
             if (draws < my_static) t = my_begin + draws;
             else if (pool_q == 0) t = a.num_tiles;
             else {
@@ -342,15 +325,9 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
         int issued = 0;        // loads issued so far; the k-th goes to stage k % STAGES
         bool more = true;
         int pending = 0;       // drawn one ahead of its use
-#if DCT_POOL_SPLIT > 1
-        int pending_part = -1;
-#endif
         auto try_issue = [&]() {  // lane 0 only
             if (!more) return;
             const int tile = pending, stage = issued % STAGES;
-#if DCT_POOL_SPLIT > 1
-            const int part = pending_part;
-#endif
             if (tile >= a.num_tiles) {  // publish "no more work" through the same barrier
                 more = false;
                 s_tile[stage] = -1;
@@ -358,10 +335,6 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
                 return;
             }
             pending = draw();
-#if DCT_POOL_SPLIT > 1
-            pending_part = draw_part;
-            s_part[stage] = part;
-#endif
             s_tile[stage] = tile;
             const int b = tile / tpi;
             if constexpr (DICE_LOCAL) {
@@ -372,28 +345,27 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
                 if (mark) run_b = -1;
                 s_mark[stage] = mark ? 1 : 0;
             }
-#if DCT_POOL_SPLIT > 1
-            int64_t off;
-            int len_px;
-            tile_span(tile, part, off, len_px);
-            const uint32_t npix = (uint32_t)len_px;
-#else
             const int64_t off = (int64_t)(tile - b * tpi) * TP;
             const int64_t rem = HW - off;
             const uint32_t npix = (uint32_t)(rem < TP ? rem : TP);
-#endif
             const uint32_t bytes = npix * (uint32_t)ES;   // one data row segment
             unsigned char* dst = stages + (size_t)stage * Cfg::kStageBytes;
-            uint32_t total = bytes * ROWS;
+            uint32_t total = TMAP ? (uint32_t)(ROWS * TP * ES) : bytes * ROWS;   // (a box always completes whole)
             if constexpr (LROW) total += do_lab ? 8u * npix : 0u;
             if constexpr (Op::GMAP) total += has_gmap ? 4u * npix : 0u;
             tma::mbar_expect_tx(&full[stage], total);  // release: the tile index above is visible to the waiters
+            if constexpr (TMAP) {
 #pragma unroll
-            for (int n = 0; n < NIN; ++n)
+                for (int n = 0; n < NIN; ++n)
+                    tma::tensor_load_3d(dst + (size_t)n * Cfg::kTensorStride, &maps.in[n], (int)off, 0, b, &full[stage]);
+            } else {
 #pragma unroll
-                for (int c = 0; c < C; ++c)
-                    tma::bulk_load(dst + (size_t)(n * C + c) * Cfg::kRowBytes,
-                                   static_cast<const ET*>(a.in[n]) + ((int64_t)b * C + c) * HW + off, bytes, &full[stage]);
+                for (int n = 0; n < NIN; ++n)
+#pragma unroll
+                    for (int c = 0; c < C; ++c)
+                        tma::bulk_load(dst + Cfg::row_off(n, c),
+                                       static_cast<const ET*>(a.in[n]) + ((int64_t)b * C + c) * HW + off, bytes, &full[stage]);
+            }
             if constexpr (LROW) {
                 if (do_lab) tma::bulk_load(dst + Cfg::kLabelOffB, a.labels + (int64_t)b * HW + off, 8u * npix, &full[stage]);
             }
@@ -436,9 +408,6 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
         };
         if (lane == 0) {
             pending = draw();
-#if DCT_POOL_SPLIT > 1
-            pending_part = draw_part;
-#endif
 #pragma unroll 1
             for (int s = 0; s < STAGES; ++s) try_issue();
         }
@@ -497,24 +466,21 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
             __syncwarp();
             if (lane == 0) {
                 if constexpr (NOUT > 0) {
-#if DCT_POOL_SPLIT > 1
-                    int64_t off;
-                    int len_px;
-                    tile_span(tile, s_part[stage], off, len_px);
-                    const uint32_t bytes = (uint32_t)len_px * (uint32_t)ES;
-#else
                     const int64_t off = (int64_t)(tile - b * tpi) * TP;
                     const int64_t rem = HW - off;
                     const uint32_t bytes = (uint32_t)(rem < TP ? rem : TP) * (uint32_t)ES;
-#endif
                     const unsigned char* st = stages + (size_t)stage * Cfg::kStageBytes;
 #pragma unroll
                     for (int n = 0; n < NOUT; ++n)
                         if (a.out[n] != nullptr) {
+                            if constexpr (TMAP) {
+                                tma::tensor_store_3d(&maps.out[n], (int)off, 0, b, st + (size_t)n * Cfg::kTensorStride);
+                            } else {
 #pragma unroll
-                            for (int c = 0; c < C; ++c)
-                                tma::bulk_store(static_cast<ET*>(a.out[n]) + ((int64_t)b * C + c) * HW + off,
-                                                st + (size_t)(n * C + c) * Cfg::kRowBytes, bytes);
+                                for (int c = 0; c < C; ++c)
+                                    tma::bulk_store(static_cast<ET*>(a.out[n]) + ((int64_t)b * C + c) * HW + off,
+                                                    st + Cfg::row_off(n, c), bytes);
+                            }
                         }
                     tma::bulk_commit();
                     // load i-1's store group has drained its stage once at most one group is still reading:
@@ -576,15 +542,9 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
             if (tile < 0) break;
             const int b = tile / tpi;
             const bool hand_over = DICE_LOCAL && do_dice && s_mark[stage] != 0;   // uniform across the CTA's consumers
-#if DCT_POOL_SPLIT > 1
-            int64_t off;
-            int len;
-            tile_span(tile, s_part[stage], off, len);
-#else
             const int64_t off = (int64_t)(tile - b * tpi) * TP;
             const int64_t rem = HW - off;
             const int len = (int)(rem < TP ? rem : TP);
-#endif
             unsigned char* st = stages + (size_t)stage * Cfg::kStageBytes;
             const int p0 = tid * PPT;
             const bool active = p0 < len;
@@ -632,7 +592,7 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
 #pragma unroll
                 for (int n = 0; n < NIN; ++n)
 #pragma unroll
-                    for (int c = 0; c < C; ++c) xin[n][c] = tile_ld_row<PPT, ET>(st + (size_t)(n * C + c) * Cfg::kRowBytes, p0);
+                    for (int c = 0; c < C; ++c) xin[n][c] = tile_ld_row<PPT, ET>(st + Cfg::row_off(n, c), p0);
                 FVec<PPT> mapv;
                 float part = 0.0f;
 #pragma unroll
@@ -724,7 +684,7 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
                 for (int n = 0; n < NOUT; ++n)
                     if (a.out[n] != nullptr) {
 #pragma unroll
-                        for (int c = 0; c < C; ++c) tile_st_row<PPT, ET>(st + (size_t)(n * C + c) * Cfg::kRowBytes, p0, xin[n][c]);
+                        for (int c = 0; c < C; ++c) tile_st_row<PPT, ET>(st + Cfg::row_off(n, c), p0, xin[n][c]);
                     }
             }
             if constexpr (NOUT > 0) tma::fence_proxy_async_smem();
@@ -833,16 +793,26 @@ int tile_launch_ct(TileArgs a, int64_t B, cudaStream_t stream) {
     //                    (profiles/r09/kbench_wide_more.log: 4245 GB/s; 6 warps 3750, 2 x 3 warps 3744, 5 warps x 4 stages 3205)
     //   DCT_STREAM_MIN_ROWS (off by default): ops with a shared-memory-resident body work on the stage in place; measured
     //                    equal or slower than the register-resident body at every shape (profiles/r08/kbench_wide_stream.log)
-    constexpr bool STREAMK = op_stream<Op>::value && ROWS >= DCT_STREAM_MIN_ROWS && std::is_same<ET, float>::value;
     constexpr int PPT = ROWS <= 4 ? 4 : (ROWS <= 40 ? 2 : 1);
     constexpr int NCW = ROWS <= 16 ? 8 : (ROWS <= 24 ? 4 : (ROWS <= 40 ? (Op::NOUT == 0 ? 8 : 3) : (ROWS <= 60 ? 5 : 7)));
     constexpr int MINB = ROWS <= 24 ? 2 : (ROWS <= 40 ? (Op::NOUT == 0 ? 1 : 2) : (ROWS <= 60 ? 2 : 1));
-    (void)STREAMK;
+    constexpr int TPX = NCW * 32 * PPT;
+    // wide stages (C = 19) whose tile is one box (<= 256 pixels): tensor-map TMA, one copy per tensor instead of one per row
+    constexpr bool TMAP = (DCT_TMAP != 0) && CT > 4 && TPX <= 256;
     // bf16 tensors: same shapes (the register budget follows the number of rows, not their width); the 2-byte rows
     // simply buy more stages
-    constexpr int STAGES = tile_stages<tile_row_bytes<Op, CT, ET>(), PPT, NCW * 32, MINB, 1>();
-    using Cfg = TileCfg<Op, CT, PPT, NCW * 32, STAGES, ET>;
-    auto kern = tile_kernel<Op, CT, PPT, NCW, STAGES, MINB, ET, PUB>;
+    constexpr int STAGES = tile_stages<tile_stage_bytes<Op, CT, TPX, ET, TMAP>(), MINB>();
+    using Cfg = TileCfg<Op, CT, PPT, NCW * 32, STAGES, ET, TMAP>;
+    auto kern = tile_kernel<Op, CT, PPT, NCW, STAGES, MINB, ET, PUB, TMAP>;
+    TileMaps<TMAP> maps{};
+    if constexpr (TMAP) {
+        // descriptors of this launch's tensors (host-side encode, ~1 us each; nothing is launched if the driver refuses)
+        for (int n = 0; n < Op::NIN; ++n)
+            if (!make_tmap_bchw(&maps.in[n], a.in[n], (int)sizeof(ET), a.HW, CT, B, Cfg::TP)) return DCT_ERR_UNSUPPORTED;
+        for (int n = 0; n < Op::NOUT; ++n)
+            if (a.out[n] != nullptr && !make_tmap_bchw(&maps.out[n], a.out[n], (int)sizeof(ET), a.HW, CT, B, Cfg::TP))
+                return DCT_ERR_UNSUPPORTED;
+    }
     static bool configured[64] = {};  // per instantiation and device (the attribute is per device function)
     int devid = 0;
     cudaGetDevice(&devid);
@@ -856,7 +826,7 @@ int tile_launch_ct(TileArgs a, int64_t B, cudaStream_t stream) {
     int grid = kSMs * MINB;
     if (grid > a.num_tiles) grid = a.num_tiles;
     if (a.trace == nullptr) a.trace = trace_next(grid);
-    cudaError_t e = launch_pdl(kern, dim3(grid), dim3(NCW * 32 + 32), Cfg::kSmemBytes, stream, a);
+    cudaError_t e = launch_pdl(kern, dim3(grid), dim3(NCW * 32 + 32), Cfg::kSmemBytes, stream, a, maps);
     if (e != cudaSuccess) { g_last_cuda_error = e; return DCT_ERR_CUDA; }
     return check_launch();
 }

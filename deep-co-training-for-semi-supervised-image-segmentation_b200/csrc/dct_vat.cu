@@ -55,14 +55,37 @@ __device__ __forceinline__ float block_sum_f(float v, float* s_warp) {
     return t;
 }
 
+// What one element goes through once the sample's sum of squares `ss` is known: d / n1 [/ n2] * scale, each step rounded
+// like the reference's own sequence of ops (AEGenerator.py:72,103: `d /= norm`, again, `xi * d`), with the divisions as
+// multiplications by the correctly rounded reciprocal (<= 1 ulp each; an IEEE divide per element is ~10 instructions and
+// these launches are latency-bound).  n1 = sqrt(ss) + 1e-16; n2 = || d / n1 || + 1e-16 = sqrt(ss) / n1 + 1e-16.
+struct L2Scale {
+    float r1, r2, scale;
+    bool twice;
+};
+__device__ __forceinline__ L2Scale l2_scales(float ss, int passes, float scale) {
+    const float root = sqrtf(ss);
+    const float n1 = root + 1e-16f;
+    L2Scale s;
+    s.r1 = __frcp_rn(n1);
+    s.twice = passes > 1;
+    s.r2 = s.twice ? __frcp_rn(__fdiv_rn(root, n1) + 1e-16f) : 1.0f;
+    s.scale = scale;
+    return s;
+}
+__device__ __forceinline__ float l2_apply(float x, const L2Scale& s) {
+    float q = __fmul_rn(x, s.r1);
+    if (s.twice) q = __fmul_rn(q, s.r2);
+    return __fmul_rn(s.scale, q);
+}
+
 // One cluster per sample; NV float4 per thread (compile-time so the slice lives in registers).
-// Critical path per normalisation pass: warp shuffle tree -> one shared-memory word per warp -> ONE
-// cluster barrier -> every warp gathers the 8 CTAs x 8 warps partials through distributed shared
-// memory (2 per lane) and reduces them with the same shuffle tree (so all 2048 threads of the
-// cluster hold bit-identical norms).  Per-pass slots make a second barrier per pass unnecessary;
-// the image (for the clamp(img + r) tail) is prefetched before the first barrier.
+// Critical path: warp shuffle tree -> one shared-memory word per warp -> ONE cluster barrier -> every warp gathers the
+// 8 CTAs x 8 warps partials through distributed shared memory (2 per lane) and reduces them with the same shuffle tree
+// (so all 2048 threads of the cluster hold bit-identical norms); the image (for the clamp(img + r) tail) is prefetched
+// before the barrier.
 template <int NV, bool IMG, int CL = kL2Cluster>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(kL2Threads)
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(kL2Threads, (NV <= 8 ? 3 : 1))   // <= 80 registers up to NV = 8
 l2_cluster_kernel(const L2Args a) {
     constexpr int kL2Cluster = CL;   // (shadows the namespace constant: 8, or 16 for the large-sample instantiations)
     constexpr int kWarps = kL2Threads / 32;
@@ -75,7 +98,6 @@ l2_cluster_kernel(const L2Args a) {
     const int64_t base = b * a.M;
     const int64_t nvec = a.M / 4;
     FVec<4> v[NV];
-    FVec<4> im[IMG ? NV : 1];
     float ss = 0.0f;
     pdl_wait();
     if (a.trace != nullptr && threadIdx.x == 0) a.trace[kTraceSlots * blockIdx.x] = globaltimer_ns();
@@ -84,7 +106,12 @@ l2_cluster_kernel(const L2Args a) {
         const int64_t q = ((int64_t)j * kL2Cluster + rank) * kL2Threads + threadIdx.x;  // float4 index in sample
         if (q < nvec) {
             v[j] = ld_stream<4>(a.d + base + q * 4);
-            if constexpr (IMG) im[j] = ld_stream<4>(a.img + base + q * 4);
+            // the image is only needed after the exchange: its lines are pulled into L2 now (one prefetch per 128-byte line)
+            // and read from there later, instead of sitting in 4 * NV more registers per thread -- at 96 registers only
+            // 31 of a 32-sample batch's clusters were co-resident and the last one started a whole kernel late (profiles/r25)
+            if constexpr (IMG) {
+                if ((threadIdx.x & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.img + base + q * 4));
+            }
         }
     }
 #pragma unroll
@@ -92,28 +119,26 @@ l2_cluster_kernel(const L2Args a) {
         const int64_t q = ((int64_t)j * kL2Cluster + rank) * kL2Threads + threadIdx.x;
         if (q < nvec) ss += v[j].v[0] * v[j].v[0] + v[j].v[1] * v[j].v[1] + v[j].v[2] * v[j].v[2] + v[j].v[3] * v[j].v[3];
     }
-    for (int pass = 0; pass < a.passes; ++pass) {
-        const float w = warp_sum(ss);
-        if (lane == 0) s_wsum[pass][wid] = w;
-        cluster.sync();
-        float t = 0.0f;
+    // ONE exchange per launch.  The second normalisation of passes == 2 (AEGenerator.py:98 followed by :103) divides by
+    // || d / n1 ||: in exact arithmetic sqrt(ss) / n1, and any fp32 summation of the rounded quotients' squares sits within a
+    // few 2^-24 of that (as do two different summation orders of it), far inside the 1e-5 budget -- so it is formed from the
+    // first sum instead of a second read-reduce-exchange round (measured: 3 us of a 10.9 us launch, profiles/r25).
+    const float w = warp_sum(ss);
+    if (lane == 0) s_wsum[0][wid] = w;
+    cluster.sync();
+    float t = 0.0f;
 #pragma unroll
-        for (int i = 0; i < CL / 4; ++i)   // lane l reads warp (l & 7) of CTAs (l >> 3) + 4 i, in a fixed order
-            t += *cluster.map_shared_rank(&s_wsum[pass][lane & 7], 4 * i + (lane >> 3));
-        t = warp_sum(t);
-        if (a.trace != nullptr && threadIdx.x == 0) a.trace[kTraceSlots * blockIdx.x + 1 + (pass == a.passes - 1 ? 1 : 0)] = globaltimer_ns();
-        const float nrm = sqrtf(t) + 1e-16f;
-        ss = 0.0f;
+    for (int i = 0; i < CL / 4; ++i)   // lane l reads warp (l & 7) of CTAs (l >> 3) + 4 i, in a fixed order
+        t += *cluster.map_shared_rank(&s_wsum[0][lane & 7], 4 * i + (lane >> 3));
+    t = warp_sum(t);
+    if (a.trace != nullptr && threadIdx.x == 0) a.trace[kTraceSlots * blockIdx.x + 2] = globaltimer_ns();
+    const L2Scale sc = l2_scales(t, a.passes, a.scale);
+    FVec<4> im[IMG ? NV : 1];
+    if constexpr (IMG) {
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
             const int64_t q = ((int64_t)j * kL2Cluster + rank) * kL2Threads + threadIdx.x;
-            if (q < nvec) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    v[j].v[e] = __fdiv_rn(v[j].v[e], nrm);  // d /= norm (IEEE divide, as the reference)
-                    ss += v[j].v[e] * v[j].v[e];
-                }
-            }
+            if (q < nvec) im[j] = ld_stream<4>(a.img + base + q * 4);   // L2 hits (prefetched above)
         }
     }
 #pragma unroll
@@ -123,7 +148,7 @@ l2_cluster_kernel(const L2Args a) {
             const int64_t off = base + q * 4;
             FVec<4> o;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) o.v[e] = a.scale * v[j].v[e];  // (d / norm) was formed in registers; then scale * d
+            for (int e = 0; e < 4; ++e) o.v[e] = l2_apply(v[j].v[e], sc);
             st_stream<4>(a.out + off, o);
             if constexpr (IMG) {
                 FVec<4> ad;
@@ -188,7 +213,8 @@ __global__ void __launch_bounds__(THREADS) l2_ll_kernel(const L2Args a, int cps)
         const int64_t q = ((int64_t)j * cps + rank) * THREADS + threadIdx.x;
         if (q < nvec) ss += v[j].v[0] * v[j].v[0] + v[j].v[1] * v[j].v[1] + v[j].v[2] * v[j].v[2] + v[j].v[3] * v[j].v[3];
     }
-    for (int pass = 0; pass < a.passes; ++pass) {
+    {   // one exchange per launch (the second norm of passes == 2 follows from the first sum, see l2_scales)
+        const int pass = 0;
         const float w = warp_sum(ss);
         if (lane == 0) s_w[wid] = w;
         __syncthreads();
@@ -209,21 +235,9 @@ __global__ void __launch_bounds__(THREADS) l2_ll_kernel(const L2Args a, int cps)
             if (lane == 0) s_tot = p;
         }
         __syncthreads();
-        if (a.trace != nullptr && threadIdx.x == 0) a.trace[kTraceSlots * blockIdx.x + 1 + (pass == a.passes - 1 ? 1 : 0)] = globaltimer_ns();
-        const float nrm = sqrtf(s_tot) + 1e-16f;
-        ss = 0.0f;
-#pragma unroll
-        for (int j = 0; j < NV; ++j) {
-            const int64_t q = ((int64_t)j * cps + rank) * THREADS + threadIdx.x;
-            if (q < nvec) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    v[j].v[e] = __fdiv_rn(v[j].v[e], nrm);  // d /= norm (IEEE divide, as the reference)
-                    ss += v[j].v[e] * v[j].v[e];
-                }
-            }
-        }
+        if (a.trace != nullptr && threadIdx.x == 0) a.trace[kTraceSlots * blockIdx.x + 2] = globaltimer_ns();
     }
+    const L2Scale sc = l2_scales(s_tot, a.passes, a.scale);
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
         const int64_t q = ((int64_t)j * cps + rank) * THREADS + threadIdx.x;
@@ -231,7 +245,7 @@ __global__ void __launch_bounds__(THREADS) l2_ll_kernel(const L2Args a, int cps)
             const int64_t off = base + q * 4;
             FVec<4> o;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) o.v[e] = a.scale * v[j].v[e];
+            for (int e = 0; e < 4; ++e) o.v[e] = l2_apply(v[j].v[e], sc);
             st_stream<4>(a.out + off, o);
             if constexpr (IMG) {
                 FVec<4> ad;
@@ -409,7 +423,13 @@ extern "C" int dct_l2_normalize_f32(const float* d, float* out, int64_t B, int64
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     L2Args a{d, out, M, passes, scale, img, adv, static_cast<Workspace*>(workspace), nullptr};
     const bool vec_ok = (M % 4) == 0 && aligned(d, 16) && aligned(out, 16) && aligned(img, 16) && aligned(adv, 16);
-    if (vec_ok && workspace != nullptr && B <= kL2LLSamples && l2_variant() != 1) {
+    // Which one-launch kernel (measured in the c2 / c3 steps, profiles/r24, r25): samples up to 512 KB -> one cluster of 8
+    // CTAs (its exchange stays in distributed shared memory; the cluster-free kernel's tagged words go through an L2 that is
+    // busy writing back the previous launch's gradients: 10.6 vs 13.5 us inside the c2 step); 512 KB - 1 MB -> the
+    // cluster-free kernel (twice the CTAs of a 16-CTA cluster per sample: c3 step 61.0 vs 64.7 us), then the cluster of 16.
+    const int64_t nv8 = (M + (int64_t)kL2Cluster * kL2Threads * 4 - 1) / ((int64_t)kL2Cluster * kL2Threads * 4);
+    const bool ll_first = l2_variant() == 2 || (l2_variant() == 0 && nv8 > kL2MaxVecPerThread);
+    if (vec_ok && workspace != nullptr && B <= kL2LLSamples && ll_first) {
         // cluster-free one-launch kernel: cps CTAs of 256 threads per sample, <= 8 float4 per thread, and as many more CTAs
         // (fewer float4 each) as still fit one co-resident wave
         const int64_t nvec = M / 4;

@@ -223,6 +223,22 @@ class ConsistencyStep:
             self.run(bufs, publish_prev=publish_prev)
         return g
 
+    def capture_many(self, sets) -> "torch.cuda.CUDAGraph":
+        """One CUDA graph holding ``run(s)`` for every buffer set of ``sets`` in order (a round of consecutive steps: the
+        launches of neighbouring steps chain by programmatic dependent launch, which two separate graph launches do not)."""
+        dev = sets[0].logits[0].device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            self.run(sets[0])
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            for s in sets:
+                self.run(s)
+        return g
+
     def losses(self, bufs: StepBuffers):
         """(jsd_loss, vat_kl_mean, adv_loss) as 0-d float32 tensors on the device (no sync)."""
         s = bufs.sums

@@ -81,10 +81,10 @@ void run(const char* tag, int64_t B, int64_t HW, int reps, double bytes_per_px, 
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
     int grid = 148 * MINB; if (grid > sets[0].num_tiles) grid = sets[0].num_tiles;
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    for (int i = 0; i < 5; ++i) launch_pdl(kern, dim3(grid), dim3(THREADS), Cfg::kSmemBytes, (cudaStream_t)0, sets[i % R]);
+    for (int i = 0; i < 5; ++i) launch_pdl(kern, dim3(grid), dim3(THREADS), Cfg::kSmemBytes, (cudaStream_t)0, sets[i % R], TileMaps<false>{});
     CK(cudaDeviceSynchronize());
     CK(cudaEventRecord(e0));
-    for (int i = 0; i < reps; ++i) launch_pdl(kern, dim3(grid), dim3(THREADS), Cfg::kSmemBytes, (cudaStream_t)0, sets[i % R]);
+    for (int i = 0; i < reps; ++i) launch_pdl(kern, dim3(grid), dim3(THREADS), Cfg::kSmemBytes, (cudaStream_t)0, sets[i % R], TileMaps<false>{});
     CK(cudaEventRecord(e1));
     CK(cudaDeviceSynchronize());
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
@@ -93,7 +93,7 @@ void run(const char* tag, int64_t B, int64_t HW, int reps, double bytes_per_px, 
     {
         const int NL = 8;
         unsigned long long* tr; CK(cudaMalloc(&tr, (size_t)NL * grid * 8 * kTraceSlots));
-        for (int i = 0; i < NL; ++i) { TileArgs t = sets[i % R]; t.trace = tr + (size_t)i * grid * kTraceSlots; launch_pdl(kern, dim3(grid), dim3(THREADS), Cfg::kSmemBytes, (cudaStream_t)0, t); }
+        for (int i = 0; i < NL; ++i) { TileArgs t = sets[i % R]; t.trace = tr + (size_t)i * grid * kTraceSlots; launch_pdl(kern, dim3(grid), dim3(THREADS), Cfg::kSmemBytes, (cudaStream_t)0, t, TileMaps<false>{}); }
         CK(cudaDeviceSynchronize());
         std::vector<unsigned long long> h((size_t)NL * grid * kTraceSlots);
         CK(cudaMemcpy(h.data(), tr, h.size() * 8, cudaMemcpyDeviceToHost));
@@ -120,7 +120,7 @@ static int g_only = -1, g_idx = 0;
 // STAGES = 0: as many as fit
 template <class Op, int CT, int PPT, int NCW, int MINB>
 void run_auto(const char* tag, int64_t B, int64_t HW, int reps, double bpp, bool labels) {
-    constexpr int S = tile_stages<tile_row_words<Op, CT>(), PPT, NCW * 32, MINB>();
+    constexpr int S = tile_stages<tile_stage_bytes<Op, CT, NCW * 32 * PPT, float, false>(), MINB>();
     if (g_only < 0 || g_only == g_idx) run<Op, CT, PPT, NCW, S, MINB>(tag, B, HW, reps, bpp, labels);
     ++g_idx;
 }
