@@ -35,10 +35,27 @@ METRIC = "consistency-loss pixels/sec (fwd+bwd)"
 UNIT = "pixels/s"
 
 
+def csrc_sha16():
+    """Hash of the kernel sources the loaded library was built from (tools/ncu_traffic.py stamps captures with it)."""
+    import hashlib
+    d = os.path.join(ROOT, "deep-co-training-for-semi-supervised-image-segmentation_b200", "csrc")
+    h = hashlib.sha256()
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(f.encode())
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def load_traffic(workload):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json)."""
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json) --
+    only if that capture was taken from the kernel sources this build was made of; else None (traffic is never guessed)."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[workload]
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[workload]
+        if t.get("csrc_sha16") != csrc_sha16():
+            return {"bytes": None, "stale": f"capture {t.get('source')} was taken from other kernel sources "
+                                            f"({t.get('csrc_sha16')} != {csrc_sha16()})"}
+        return t
     except Exception:
         return None
 
@@ -164,20 +181,54 @@ def time_cpu(K, C, B, H, W, cin, steps, warmup, with_vat=True, budget_s=None):
     return Bs * Hs * W * steps / dt, dt / steps, O.num_threads(), sample
 
 
+def reference_staged():
+    """The unmodified reference (baseline/_ref, staged by tools/stage_reference.sh; /root/reference in the build container)."""
+    try:
+        import ref_trainer
+        return ref_trainer if ref_trainer.available() else None
+    except Exception:
+        return None
+
+
+def time_cpu_reference(rt, K, C, B, H, W, cin, steps, warmup, with_vat, with_dice, budget_s):
+    """The reference's OWN modules (generalframework.loss / .metrics / .utils.AEGenerator through oracle/ref_trainer.py) on
+    the host cores, torch intra-op threads = all of them, on a bounded sample of the workload's batch."""
+    import torch
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    dev = torch.device("cpu")
+    _, t_img, _ = rt.time_reference_step(dev, K, C, 1, H, W, cin, steps=1, warmup=1, with_vat=with_vat, with_dice=with_dice)
+    per_step = budget_s / max(steps + warmup, 1)
+    Bs = int(max(1, min(B, per_step / max(t_img, 1e-6))))
+    v, sec, losses = rt.time_reference_step(dev, K, C, Bs, H, W, cin, steps=steps, warmup=warmup, with_vat=with_vat,
+                                            with_dice=with_dice)
+    sample = (f"same step on {Bs} image(s) of {H}x{W} (workload: {B}), {steps} steps, the unmodified reference's modules "
+              f"(JSD_2D, DiceMeter, VATGenerator statics, KL_Divergence_2D) on torch CPU, {threads} intra-op threads")
+    return v, sec, threads, sample
+
+
 def run_reference(args, wl):
-    """--impl reference: the path's CPU implementation on the host cores (oracle port; the reference is
-    pure Python/PyTorch and does not exist on the GPU box), bounded sample of the same workload."""
+    """--impl reference: the path's CPU implementation on the host cores.  The reference is pure Python on PyTorch: when
+    it is staged (baseline/_ref) its own modules run, unmodified (kind "reference"); otherwise the C/OpenMP oracle port
+    (kind "port" -- a FASTER baseline than the real one).  Bounded sample of the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     K, C, B, H, W, cin, desc = wl
-    val, sec, cores, sample = time_cpu(K, C, B, H, W, cin, args.steps, max(args.warmup, 1),
-                                       with_vat=(args.workload != "c1"), budget_s=150.0)
+    with_vat, with_dice = args.workload != "c1", args.workload != "c4"
+    rt = reference_staged()
+    if rt is not None:
+        val, sec, cores, sample = time_cpu_reference(rt, K, C, B, H, W, cin, args.steps, max(min(args.warmup, 2), 1), with_vat,
+                                                     with_dice, budget_s=150.0)
+        kind = "reference"
+    else:
+        val, sec, cores, sample = time_cpu(K, C, B, H, W, cin, args.steps, max(args.warmup, 1), with_vat=with_vat, budget_s=150.0)
+        kind = "port"
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "K": K, "C": C, "H": H, "W": W, "batch_per_gpu": B},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -399,18 +450,32 @@ def run_ours(args, wl):
     e2e = run_e2e(args, dct_b200, step, sets[0], dev, world, n_local, K, C, B, H, W, with_vat, with_dice)
     dct_b200.raise_if_flagged()
     clocks = sampler.stop() if rank == 0 else None
+    steps_per_graph = R if round_graph is not None else (1 if args.graph else 0)
+    del graphs, round_graph, sets
+    torch.cuda.empty_cache()
+    extras = {}
+    if not args.no_extras:
+        extras = run_extras(args, dct_b200, dev, rank, world, local, peak)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, sec, cores, sample = time_cpu(K, C, B, H, W, cin, steps=10, warmup=1, with_vat=with_vat, budget_s=15.0)
+        v, sec, cores, sample = time_cpu(K, C, B, H, W, cin, steps=10, warmup=1, with_vat=with_vat, budget_s=10.0)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        rt = reference_staged()
+        if rt is not None:   # the reference itself is staged: ITS modules are the baseline, the C port is kept beside it
+            try:
+                rv, rsec, rcores, rsample = time_cpu_reference(rt, K, C, B, H, W, cin, 3, 1, with_vat, with_dice, budget_s=20.0)
+                cpu = {"value": rv, "unit": UNIT, "cores": rcores, "kind": "reference", "sample": rsample,
+                       "oracle_port": {"value": v, "cores": cores, "sample": sample}}
+            except Exception as e:
+                cpu["reference_error"] = f"{type(e).__name__}: {e}"
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"{args.workload}: {desc}", "K": K, "C": C, "H": H, "W": W, "batch_per_gpu": B,
                            "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": bool(args.graph),
-                           "steps_per_graph": R if round_graph is not None else (1 if args.graph else 0),
+                           "steps_per_graph": steps_per_graph,
                            "exchange": {"none": "none (1 GPU)", "nccl": "NCCL all-reduce of the loss sums per step (side stream)",
                                         "p2p": "a one-CTA kernel chained to the step's last kernel by programmatic dependent "
                                                "launch stores the loss sums into every rank's mailbox over NVLink peer memory "
@@ -422,11 +487,138 @@ def run_ours(args, wl):
                            "exchange_check": exchange_check,
                            "l2": f"inputs larger than L2: {R} rotating buffer sets of {per_set / 2**20:.0f} MiB inputs"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": step.launches_per_step * args.steps,
-                "roofline": roofline, "cpu_baseline": cpu}
+                "roofline": roofline, "cpu_baseline": cpu, **extras}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bench_workload(dct, name, dev, world, steps, peak):
+    """ms/step and the dominant kernel's roofline fraction of another BASELINE workload (c1 / c3 / c4), same method as the
+    headline: R rotating buffer sets larger than L2, R steps per CUDA graph, CUDA events."""
+    import torch
+    from dct_b200.engine import ConsistencyStep, StepBuffers
+    K, C, B, H, W, cin, desc = WORKLOADS[name]
+    with_vat, with_dice = name != "c1", name != "c4"
+    step = ConsistencyStep(K, C, B, H, W, cin=cin, n_global=B * H * W * world, with_vat=with_vat, with_dice=with_dice)
+    gen = torch.Generator(device=dev).manual_seed(4321)
+    per_set = sum(t.numel() * t.element_size() for t in StepBuffers.allocate(K, C, 1, H, W, cin, dev).input_tensors()) * B
+    R = max(2, min(8, int(1.5e9 // max(per_set, 1)) or 2))
+    sets = [StepBuffers.allocate(K, C, B, H, W, cin, dev, gen) for _ in range(R)]
+    g = step.capture_many(sets)
+    rounds = max(2, steps // R)
+    for _ in range(2):
+        g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(rounds):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / (rounds * R)
+    # the dominant (JSD) launch on its own
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    kg = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(kg, stream=side):
+        for s in sets:
+            step.run_part(s, "jsd")
+    kg.replay()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(rounds):
+        kg.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    k_ms = e0.elapsed_time(e1) / (rounds * R)
+    pb = step.part_bytes()
+    out = {"workload": f"{name}: {desc}", "value": B * H * W * 1e3 / ms, "unit": UNIT, "ms_per_step": ms, "steps": rounds * R,
+           "step_achieved_GBps": sum(pb.values()) / (ms * 1e-3) / 1e9, "step_frac": sum(pb.values()) / (ms * 1e-3) / 1e9 / peak,
+           "dominant_kernel_ms": k_ms, "dominant_kernel_frac": pb["jsd"] / (k_ms * 1e-3) / 1e9 / peak,
+           "n_gpus": world, "per_gpu": True}
+    del g, kg, sets
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_extras(args, dct, dev, rank, world, local, peak):
+    """The rest of BASELINE.json's metric in the same JSON line: the reference's stock ATen composition of the step on this
+    GPU (the meaningful speed-up denominator), co-training iterations/s (the reference's own trainer stock vs
+    with the drop-ins installed at N = 1; the DDP engine and the networks-alone floor at every N), and the other workloads."""
+    import torch
+    import torch.distributed as dist
+    K, C, B, H, W, cin, desc = WORKLOADS[args.workload]
+    with_vat, with_dice = args.workload != "c1", args.workload != "c4"
+    out = {}
+    rt = reference_staged()
+    # ---- the step through the reference's own modules on this GPU
+    if rank == 0:
+        if rt is not None:
+            try:
+                v, sec, losses = rt.time_reference_step(dev, K, C, B, H, W, cin, steps=3, warmup=1, with_vat=with_vat,
+                                                        with_dice=with_dice)
+                out["aten_gpu_baseline"] = {"value": v, "unit": UNIT, "ms_per_step": sec * 1e3, "steps": 3, "kind": "reference",
+                                            "what": "the same step through the unmodified reference's modules (DiceMeter.add x K, "
+                                                    "JSD_2D, VATGenerator statics, KL_Divergence_2D, autograd backward) in stock "
+                                                    "ATen on this GPU, inputs resident in HBM, losses + Dice rows read back",
+                                            "last_losses": losses}
+            except Exception as e:
+                out["aten_gpu_baseline"] = {"unavailable": f"{type(e).__name__}: {e}"}
+        else:
+            out["aten_gpu_baseline"] = {"unavailable": "reference not staged (tools/stage_reference.sh -> baseline/_ref)"}
+    torch.cuda.empty_cache()
+    if world > 1:
+        dist.barrier()
+    # ---- co-training iterations/s
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import cotrain_bench as cb
+    cot = {}
+    for cfg_name, iters, warm in (("c1", 20, 3), (args.workload if args.workload != "c1" else "c3", 4 if args.workload == "c2" else 8, 1)):
+        entry = {}
+        try:
+            lines = cb.measure(cfg_name, ["ours", "nets"], iters, warm, dev, rank, world, local)
+            for ln in lines:
+                entry["engine_ddp" if ln["arm"] == "ours" else "networks_alone"] = {"it_per_s": ln["value"], "ms_per_iter": ln["ms_per_iter"]}
+            entry["config"] = lines[0]["config"]
+            entry["images_per_iter_per_gpu"] = lines[0]["images_per_iter_per_gpu"]
+        except Exception as e:
+            entry["engine_error"] = f"{type(e).__name__}: {e}"
+        if world == 1 and rt is not None:
+            Kc, Cc, cinc, Hc, Wc, BL, BU = cb.CONFIGS[cfg_name]
+            if cinc == 1 and Cc == 4:   # the reference trainer's validation loop hard-codes C = 4 and its datasets are grey-scale
+                try:
+                    kw = dict(iters=iters if cfg_name == "c1" else 3, K=Kc, arch=cb.REF_ARCH[cfg_name], C=Cc, B=BL, H=Hc, W=Wc,
+                              train_jsd=True, train_adv=True, deterministic=False, warmup_iters=1)
+                    stock = rt.run_train_loop(dev, False, **kw)
+                    drop = rt.run_train_loop(dev, True, **kw)
+                    entry["reference_trainer_stock"] = {"it_per_s": stock["it_per_s"], "iters": stock["iters"]}
+                    entry["reference_trainer_with_dropins"] = {"it_per_s": drop["it_per_s"], "iters": drop["iters"],
+                                                               "first_total_loss_rel_diff": float(abs(drop["total_loss"][0] - stock["total_loss"][0]) / abs(stock["total_loss"][0]))}
+                except Exception as e:
+                    entry["reference_trainer_error"] = f"{type(e).__name__}: {e}"
+        cot[cfg_name] = entry
+        torch.cuda.empty_cache()
+    out["cotrain_it_s"] = cot
+    # ---- the other workloads of BASELINE.json (per-GPU numbers; at N > 1 every rank runs them, rank 0 reports)
+    others = {}
+    for name in ("c1", "c3", "c4"):
+        if name == args.workload:
+            continue
+        try:
+            others[name] = bench_workload(dct, name, dev, world, 240 if name != "c4" else 60, peak)
+        except Exception as e:
+            others[name] = {"error": f"{type(e).__name__}: {e}"}
+        if world > 1:
+            v = torch.tensor([others[name].get("ms_per_step", 0.0)], dtype=torch.float64, device=dev)
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+            if "ms_per_step" in others[name]:
+                Kx, Cx, Bx, Hx, Wx, _, _ = WORKLOADS[name]
+                others[name]["ms_per_step_max_over_ranks"] = float(v.item())
+                others[name]["value_all_gpus"] = Bx * Hx * Wx * world * 1e3 / float(v.item())
+    out["other_workloads"] = others
+    return out
 
 
 def run_e2e(args, dct, step, dev_set, dev, world, n_local, K, C, B, H, W, with_vat, with_dice=True):
@@ -497,29 +689,79 @@ def run_e2e(args, dct, step, dev_set, dev, world, n_local, K, C, B, H, W, with_v
         freed[j].record(cur)
 
     steps = max(3, min(args.steps, args.e2e_steps))
-    for j in range(nbuf):
-        freed[j].record(torch.cuda.current_stream(dev))
-    for i in range(3):  # warm-up
-        upload(i); compute(i)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    upload(0)
-    for i in range(steps):
-        if i + 1 < steps:
-            upload(i + 1)
-        compute(i)
-    torch.cuda.synchronize()
-    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    dt = float(dt.item())
-    return {"value": n_glob * steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "steps": steps, "ms_per_step": dt / steps * 1e3,
-            "api": "jsd_consistency_from_logits + DiceMeter.add_counts + l2_normalize + kl_div_with_logit + "
-                   "kl_consistency_from_logits (autograd), pinned host inputs, double-buffered H2D",
-            "last_losses": [float(v) for v in out_host[:3]]}
+
+    def timed(fn_upload, fn_compute):
+        for j in range(nbuf):
+            freed[j].record(torch.cuda.current_stream(dev))
+        for i in range(3):  # warm-up
+            fn_upload(i); fn_compute(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        fn_upload(0)
+        for i in range(steps):
+            if i + 1 < steps:
+                fn_upload(i + 1)
+            fn_compute(i)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return float(dt.item())
+
+    dt = timed(upload, compute)
+
+    # The same uploads with NO compute behind them: what the host link alone sustains with N ranks copying at once.  When
+    # the end-to-end step time equals this, the limiter is the host side (PCIe / host DRAM shared by the N GPUs), not a kernel.
+    def no_compute(i):
+        j = i % nbuf
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(ready[j])
+        freed[j].record(cur)
+
+    dt_copy = timed(upload, no_compute)
+    res = {"value": n_glob * steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "steps": steps, "ms_per_step": dt / steps * 1e3, "h2d_GBps_per_gpu": h2d * steps / dt / 1e9,
+           "copy_only": {"ms_per_step": dt_copy / steps * 1e3, "h2d_GBps_per_gpu": h2d * steps / dt_copy / 1e9,
+                         "what": "the same pinned-memory uploads with no kernels behind them, all ranks at once (max over ranks)"},
+           "api": "jsd_consistency_from_logits + DiceMeter.add_counts + l2_normalize + kl_div_with_logit + "
+                  "kl_consistency_from_logits (autograd), pinned host inputs, double-buffered H2D",
+           "last_losses": [float(v) for v in out_host[:3]]}
+
+    # bf16 variant (networks under autocast hand the path bf16 logits): the [B,C,H,W] tensors travel as 2-byte elements
+    # (images, the VAT direction and the int64 labels as they are), fp32 math in the kernels, bf16 gradients.
+    try:
+        is_big = [t.is_floating_point() and t.dim() == 4 and t.shape[1] == C and C > 1 for t in host]
+        host16 = [t.to(torch.bfloat16).pin_memory() if big else t for t, big in zip(host, is_big)]
+        # the detached target must stay a simplex to 1e-5 after rounding (the reference's own assert): a one-hot target does
+        host16[K + 6] = torch.nn.functional.one_hot(host[K + 6].argmax(1), C).permute(0, 3, 1, 2).contiguous().to(torch.bfloat16).pin_memory()
+        slots16 = [[torch.empty_like(t, device=dev) for t in host16] for _ in range(nbuf)]
+        h2d16 = sum(t.numel() * t.element_size() for t in host16)
+
+        def upload16(i):
+            j = i % nbuf
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(freed[j])
+                for dst, src in zip(slots16[j], host16):
+                    dst.copy_(src, non_blocking=True)
+                ready[j].record(copy_stream)
+
+        def compute16(i):
+            nonlocal slots
+            keep, slots = slots, slots16
+            try:
+                compute(i)
+            finally:
+                slots = keep
+
+        dt16 = timed(upload16, compute16)
+        res["bf16"] = {"value": n_glob * steps / dt16, "unit": UNIT, "h2d_bytes_per_step": h2d16, "ms_per_step": dt16 / steps * 1e3,
+                       "h2d_GBps_per_gpu": h2d16 * steps / dt16 / 1e9, "last_losses": [float(v) for v in out_host[:3]],
+                       "what": "same step, logits / probabilities as bfloat16 in host memory and on the device"}
+    except Exception as e:
+        res["bf16"] = {"error": f"{type(e).__name__}: {e}"}
+    return res
 
 
 def main():
@@ -534,6 +776,8 @@ def main():
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "p2p-deferred", "p2p-fused", "nccl"],
                     help="N > 1: how the loss sums cross ranks (auto = p2p, NCCL if peer mapping is refused)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip aten_gpu_baseline / cotrain_it_s / other_workloads (developer A/B runs)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

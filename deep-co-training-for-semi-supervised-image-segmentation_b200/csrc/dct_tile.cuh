@@ -30,6 +30,8 @@
 #pragma once
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "dct_common.cuh"
 #include "dct_tma.cuh"
 #include "dct_tmap.cuh"
@@ -128,6 +130,7 @@ struct TileArgs {
     int tiles_per_image;
     int num_tiles;
     int pool_div;                  // developer knob: the tail pool is 1/pool_div of every CTA's range (0 = default 5)
+    int prefetch;                  // tiles of this CTA's range whose rows are prefetched into L2 before the dependency wait (DCT_TILE_PREFETCH)
     int force_static;              // developer switch (tools/kbench_tile.cu): 1 = no tail pool (purely static contiguous ranges) even with a workspace
     unsigned long long* trace;     // developer tracing: kTraceSlots words per CTA (start, first tile landed, -, end) in ns; null in the product
 };
@@ -274,6 +277,39 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
         }
     }
     __syncthreads();
+    // Ramp hiding.  This CTA's first tiles are known before anything of the previous grid is (contiguous static ranges), so
+    // their rows are pulled into L2 while that grid is still draining: resident since its first CTAs left, this grid would
+    // otherwise idle in the dependency wait and then pay a cold DRAM round trip for its first stage (first data 1.6-2.5 us
+    // after the wait, profiles/r26).  A prefetch moves no value into the SM: ordering against the previous grid's writes is
+    // untouched (L2 is the point of coherence; a line it still rewrites is simply updated in place).
+    if (a.prefetch > 0 && tid == CTHREADS) {
+        const int per = a.num_tiles / (int)gridDim.x, extra = a.num_tiles % (int)gridDim.x;
+        const int my_begin = (int)blockIdx.x * per + min((int)blockIdx.x, extra);
+        const int my_n = per + ((int)blockIdx.x < extra ? 1 : 0);
+        const int npre = min(min(a.prefetch, STAGES), my_n);
+        for (int s = 0; s < npre; ++s) {
+            const int tile = my_begin + s, b = tile / tpi;
+            const int64_t off = (int64_t)(tile - b * tpi) * TP;
+            const int64_t rem = HW - off;
+            const uint32_t npix = (uint32_t)(rem < TP ? rem : TP);
+            if constexpr (TMAP) {
+#pragma unroll
+                for (int n = 0; n < NIN; ++n) tma::tensor_prefetch_3d(&maps.in[n], (int)off, 0, b);
+            } else {
+#pragma unroll
+                for (int n = 0; n < NIN; ++n)
+#pragma unroll
+                    for (int c = 0; c < C; ++c)
+                        tma::bulk_prefetch_l2(static_cast<const ET*>(a.in[n]) + ((int64_t)b * C + c) * HW + off, npix * (uint32_t)ES);
+            }
+            if constexpr (LROW) {
+                if (do_lab) tma::bulk_prefetch_l2(a.labels + (int64_t)b * HW + off, 8u * npix);
+            }
+            if constexpr (Op::GMAP) {
+                if (has_gmap) tma::bulk_prefetch_l2(a.up.gmap + (int64_t)b * HW + off, 4u * npix);
+            }
+        }
+    }
     pdl_wait();               // the previous grid has completed and its writes are visible (no-op without PDL)
     if (a.trace != nullptr && tid == 0) a.trace[kTraceSlots * blockIdx.x] = globaltimer_ns();
     if constexpr (DICE) {
@@ -305,6 +341,9 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
         const int pool_q = dynamic ? per / (a.pool_div > 0 ? a.pool_div : 5) : 0;             // pool tiles taken from the end of every CTA's range
         const int my_static = my_n - pool_q;
         int draws = 0;
+        // (A tapered look-ahead -- fewer loads in flight per CTA the deeper a draw lands in the pool, so that the last tiles
+        // stay unclaimed for whichever CTA frees up first -- was measured and removed: the end spread did not shrink and the
+        // thinner pipelines cost bandwidth: c2 step 102.3 -> 109.8 us, profiles/r30/ab_taper.log.)
         auto draw = [&]() -> int {  // next tile index for this CTA; >= num_tiles when there is no more work
             int t;
             if (draws < my_static) t = my_begin + draws;
@@ -823,6 +862,14 @@ int tile_launch_ct(TileArgs a, int64_t B, cudaStream_t stream) {
     }
     a.tiles_per_image = (int)((a.HW + Cfg::TP - 1) / Cfg::TP);
     a.num_tiles = (int)(a.tiles_per_image * B);
+    {   // schedule knobs (developer A/B through the environment; the defaults are the measured product choice)
+        static const int env_pool = [] { const char* e = std::getenv("DCT_TILE_POOL_DIV"); return e ? std::atoi(e) : 0; }();
+        static const int env_pre = [] { const char* e = std::getenv("DCT_TILE_PREFETCH"); return e ? std::atoi(e) : -1; }();
+        // 2 tiles per CTA (measured, profiles/r30/ab_prefetch.log: c2 step 102.3 -> 101.9 us, c3 52.6 -> 51.8, c1 11.3 -> 10.5;
+        // 4 or 8 tiles queue so much ahead of the first real loads that the short KL launches get slower)
+        a.prefetch = env_pre >= 0 ? env_pre : 2;
+        if (env_pool > 0 && a.pool_div == 0) a.pool_div = env_pool;
+    }
     int grid = kSMs * MINB;
     if (grid > a.num_tiles) grid = a.num_tiles;
     if (a.trace == nullptr) a.trace = trace_next(grid);

@@ -49,6 +49,11 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, 
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// hint: pull [gmem_src, gmem_src + bytes) into L2 (no destination, no completion to wait for).  L2 is the point of coherence,
+// so a prefetch is safe even for memory another grid may still be writing: it can only turn out to be useless.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
 // shared -> global bulk copy, tracked by the thread's bulk async-group
 __device__ __forceinline__ void bulk_store(void* gmem_dst, const void* smem_src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),

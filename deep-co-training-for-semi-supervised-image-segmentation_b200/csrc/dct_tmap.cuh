@@ -33,6 +33,12 @@ __device__ __forceinline__ void tensor_store_3d(const CUtensorMap* map, int x, i
                  "r"(x), "r"(y), "r"(z), "r"(smem_u32(smem_src))
                  : "memory");
 }
+// hint: pull the box at {x, y, z} into L2 (see bulk_prefetch_l2)
+__device__ __forceinline__ void tensor_prefetch_3d(const CUtensorMap* map, int x, int y, int z) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(map)),
+                 "r"(x), "r"(y), "r"(z)
+                 : "memory");
+}
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }

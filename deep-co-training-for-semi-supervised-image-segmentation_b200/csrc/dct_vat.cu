@@ -36,6 +36,7 @@ struct L2Args {
     float* adv;        // nullable
     Workspace* ws;
     unsigned long long* trace;   // developer tracing (dct_common.cuh, trace_next); null in the product
+    int prefetch;                // 1: the sample's lines are pulled into L2 before the dependency wait (DCT_L2_PREFETCH)
 };
 
 __device__ __forceinline__ float block_sum_f(float v, float* s_warp) {
@@ -99,6 +100,15 @@ l2_cluster_kernel(const L2Args a) {
     const int64_t nvec = a.M / 4;
     FVec<4> v[NV];
     float ss = 0.0f;
+    if (a.prefetch && (threadIdx.x & 7) == 0) {
+        // ramp hiding (see dct_tile.cuh): this CTA's lines of `d` go to L2 while the previous grid drains; a prefetch moves
+        // no value into the SM, so the ordering against that grid's writes is untouched
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int64_t q = ((int64_t)j * kL2Cluster + rank) * kL2Threads + threadIdx.x;
+            if (q < nvec) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.d + base + q * 4));
+        }
+    }
     pdl_wait();
     if (a.trace != nullptr && threadIdx.x == 0) a.trace[kTraceSlots * blockIdx.x] = globaltimer_ns();
 #pragma unroll
@@ -196,6 +206,16 @@ __global__ void __launch_bounds__(THREADS) l2_ll_kernel(const L2Args a, int cps)
     const int64_t nvec = a.M / 4;
     FVec<4> v[NV];
     FVec<4> im[IMG ? NV : 1];
+    if (a.prefetch && (threadIdx.x & 7) == 0) {   // ramp hiding, as in the cluster kernel
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int64_t q = ((int64_t)j * cps + rank) * THREADS + threadIdx.x;
+            if (q < nvec) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.d + base + q * 4));
+                if constexpr (IMG) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.img + base + q * 4));
+            }
+        }
+    }
     pdl_wait();
     if (a.trace != nullptr && threadIdx.x == 0) a.trace[kTraceSlots * blockIdx.x] = globaltimer_ns();
     const unsigned int epoch = __ldcg(&a.ws->l2_epoch);
@@ -290,13 +310,12 @@ static int l2_variant() {
     return v;
 }
 
-// ---- large / odd samples: grid-wide passes through the workspace ------------------------------------------------------
-// Workspace layout of this path: sample b owns kL2Stride(gx) = gx + 2 doubles: [0, gx) one partial per CTA of its row of the
-// grid, [gx] and [gx + 1] two norm slots (a double holding the float `sqrtf((float)sum) + 1e-16f`).  Pass p reads slot
-// p & 1 and, when another normalisation follows, writes slot (p + 1) & 1: a CTA that starts late never sees the new norm.
-// The CTA that draws the last ticket of a launch adds every sample's partials in a fixed order (one warp per sample: lane l
-// takes partials l, l + 32, ...; shuffle tree) -- deterministic -- and re-arms the ticket.
-__device__ __forceinline__ void l2_finish_norms(double ss, Workspace* ws, int gx, int slot) {
+// ---- large / odd samples: two grid-wide launches through the workspace ------------------------------------------------
+// Workspace layout of this path: sample b owns gx + 1 doubles: [0, gx) one partial per CTA of its row of the grid, [gx] the
+// sample's sum of squares (as the float the scale launch works with).  The CTA that draws the last ticket of the first
+// launch adds every sample's partials in a fixed order (one warp per sample: lane l takes partials l, l + 32, ...; shuffle
+// tree) -- deterministic -- and re-arms the ticket.
+__device__ __forceinline__ void l2_finish_sums(double ss, Workspace* ws, int gx) {
     __shared__ double s_warp[8];
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -306,7 +325,7 @@ __device__ __forceinline__ void l2_finish_norms(double ss, Workspace* ws, int gx
     if (threadIdx.x == 0) {
         double t = 0.0;
         for (int w = 0; w < 8; ++w) t += s_warp[w];
-        ws->partials[(size_t)blockIdx.y * (gx + 2) + blockIdx.x] = t;
+        ws->partials[(size_t)blockIdx.y * (gx + 1) + blockIdx.x] = t;
         __threadfence();
         const unsigned int ticket = atomicAdd(&ws->ticket, 1u);
         s_last = ticket == gridDim.x * gridDim.y - 1u;
@@ -315,23 +334,24 @@ __device__ __forceinline__ void l2_finish_norms(double ss, Workspace* ws, int gx
     if (!s_last) return;
     __threadfence();
     for (int b = wid; b < (int)gridDim.y; b += 8) {
-        const double* part = ws->partials + (size_t)b * (gx + 2);
+        const double* part = ws->partials + (size_t)b * (gx + 1);
         double t = 0.0;
         for (int i = lane; i < gx; i += 32) t += __ldcg(part + i);
         t = warp_sum(t);
-        if (lane == 0) ws->partials[(size_t)b * (gx + 2) + gx + slot] = (double)(sqrtf((float)t) + 1e-16f);
+        if (lane == 0) ws->partials[(size_t)b * (gx + 1) + gx] = (double)(float)t;
     }
     __syncthreads();
     if (threadIdx.x == 0) { __threadfence(); ws->ticket = 0u; }
 }
 
-// pass A: sum of squares of d -> norms.  VEC = 4: 128-bit streaming loads (M % 4 == 0, 16-byte aligned rows)
+// launch A: sum of squares of every sample.  VEC = 4: 128-bit streaming loads (M % 4 == 0, 16-byte aligned rows)
 template <int VEC>
-__global__ void __launch_bounds__(256) l2_sumsq_kernel(const float* __restrict__ d, int64_t M, Workspace* ws, int gx) {
+__global__ void __launch_bounds__(256) l2_sumsq_kernel(const L2Args a, int gx) {
     pdl_wait();
-    const float* x = d + (int64_t)blockIdx.y * M;
+    if (a.trace != nullptr && threadIdx.x == 0) a.trace[kTraceSlots * (blockIdx.y * gridDim.x + blockIdx.x)] = globaltimer_ns();
+    const float* x = a.d + (int64_t)blockIdx.y * a.M;
     double ss = 0.0;
-    const int64_t n = M / VEC;
+    const int64_t n = a.M / VEC;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const FVec<VEC> v = ld_stream<VEC>(x + i * VEC);
         float s = 0.0f;
@@ -340,29 +360,24 @@ __global__ void __launch_bounds__(256) l2_sumsq_kernel(const float* __restrict__
         ss += (double)s;
     }
     pdl_launch_dependents();
-    l2_finish_norms(ss, ws, gx, 0);
+    l2_finish_sums(ss, a.ws, gx);
+    if (a.trace != nullptr && threadIdx.x == 0) a.trace[kTraceSlots * (blockIdx.y * gridDim.x + blockIdx.x) + 3] = globaltimer_ns();
 }
 
-// pass B: out = scale * (d / norm) [, adv = clamp(img + out, 0, 1)]; NEXT: also the sum of squares of (d / norm) -> the
-// norms of the next normalisation pass (normalise(normalise(d)), AEGenerator.py:98 + :103) without another read pass.
-template <int VEC, bool NEXT>
-__global__ void __launch_bounds__(256) l2_scale_kernel(const L2Args a, int gx, int slot) {
+// launch B: out = scale * d / n1 [/ n2] [, adv = clamp(img + out, 0, 1)] -- both normalisations of passes == 2 in one sweep
+// (the second norm follows from the first sum, l2_scales): d is read twice and written once per call, whatever `passes`.
+template <int VEC>
+__global__ void __launch_bounds__(256) l2_scale_kernel(const L2Args a, int gx) {
     pdl_wait();
+    if (a.trace != nullptr && threadIdx.x == 0) a.trace[kTraceSlots * (blockIdx.y * gridDim.x + blockIdx.x)] = globaltimer_ns();
     const int64_t base = (int64_t)blockIdx.y * a.M;
-    const float nrm = (float)__ldcg(&a.ws->partials[(size_t)blockIdx.y * (gx + 2) + gx + slot]);
-    double ss = 0.0;
+    const L2Scale sc = l2_scales((float)__ldcg(&a.ws->partials[(size_t)blockIdx.y * (gx + 1) + gx]), a.passes, a.scale);
     const int64_t n = a.M / VEC;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t off = base + i * VEC;
         FVec<VEC> v = ld_stream<VEC>(a.d + off), o;
-        float s = 0.0f;
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-            const float q = __fdiv_rn(v.v[e], nrm);  // d /= norm (IEEE divide, as the reference)
-            s = fmaf(q, q, s);
-            o.v[e] = a.scale * q;                    // scale == 1 on all but the last pass
-        }
-        ss += (double)s;
+        for (int e = 0; e < VEC; ++e) o.v[e] = l2_apply(v.v[e], sc);
         st_stream<VEC>(a.out + off, o);
         if (a.img != nullptr) {
             const FVec<VEC> im = ld_stream<VEC>(a.img + off);
@@ -373,7 +388,7 @@ __global__ void __launch_bounds__(256) l2_scale_kernel(const L2Args a, int gx, i
         }
     }
     pdl_launch_dependents();
-    if constexpr (NEXT) l2_finish_norms(ss, a.ws, gx, slot ^ 1);
+    if (a.trace != nullptr && threadIdx.x == 0) a.trace[kTraceSlots * (blockIdx.y * gridDim.x + blockIdx.x) + 3] = globaltimer_ns();
 }
 
 template <int VEC>
@@ -421,7 +436,8 @@ extern "C" int dct_l2_normalize_f32(const float* d, float* out, int64_t B, int64
     if ((img == nullptr) != (adv == nullptr)) return DCT_ERR_BAD_ARG;
     if (!aligned(d, 4) || !aligned(out, 4) || !aligned(img, 4) || !aligned(adv, 4)) return DCT_ERR_MISALIGNED;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    L2Args a{d, out, M, passes, scale, img, adv, static_cast<Workspace*>(workspace), nullptr};
+    static const int env_pre = [] { const char* e = std::getenv("DCT_L2_PREFETCH"); return e ? std::atoi(e) : 1; }();   // on: c2 l2 launches 5.93 -> 5.47 / 9.95 -> 8.64 us (profiles/r30)
+    L2Args a{d, out, M, passes, scale, img, adv, static_cast<Workspace*>(workspace), nullptr, env_pre};
     const bool vec_ok = (M % 4) == 0 && aligned(d, 16) && aligned(out, 16) && aligned(img, 16) && aligned(adv, 16);
     // Which one-launch kernel (measured in the c2 / c3 steps, profiles/r24, r25): samples up to 512 KB -> one cluster of 8
     // CTAs (its exchange stays in distributed shared memory; the cluster-free kernel's tagged words go through an L2 that is
@@ -488,35 +504,25 @@ extern "C" int dct_l2_normalize_f32(const float* d, float* out, int64_t B, int64
         return check_launch();
     }
     if (workspace == nullptr) return DCT_ERR_BAD_ARG;
-    if (B > 65535 || B > kMaxPartials / 3) return DCT_ERR_UNSUPPORTED;
+    if (B > 65535 || B > kMaxPartials / 2) return DCT_ERR_UNSUPPORTED;
     // CTAs per sample: about eight 256-thread CTAs per SM over the whole grid, grid-stride loops inside
     const int vec = vec_ok ? 4 : 1;
     int64_t gx = (kSMs * 8 + B - 1) / B;
     const int64_t need = (M / vec + 255) / 256;
     if (gx > need) gx = need;
-    const int64_t cap = kMaxPartials / B - 2;
+    const int64_t cap = kMaxPartials / B - 1;
     if (gx > cap) gx = cap;
     if (gx < 1) gx = 1;
     const dim3 grid((unsigned)gx, (unsigned)B), block(256);
-    cudaError_t e = vec_ok ? launch_pdl(l2_sumsq_kernel<4>, grid, block, 0, s, d, M, a.ws, (int)gx)
-                           : launch_pdl(l2_sumsq_kernel<1>, grid, block, 0, s, d, M, a.ws, (int)gx);
+    L2Args a1 = a, a2 = a;
+    a1.trace = trace_next((int)(gx * B));
+    cudaError_t e = vec_ok ? launch_pdl(l2_sumsq_kernel<4>, grid, block, 0, s, a1, (int)gx)
+                           : launch_pdl(l2_sumsq_kernel<1>, grid, block, 0, s, a1, (int)gx);
     if (e != cudaSuccess) { g_last_cuda_error = e; return DCT_ERR_CUDA; }
-    for (int pass = 0; pass < passes; ++pass) {
-        // one launch per pass; intermediate passes write the unscaled result to `out`, continue from there, and also
-        // produce the next pass's norms (no separate sum-of-squares read)
-        const bool last = (pass == passes - 1);
-        L2Args p = a;
-        p.d = (pass == 0) ? d : out;
-        p.scale = last ? scale : 1.0f;
-        p.img = last ? img : nullptr;
-        p.adv = last ? adv : nullptr;
-        const int slot = pass & 1;
-        if (vec_ok) e = last ? launch_pdl(l2_scale_kernel<4, false>, grid, block, 0, s, p, (int)gx, slot)
-                             : launch_pdl(l2_scale_kernel<4, true>, grid, block, 0, s, p, (int)gx, slot);
-        else e = last ? launch_pdl(l2_scale_kernel<1, false>, grid, block, 0, s, p, (int)gx, slot)
-                      : launch_pdl(l2_scale_kernel<1, true>, grid, block, 0, s, p, (int)gx, slot);
-        if (e != cudaSuccess) { g_last_cuda_error = e; return DCT_ERR_CUDA; }
-    }
+    a2.trace = trace_next((int)(gx * B));
+    e = vec_ok ? launch_pdl(l2_scale_kernel<4>, grid, block, 0, s, a2, (int)gx)
+               : launch_pdl(l2_scale_kernel<1>, grid, block, 0, s, a2, (int)gx);
+    if (e != cudaSuccess) { g_last_cuda_error = e; return DCT_ERR_CUDA; }
     return check_launch();
 }
 

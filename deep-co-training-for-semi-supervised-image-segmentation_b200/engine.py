@@ -99,11 +99,11 @@ class ConsistencyStep:
         self._pub_stream = None
         self._h = _lib.lib()
         # kernels launched per run(): the JSD kernel (Dice fused for C <= 4, else K counting launches), the two KL kernels,
-        # the two normalisations (one cluster launch each up to 16 x 256 x 64 floats per sample, else sum-of-squares +
-        # one launch per pass), the publication kernel of a chained / deferred exchange
+        # the two normalisations (one launch each up to 16 x 256 x 64 floats per sample, else a sum-of-squares launch + a
+        # scale launch each), the publication kernel of a chained / deferred exchange
         big = (self.M > 16 * 256 * 64) or (self.M % 4 != 0)   # (a cluster of 16 CTAs serves samples up to 1 MB)
         self.launches_per_step = 1 + (0 if (not with_dice or (C <= 4 and K * C <= 16)) else K) + \
-            ((2 + (3 + 2 if big else 2)) if with_vat else 0) + \
+            ((2 + (2 + 2 if big else 2)) if with_vat else 0) + \
             (1 if (exchange is not None and (not with_vat or exchange_mode != "fused")) else 0)
 
     # bytes that MUST move per step (algorithmic, fp32): see DESIGN.md "Algorithmic bytes"

@@ -76,7 +76,8 @@ class SynthSet(torch.utils.data.Dataset):
 
 
 def run_train_loop(device, use_dropins, iters=3, K=2, arch="enet", C=4, B=4, H=256, W=256, seed=1234, train_jsd=True,
-                   train_adv=True, cot_weight=0.5, adv_weight=0.05, eps=0.03, deterministic=True, warmup_iters=0):
+                   train_adv=True, cot_weight=0.5, adv_weight=0.05, eps=0.03, deterministic=True, warmup_iters=0,
+                   keep_inputs=0):
     """One truncated epoch of the reference's co-training loop, stock (``use_dropins=False``) or after
     ``dct_b200.install()``.  Returns a dict of recorded values (numpy) and timings."""
     ref_shim.install()
@@ -118,7 +119,7 @@ def run_train_loop(device, use_dropins, iters=3, K=2, arch="enet", C=4, B=4, H=2
                            cot_scheduler_dict=const(cot_weight), adv_training_dict={"eplision": eps}, use_tqdm=True)
 
     # ---- recorders (monkey-patches of module globals / torch; restored below; the reference files are not touched)
-    losses, rows, stamps = [], [], []
+    losses, rows, meter_inputs = [], [], []
     orig_backward = torch.Tensor.backward
     orig_tqdm = ct.tqdm_
     Meter = ct.DiceMeter
@@ -127,6 +128,8 @@ def run_train_loop(device, use_dropins, iters=3, K=2, arch="enet", C=4, B=4, H=2
         def add(self, pred_logit, gt):
             super().add(pred_logit, gt)
             rows.append(self.diceLog[-1].detach().clone())
+            if len(meter_inputs) < keep_inputs:   # the first adds' inputs, for the near-tie analysis of the GPU test
+                meter_inputs.append((pred_logit.detach().clone(), gt.detach().clone()))
 
     def rec_backward(self, *a, **k):
         losses.append(self.detach().clone())
@@ -161,8 +164,81 @@ def run_train_loop(device, use_dropins, iters=3, K=2, arch="enet", C=4, B=4, H=2
     total = [float(v) for v in losses[per_iter - 1::per_iter]]
     return {"total_loss": np.asarray(total, dtype=np.float64),
             "all_backward_losses": np.asarray([float(v) for v in losses], dtype=np.float64),
-            "dice_rows": [r.float().cpu().numpy() for r in rows],
+            "dice_rows": [r.float().cpu().numpy() for r in rows], "meter_inputs": meter_inputs,
             "lab_dice": lab_dice.detach().cpu().numpy(), "unlab_dice": unlab_dice.detach().cpu().numpy(),
             "seconds": dt, "iters": iters, "it_per_s": iters / dt,
             "meter_class": f"{Meter.__module__}.{Meter.__name__}",
             "jsd_class": f"{type(criterions['jsd']).__module__}.{type(criterions['jsd']).__name__}"}
+
+
+# ----------------------------------------------------------------------------------------------------
+# The consistency STEP of bench.py through the reference's own modules (stock ATen composition), on any device
+# ----------------------------------------------------------------------------------------------------
+def reference_step_inputs(device, K, C, B, H, W, cin, seed=1234):
+    """The synthetic tensors of one step, same distributions as engine.StepBuffers.allocate."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    rn = lambda *s: torch.randn(*s, generator=g)  # noqa: E731
+    t = {"logits": [3 * rn(B, C, H, W) for _ in range(K)],
+         "labels": torch.randint(0, C, (B, 1, H, W), generator=g),
+         "d": rn(B, cin, H, W), "d_grad": rn(B, cin, H, W), "img": torch.rand(B, cin, H, W, generator=g),
+         "yhat": 3 * rn(B, C, H, W), "adv": 3 * rn(B, C, H, W), "real": torch.softmax(3 * rn(B, C, H, W), 1)}
+    mv = lambda x: [v.to(device) for v in x] if isinstance(x, list) else x.to(device)  # noqa: E731
+    return {k: mv(v) for k, v in t.items()}
+
+
+def reference_step(inp, with_vat=True, with_dice=True, xi=1e-6, eps=10.0):
+    """One pass of the hot path exactly as the reference composes it, with the reference's own classes:
+    ``unlabdiceMeters[k].add(prob_k, gt)`` x K -> ``JSD_2D(probs).mean()`` (cotraining_totalloss.py:223-226); the VAT
+    arithmetic (AEGenerator.py:97-117: ``_l2_normalize`` x 3, ``kl_div_with_logit(...).mean().backward()``); the
+    adversarial ``KL_Divergence_2D(reduce=True)`` (:391-392); backward; losses and Dice rows read back to the host.
+    The network passes between those points are not part of the path (their outputs are the synthetic tensors)."""
+    ref_shim.install()
+    import torch.nn.functional as F
+    from generalframework.loss import JSD_2D, KL_Divergence_2D
+    from generalframework.metrics import DiceMeter
+    from generalframework.utils.AEGenerator import VATGenerator
+    K, C = len(inp["logits"]), inp["logits"][0].shape[1]
+    z = [x.detach().requires_grad_() for x in inp["logits"]]
+    probs = [F.softmax(x, 1) for x in z]
+    rows = []
+    if with_dice:
+        for k in range(K):
+            m = DiceMeter(method="2d", C=C)
+            m.add(probs[k], inp["labels"])
+            rows.append(m.log)
+    jsd = JSD_2D()(probs).mean()
+    total = jsd
+    outs = [jsd.detach()]
+    if with_vat:
+        d = VATGenerator._l2_normalize(inp["d"].clone())
+        d = xi * VATGenerator._l2_normalize(d)
+        yh = inp["yhat"].detach().requires_grad_()
+        vkl = VATGenerator.kl_div_with_logit(z[0].detach(), yh).mean()
+        vkl.backward()
+        r_adv = eps * VATGenerator._l2_normalize(inp["d_grad"].clone())
+        img_adv = torch.clamp(inp["img"] + r_adv.detach(), 0, 1)  # noqa: F841
+        adv = KL_Divergence_2D(reduce=True)(F.softmax(inp["adv"].detach().requires_grad_(), 1), inp["real"].detach())
+        total = total + adv
+        outs += [vkl.detach(), adv.detach()]
+    total.backward()
+    res = torch.stack(outs).cpu()
+    rows = [r.cpu() for r in rows]
+    return res, rows
+
+
+def time_reference_step(device, K, C, B, H, W, cin, steps, warmup, with_vat=True, with_dice=True, threads=None):
+    """(pixels/s, s/step, last losses) of ``reference_step`` on ``device`` over ``steps`` timed steps."""
+    if threads:
+        torch.set_num_threads(threads)
+    inp = reference_step_inputs(device, K, C, B, H, W, cin)
+    for _ in range(warmup):
+        res, _ = reference_step(inp, with_vat, with_dice)
+    if device.type == "cuda":
+        torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        res, _ = reference_step(inp, with_vat, with_dice)
+    if device.type == "cuda":
+        torch.cuda.synchronize(device)
+    dt = time.perf_counter() - t0
+    return B * H * W * steps / dt, dt / steps, [float(v) for v in res]

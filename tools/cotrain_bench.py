@@ -13,8 +13,9 @@ backward, K optimizer steps, and the per-iteration reporting.  Two arms on the S
          single GPU (the reference's multi-GPU path is nn.DataParallel, not reproduced).
   nets   the networks alone (same forward/backward passes with a trivial loss): the floor neither arm can beat.
 
-The networks are stand-ins (a small UNet in stock PyTorch/cuDNN, random init): ENet/UNet of generalframework/arch
-are out of scope, and what is measured is how much of an iteration the loss/metric path costs.
+The networks are BASELINE's own (ENet / UNet / Cityscapes ENet built by the staged reference's ``get_arch``, random init,
+stock cuDNN) when baseline/_ref is staged (tools/stage_reference.sh), else a small stand-in UNet: they are out of scope
+(SURVEY.md 8), and what is measured is how much of an iteration the loss / metric path costs.
 Prints one JSON line per arm (rank 0) and writes them to --out.
 """
 import argparse
@@ -62,6 +63,33 @@ class SmallUNet(nn.Module):
         d2 = self.d2(torch.cat((up(d3, e2), e2), 1))
         d1 = self.d1(torch.cat((up(d2, e1), e1), 1))
         return self.head(d1)
+
+
+REF_ARCH = {"c1": "enet", "c2": "unet", "c3": "enet", "c4": "deeplabenet"}   # config/*_cotraing.yaml "Arch: name"
+
+
+def make_net(config, cin, C, base=16, prefer_reference=True):
+    """The network of BASELINE's config when the unmodified reference is staged (baseline/_ref or /root/reference: ENet
+    generalframework/arch/enet.py:234-244, UNet arch/network.py:196-290, Cityscapes ENet arch/deeplab/enet.py:485-648,
+    built through the reference's own ``get_arch``), else the stand-in UNet above.  Returns (module, description)."""
+    if prefer_reference:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import ref_shim
+            if ref_shim.reference_available():
+                ref_shim.install()
+                from generalframework.arch import get_arch
+                name = REF_ARCH[config]
+                kw = {"num_classes": C}
+                net = get_arch(name, kw)
+                x = torch.zeros(1, cin, 256, 256)
+                with torch.no_grad():
+                    net.eval()
+                    assert net(x).shape[1] == C
+                return net, f"reference get_arch('{name}') ({sum(p.numel() for p in net.parameters()) / 1e6:.2f} M parameters), fp32, random init"
+        except Exception as e:  # input channels / optional packages the arch wants: fall back, say why
+            return SmallUNet(cin, C, base), f"stand-in SmallUNet(base={base}) (reference arch unavailable: {type(e).__name__}: {e})"
+    return SmallUNet(cin, C, base), f"stand-in SmallUNet(base={base}), fp32, random init"
 
 
 # --------------------------------------------------------------------------------------------- the ATen arm
@@ -204,40 +232,36 @@ def nets_only_iteration(nets, opts, lab, unlab, cfg):
     return total
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--config", default="c1", choices=sorted(CONFIGS))
-    ap.add_argument("--arms", default="ours,aten,nets")
-    ap.add_argument("--iters", type=int, default=60)
-    ap.add_argument("--warmup", type=int, default=8)
-    ap.add_argument("--base", type=int, default=16, help="width of the stand-in UNet")
-    ap.add_argument("--adv", type=int, default=1)
-    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "cotrain"))
-    args = ap.parse_args()
-
+def measure(config, arms, iters, warmup, dev, rank, world, local, base=16, adv=True, batch=None, prefer_reference=True,
+            on_line=None):
+    """Iterations/s of the arms on ``config`` (one process per GPU; DDP inside the ``ours`` / ``nets`` arms at world > 1).
+    Returns the JSON-able lines (every rank computes them; rank 0's are the ones to print)."""
     import dct_b200
-    from dct_b200.cotrain import CoTrainConfig, CoTrainStep, init_distributed
-    rank, world, local = init_distributed()
-    dev = torch.device("cuda", local)
-    K, C, cin, H, W, BL, BU = CONFIGS[args.config]
+    from dct_b200.cotrain import CoTrainConfig, CoTrainStep
+    K, C, cin, H, W, BL, BU = CONFIGS[config]
+    if batch is not None:
+        BL = BU = int(batch)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     lab = [(torch.rand(BL, cin, H, W, device=dev, generator=g),
             torch.randint(0, C, (BL, 1, H, W), device=dev, generator=g)) for _ in range(K)]
     unlab = (torch.rand(BU, cin, H, W, device=dev, generator=g), torch.randint(0, C, (BU, 1, H, W), device=dev, generator=g))
     axises = list(range(1, C)) if C > 2 else [0, 1]
-    cfg = {"cot": 0.5, "advw": 0.05, "eps": 0.03, "adv": bool(args.adv) and K >= 2}
-    dct_b200.set_check_mode("deferred")
-    os.makedirs(args.out, exist_ok=True)
+    cfg = {"cot": 0.5, "advw": 0.05, "eps": 0.03, "adv": bool(adv) and K >= 2}
+    old_mode = dct_b200.set_check_mode("deferred")
     lines = []
+    net_desc = [None]
 
     def fresh():
         torch.manual_seed(1234)
-        nets = [SmallUNet(cin, C, args.base).to(dev).train() for _ in range(K)]
+        nets = []
+        for _ in range(K):
+            n, net_desc[0] = make_net(config, cin, C, base, prefer_reference)
+            nets.append(n.to(dev).train())
         opts = [torch.optim.Adam(n.parameters(), lr=1e-3, weight_decay=1e-4) for n in nets]
         return nets, opts
 
-    def timed(fn, sync_each=False):
-        for _ in range(args.warmup):
+    def timed(fn):
+        for _ in range(warmup):
             fn()
         torch.cuda.synchronize()
         if world > 1:
@@ -245,7 +269,7 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
-        for _ in range(args.iters):
+        for _ in range(iters):
             fn()
         e1.record()
         torch.cuda.synchronize()
@@ -253,9 +277,9 @@ def main():
         ms = torch.tensor([e0.elapsed_time(e1), wall * 1e3], dtype=torch.float64, device=dev)
         if world > 1:
             torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
-        return float(ms[0]) / args.iters, float(ms[1]) / args.iters
+        return float(ms[0]) / iters, float(ms[1]) / iters
 
-    for arm in args.arms.split(","):
+    for arm in arms:
         if arm == "aten" and world > 1:
             continue
         nets, opts = fresh()
@@ -263,7 +287,7 @@ def main():
         if arm == "ours":
             step = CoTrainStep(nets, opts, CoTrainConfig(num_classes=C, train_jsd=True, train_adv=cfg["adv"], cot_weight=cfg["cot"],
                                                          adv_weight=cfg["advw"], fgsm_eps=cfg["eps"],
-                                                         meter="iou" if args.config == "c4" else "dice"), dev)
+                                                         meter="iou" if config == "c4" else "dice"), dev)
             fn = lambda: step.step(lab, unlab)  # noqa: E731
             ms, wall = timed(fn)
             rep = step.report.reduce()
@@ -288,17 +312,45 @@ def main():
             ms, wall = timed(fn)
         line = {"metric": "co-train iterations/sec", "arm": arm, "value": 1e3 / ms, "unit": "iterations/s",
                 "ms_per_iter": ms, "wall_ms_per_iter": wall, "n_gpus": world, "images_per_iter_per_gpu": K * BL + BU,
-                "images_per_sec": (K * BL + BU) * world * 1e3 / ms, "iters": args.iters, "warmup": args.warmup,
-                "config": {"workload": args.config, "K": K, "C": C, "H": H, "W": W, "B_lab": BL, "B_unlab": BU, "adv": cfg["adv"],
-                           "net": f"stand-in SmallUNet(base={args.base}), fp32, random init", "scaling": "weak"}, **extra}
+                "images_per_sec": (K * BL + BU) * world * 1e3 / ms, "iters": iters, "warmup": warmup,
+                "config": {"workload": config, "K": K, "C": C, "H": H, "W": W, "B_lab": BL, "B_unlab": BU, "adv": cfg["adv"],
+                           "net": net_desc[0], "scaling": "weak"}, **extra}
         lines.append(line)
+        if on_line is not None:
+            on_line(line, lines)
+        del nets, opts
+        torch.cuda.empty_cache()
+    dct_b200.set_check_mode(old_mode)
+    return lines
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="c1", choices=sorted(CONFIGS))
+    ap.add_argument("--arms", default="ours,aten,nets")
+    ap.add_argument("--iters", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--base", type=int, default=16, help="width of the stand-in UNet")
+    ap.add_argument("--adv", type=int, default=1)
+    ap.add_argument("--batch", type=int, default=None, help="override the labeled / unlabeled batch per GPU")
+    ap.add_argument("--stand-in", action="store_true", help="the stand-in UNet even if the reference's architectures are staged")
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "cotrain"))
+    args = ap.parse_args()
+
+    from dct_b200.cotrain import init_distributed
+    rank, world, local = init_distributed()
+    dev = torch.device("cuda", local)
+    os.makedirs(args.out, exist_ok=True)
+
+    def on_line(line, lines):
         if rank == 0:
             print(json.dumps(line), flush=True)
             with open(os.path.join(args.out, f"cotrain_{args.config}_n{world}.jsonl"), "w") as f:   # after every arm
                 for ln in lines:
                     f.write(json.dumps(ln) + "\n")
-        del nets, opts
-        torch.cuda.empty_cache()
+
+    measure(args.config, args.arms.split(","), args.iters, args.warmup, dev, rank, world, local, base=args.base, adv=bool(args.adv),
+            batch=args.batch, prefer_reference=not args.stand_in, on_line=on_line)
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()

@@ -6,8 +6,8 @@ out=gpurun_out/$tag
 mkdir -p $out
 for sec in "$@"; do
   case $sec in
-    tests)    ( timeout 900 python -m pytest tests -m gpu -x -q -rxXs 2>&1 | tail -25 ) > $out/pytest_gpu.log; tail -3 $out/pytest_gpu.log ;;
-    tests:*)  f=${sec#tests:}; ( timeout 600 python -m pytest $f -m gpu -q -rxXs -s 2>&1 | tail -60 ) > $out/pytest_$(basename $f .py).log; tail -5 $out/pytest_$(basename $f .py).log ;;
+    tests)    ( timeout 900 python -m pytest tests -m gpu -q -rfxXs --tb=short 2>&1 | tail -80 ) > $out/pytest_gpu.log; tail -3 $out/pytest_gpu.log ;;
+    tests:*)  f=${sec#tests:}; ( timeout 900 python -m pytest $f -m gpu -q -rfxXs -s --tb=short 2>&1 | tail -150 ) > $out/pytest_$(basename $f .py).log; tail -5 $out/pytest_$(basename $f .py).log ;;
     smoke)    ( timeout 200 python -c 'import __graft_entry__ as g; g.smoke()' 2>&1 | tail -3 ) > $out/smoke.log; cat $out/smoke.log ;;
     bench)    ( timeout 600 python bench.py 2>$out/bench.err | tail -1 ) > $out/bench_c2.json; cut -c1-600 $out/bench_c2.json ;;
     bench:*)  w=${sec#bench:}; ( timeout 600 python bench.py --workload $w 2>$out/bench_$w.err | tail -1 ) > $out/bench_$w.json; cut -c1-400 $out/bench_$w.json ;;
