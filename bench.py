@@ -553,8 +553,8 @@ def run_extras(args, dct, dev, rank, world, local, peak):
     with_vat, with_dice = args.workload != "c1", args.workload != "c4"
     out = {}
     rt = reference_staged()
-    # ---- the step through the reference's own modules on this GPU
-    if rank == 0:
+    # ---- the step through the reference's own modules on this GPU (N = 1 only, like cpu_baseline)
+    if rank == 0 and world == 1:
         if rt is not None:
             try:
                 v, sec, losses = rt.time_reference_step(dev, K, C, B, H, W, cin, steps=3, warmup=1, with_vat=with_vat,
@@ -590,7 +590,7 @@ def run_extras(args, dct, dev, rank, world, local, peak):
             if cinc == 1 and Cc == 4:   # the reference trainer's validation loop hard-codes C = 4 and its datasets are grey-scale
                 try:
                     kw = dict(iters=iters if cfg_name == "c1" else 3, K=Kc, arch=cb.REF_ARCH[cfg_name], C=Cc, B=BL, H=Hc, W=Wc,
-                              train_jsd=True, train_adv=True, deterministic=False, warmup_iters=1)
+                              train_jsd=True, train_adv=True, deterministic=False, warmup_iters=1, tf32=None)
                     stock = rt.run_train_loop(dev, False, **kw)
                     drop = rt.run_train_loop(dev, True, **kw)
                     entry["reference_trainer_stock"] = {"it_per_s": stock["it_per_s"], "iters": stock["iters"]}

@@ -77,7 +77,7 @@ class SynthSet(torch.utils.data.Dataset):
 
 def run_train_loop(device, use_dropins, iters=3, K=2, arch="enet", C=4, B=4, H=256, W=256, seed=1234, train_jsd=True,
                    train_adv=True, cot_weight=0.5, adv_weight=0.05, eps=0.03, deterministic=True, warmup_iters=0,
-                   keep_inputs=0):
+                   keep_inputs=0, tf32=False):
     """One truncated epoch of the reference's co-training loop, stock (``use_dropins=False``) or after
     ``dct_b200.install()``.  Returns a dict of recorded values (numpy) and timings."""
     ref_shim.install()
@@ -90,11 +90,16 @@ def run_train_loop(device, use_dropins, iters=3, K=2, arch="enet", C=4, B=4, H=2
     if use_dropins:
         import dct_b200
         dct_b200.install()
+    # process-wide torch switches: saved here, restored in the `finally` below.  ``tf32=False`` (parity runs): exact fp32
+    # convolutions, so that both arms see the same network outputs; ``tf32=None`` (timing runs): PyTorch's defaults untouched
+    saved_flags = (torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32,
+                   torch.backends.cuda.matmul.allow_tf32)
     if deterministic:
         torch.backends.cudnn.deterministic = True
         torch.backends.cudnn.benchmark = False
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
+    if tf32 is not None:
+        torch.backends.cudnn.allow_tf32 = bool(tf32)
+        torch.backends.cuda.matmul.allow_tf32 = bool(tf32)
     torch.manual_seed(seed)
     np.random.seed(seed)
     import random
@@ -160,6 +165,8 @@ def run_train_loop(device, use_dropins, iters=3, K=2, arch="enet", C=4, B=4, H=2
         if use_dropins:
             import dct_b200
             dct_b200.uninstall()
+        (torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32,
+         torch.backends.cuda.matmul.allow_tf32) = saved_flags
     per_iter = 2 if train_adv else 1      # FSGMGenerator back-propagates its own CE loss before the total loss
     total = [float(v) for v in losses[per_iter - 1::per_iter]]
     return {"total_loss": np.asarray(total, dtype=np.float64),
