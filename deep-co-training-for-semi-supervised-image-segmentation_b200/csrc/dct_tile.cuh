@@ -129,6 +129,9 @@ struct TileArgs {
     int64_t ignore_index;          // LABELS ops: label value that contributes nothing (nn.NLLLoss ignore_index)
     int tiles_per_image;
     int num_tiles;
+    unsigned int tpi_mul;          // tile / tiles_per_image without a division (tile_set_geometry): q = (t + ((n - t) >> tpi_sh1)) >> tpi_sh2,
+    int tpi_sh1, tpi_sh2;          //   t = umulhi(tpi_mul, n) -- exact for every 32-bit n
+    int refill;                    // 1: a drained stage is refilled as soon as ITS OWN store group has been read (DCT_TILE_REFILL); 0: one tile later
     int pool_div;                  // developer knob: the tail pool is 1/pool_div of every CTA's range (0 = default 5)
     int prefetch;                  // tiles of this CTA's range whose rows are prefetched into L2 before the dependency wait (DCT_TILE_PREFETCH)
     int force_static;              // developer switch (tools/kbench_tile.cu): 1 = no tail pool (purely static contiguous ranges) even with a workspace
@@ -207,12 +210,30 @@ struct TileCfg {
     __host__ __device__ static constexpr size_t row_off(int n, int c) { return (size_t)n * kTensorStride + (size_t)c * kRowBytes; }
 };
 
+// image index of a tile: division by the launch's tiles_per_image through a precomputed multiplier (the hardware has no
+// integer divide: `tile / tpi` is ~25 dependent instructions incl. a MUFU.RCP, once per tile in the producer lane's critical
+// path and -- before the producer published the image index with the tile -- once per tile in every consumer thread)
+__device__ __forceinline__ int tile_image(const TileArgs& a, int tile) {
+    const unsigned int n = (unsigned int)tile, t = __umulhi(a.tpi_mul, n);
+    return (int)((t + ((n - t) >> a.tpi_sh1)) >> a.tpi_sh2);
+}
+inline void tile_set_geometry(TileArgs& a, int64_t B, int tile_pixels) {
+    a.tiles_per_image = (int)((a.HW + tile_pixels - 1) / tile_pixels);
+    a.num_tiles = (int)(a.tiles_per_image * B);
+    const unsigned int d = (unsigned int)a.tiles_per_image;
+    int l = 0;
+    while ((1ull << l) < d) ++l;                                   // ceil(log2 d)
+    a.tpi_mul = (unsigned int)((((1ull << l) - d) << 32) / d + 1);   // Granlund-Montgomery round-up multiplier (33-bit form)
+    a.tpi_sh1 = l < 1 ? l : 1;
+    a.tpi_sh2 = l < 1 ? 0 : l - 1;
+}
+
 // Warp-specialised persistent kernel: NCW consumer warps + 1 producer warp per CTA.
 //   producer: lane 0 owns the tile schedule (a contiguous range per CTA whose last fifth is shared through an
 //       atomic counter, see draw() below), publishes each tile index in the stage's shared-memory slot, issues every
 //       bulk load / store, and recycles a stage when its `done` mbarrier (NCW arrivals) has completed and, for ops
 //       with outputs, when the bulk store group that drains it has finished reading shared memory.  Fused Dice: lane 0
-//       marks the last tile of every run of one image (s_mark); on those tiles all 32 lanes add the counters the
+//       marks the last tile of every run of one image (s_info.w); on those tiles all 32 lanes add the counters the
 //       consumer warps hand over through the label row to the global int64 counters (see DCT_DICE_LOCAL above).
 //   consumers: wait on the stage's `full` mbarrier (transaction bytes), read the tile index (-1 = no more work),
 //       compute in registers, write results back in place, fence to the async proxy, arrive on `done`.
@@ -244,8 +265,10 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
     unsigned char* stages = smem_raw;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + Cfg::kStageBytes * STAGES);
     uint64_t* done = full + STAGES;
-    __shared__ int s_tile[STAGES];  // tile index held by each stage; -1 = end of work
-    __shared__ int s_mark[STAGES];  // DICE_LOCAL: 1 = hand the Dice counters over after this tile (written with s_tile)
+    // per stage, written by the producer lane before the stage's `full` barrier is armed: x = tile index held by the stage
+    // (-1 = end of work), y = its image, z = its pixel count (a ragged last tile of an image is shorter than TP),
+    // w = DICE_LOCAL: 1 = hand the Dice counters over after this tile
+    __shared__ int4 s_info[STAGES];
     __shared__ unsigned int s_conf[CONF ? CT * CT : 1];   // this CTA's confusion counts (flushed once, at the end)
     const int tid = threadIdx.x, lane = tid & 31;
     const bool is_producer = tid >= CTHREADS;
@@ -288,7 +311,7 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
         const int my_n = per + ((int)blockIdx.x < extra ? 1 : 0);
         const int npre = min(min(a.prefetch, STAGES), my_n);
         for (int s = 0; s < npre; ++s) {
-            const int tile = my_begin + s, b = tile / tpi;
+            const int tile = my_begin + s, b = tile_image(a, tile);
             const int64_t off = (int64_t)(tile - b * tpi) * TP;
             const int64_t rem = HW - off;
             const uint32_t npix = (uint32_t)(rem < TP ? rem : TP);
@@ -369,24 +392,24 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
             const int tile = pending, stage = issued % STAGES;
             if (tile >= a.num_tiles) {  // publish "no more work" through the same barrier
                 more = false;
-                s_tile[stage] = -1;
+                s_info[stage] = make_int4(-1, 0, 0, 0);
                 tma::mbar_arrive(&full[stage]);
                 return;
             }
             pending = draw();
-            s_tile[stage] = tile;
-            const int b = tile / tpi;
+            const int b = tile_image(a, tile);
+            int mark = 0;
             if constexpr (DICE_LOCAL) {
                 // last tile of a run of one image (or of this CTA's work), or the run is as long as an 8-bit field allows
                 run_len = (b == run_b) ? run_len + 1 : 1;
                 run_b = b;
-                const bool mark = pending >= a.num_tiles || pending / tpi != b || run_len == kDiceMaxTiles;
+                mark = (pending >= a.num_tiles || tile_image(a, pending) != b || run_len == kDiceMaxTiles) ? 1 : 0;
                 if (mark) run_b = -1;
-                s_mark[stage] = mark ? 1 : 0;
             }
             const int64_t off = (int64_t)(tile - b * tpi) * TP;
             const int64_t rem = HW - off;
             const uint32_t npix = (uint32_t)(rem < TP ? rem : TP);
+            s_info[stage] = make_int4(tile, b, (int)npix, mark);
             const uint32_t bytes = npix * (uint32_t)ES;   // one data row segment
             unsigned char* dst = stages + (size_t)stage * Cfg::kStageBytes;
             uint32_t total = TMAP ? (uint32_t)(ROWS * TP * ES) : bytes * ROWS;   // (a box always completes whole)
@@ -456,8 +479,8 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
             if (!__shfl_sync(0xffffffffu, (int)(i < issued), 0)) break;
             const int stage = i % STAGES;
             tma::mbar_wait(&done[stage], (uint32_t)(i / STAGES) & 1u);  // every consumer warp is through with load i
-            const int tile = s_tile[stage];
-            const int b = tile / tpi;
+            const int4 info = s_info[stage];
+            const int tile = info.x, b = info.y;
             // Dice counts of this tile: every consumer warp left its warp-reduced packed counters (8-bit fields,
             // word 0 = |gt==c|, words 1+2n / 2+2n = I / P of view n) in its own slice of the stage's label row; the
             // 32 producer lanes sum one (view, class, kind) counter each over the warps (before the stage is refilled)
@@ -468,7 +491,7 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
             if constexpr (DICE_LOCAL) {
                 // marked tile: every consumer warp left 2 * (1 + 2*NDICE) words of 16-bit fields (classes 0,2 / 1,3 of
                 // |gt==c|, then I / P of every view) in its slice of the label row; lane r sums counter r over the warps
-                hand_over = do_dice && s_mark[stage] != 0;   // written by lane 0 at issue time (a __syncwarp() ago)
+                hand_over = do_dice && info.w != 0;   // written by lane 0 at issue time (a __syncwarp() ago)
                 if (hand_over) {
                     const unsigned int* pkw = reinterpret_cast<const unsigned int*>(stages + (size_t)stage * Cfg::kStageBytes + Cfg::kLabelOffB);
 #pragma unroll
@@ -506,8 +529,7 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
             if (lane == 0) {
                 if constexpr (NOUT > 0) {
                     const int64_t off = (int64_t)(tile - b * tpi) * TP;
-                    const int64_t rem = HW - off;
-                    const uint32_t bytes = (uint32_t)(rem < TP ? rem : TP) * (uint32_t)ES;
+                    const uint32_t bytes = (uint32_t)info.z * (uint32_t)ES;
                     const unsigned char* st = stages + (size_t)stage * Cfg::kStageBytes;
 #pragma unroll
                     for (int n = 0; n < NOUT; ++n)
@@ -522,9 +544,15 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
                             }
                         }
                     tma::bulk_commit();
-                    // load i-1's store group has drained its stage once at most one group is still reading:
-                    // that stage (== issued % STAGES) takes the next load or the end marker
-                    if (i >= 1) {
+                    if (a.refill) {
+                        // immediate: wait until THIS tile's store group has been read out of shared memory (a few hundred
+                        // ns; no other stage can need the producer sooner than one tile's compute time) and hand the very
+                        // same stage to the next load: every stage spends one tile's compute time less empty
+                        tma::bulk_wait_read<0>();
+                        try_issue();
+                    } else if (i >= 1) {
+                        // lagged: load i-1's store group has drained its stage once at most one group is still reading:
+                        // that stage (== issued % STAGES) takes the next load or the end marker
                         tma::bulk_wait_read<1>();
                         try_issue();
                     }
@@ -569,21 +597,21 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
         if constexpr (Op::USES_UP) gs = upstream_scalar(a.up);
         int nbad_label = 0;
         // Dice: packed 8-bit per-class counters of this thread, [view][I,P], and |gt == c| (the same for every view).
-        // DICE_LOCAL: they live across tiles until the producer marks a tile (s_mark); DICE_FOLD: they are one tile's.
+        // DICE_LOCAL: they live across tiles until the producer marks a tile (s_info.w); DICE_FOLD: they are one tile's.
         unsigned int pk[DICE ? Op::NDICE : 1][2] = {};
         unsigned int pkG = 0u;
 #pragma unroll 1
         for (int i = 0;; ++i) {
             const int stage = i % STAGES;
             tma::mbar_wait(&full[stage], (uint32_t)(i / STAGES) & 1u);
-            const int tile = s_tile[stage];
+            const int4 info = s_info[stage];   // one 16-byte shared load: tile, image, pixel count, Dice mark
+            const int tile = info.x;
             if (a.trace != nullptr && i == 0 && tid == 0) a.trace[kTraceSlots * blockIdx.x + 1] = globaltimer_ns();
             if (tile < 0) break;
-            const int b = tile / tpi;
-            const bool hand_over = DICE_LOCAL && do_dice && s_mark[stage] != 0;   // uniform across the CTA's consumers
+            const int b = info.y;
+            const bool hand_over = DICE_LOCAL && do_dice && info.w != 0;   // uniform across the CTA's consumers
             const int64_t off = (int64_t)(tile - b * tpi) * TP;
-            const int64_t rem = HW - off;
-            const int len = (int)(rem < TP ? rem : TP);
+            const int len = info.z;
             unsigned char* st = stages + (size_t)stage * Cfg::kStageBytes;
             const int p0 = tid * PPT;
             const bool active = p0 < len;
@@ -646,6 +674,47 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
                         }
                     if constexpr (DICE) {
                         if (do_dice) {
+                            // One-hot byte of every (view, pixel) prediction.  All NDICE * LW fast-path tests (see
+                            // spec_softmax_argmax_onehot4: the class within 2^-15 of the maximum is unique and the class sum
+                            // is finite => the raw arg-max is the pinned answer) are evaluated first, branch-free, and ONE
+                            // rare branch redoes the group with the pinned arithmetic.  With a branch per prediction the six
+                            // ~10-deep dependent chains ran one after the other (ncu r33: the consumers issue every 7th
+                            // cycle, top stalls `wait` / `branch_resolving`); side by side they fill each other's latencies,
+                            // and the class maxima are shared with the op's own softmax.
+                            unsigned int hot[LW][Op::NDICE];
+                            unsigned int hsum = 0u;   // bytes: number of predictions naming class c (<= NDICE * LW <= 8)
+                            bool fin = true;
+#pragma unroll
+                            for (int n = 0; n < Op::NDICE; ++n) {
+                                T m = x[n][0], s = x[n][0];
+#pragma unroll
+                                for (int c = 1; c < C; ++c) { m = vmax(m, x[n][c]); s = vadd(s, x[n][c]); }
+                                const T t = vadds(m, -3.0517578125e-05f);
+#pragma unroll
+                                for (int j = 0; j < LW; ++j) {
+                                    const float tj = vget(t, j);
+                                    unsigned int h = 0u;
+#pragma unroll
+                                    for (int c = 0; c < C; ++c) h += (vget(x[n][c], j) >= tj) ? (1u << (8 * c)) : 0u;
+                                    hot[j][n] = h;
+                                    hsum += h;
+                                    fin &= fabsf(vget(s, j)) <= 3.4028234664e38f;
+                                }
+                            }
+                            // finite sums => every mask names at least its maximum, so "NDICE * LW names in total" <=> each
+                            // mask names exactly one class
+                            const bool all_fast = fin & (((hsum * 0x01010101u) >> 24) == (unsigned int)(Op::NDICE * LW));
+                            if (!all_fast) {
+#pragma unroll
+                                for (int j = 0; j < LW; ++j)
+#pragma unroll
+                                    for (int n = 0; n < Op::NDICE; ++n) {
+                                        float xs[C];
+#pragma unroll
+                                        for (int c = 0; c < C; ++c) xs[c] = vget(x[n][c], j);
+                                        hot[j][n] = spec_softmax_argmax_onehot4<C>(xs);
+                                    }
+                            }
 #pragma unroll
                             for (int j = 0; j < LW; ++j) {
                                 const uint2 lb = lab[gi * LW + j];
@@ -655,12 +724,8 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
                                 pkG += gmask;
 #pragma unroll
                                 for (int n = 0; n < Op::NDICE; ++n) {
-                                    float xs[C];
-#pragma unroll
-                                    for (int c = 0; c < C; ++c) xs[c] = vget(x[n][c], j);
-                                    const unsigned int hot = spec_softmax_argmax_onehot4<C>(xs);  // one-hot byte of the prediction
-                                    pk[n][1] += hot;
-                                    pk[n][0] += hot & gmask;
+                                    pk[n][1] += hot[j][n];
+                                    pk[n][0] += hot[j][n] & gmask;
                                 }
                             }
                         }
@@ -860,14 +925,19 @@ int tile_launch_ct(TileArgs a, int64_t B, cudaStream_t stream) {
         if (e != cudaSuccess) { g_last_cuda_error = e; return DCT_ERR_CUDA; }
         if (devid >= 0 && devid < 64) configured[devid] = true;
     }
-    a.tiles_per_image = (int)((a.HW + Cfg::TP - 1) / Cfg::TP);
-    a.num_tiles = (int)(a.tiles_per_image * B);
+    tile_set_geometry(a, B, Cfg::TP);
     {   // schedule knobs (developer A/B through the environment; the defaults are the measured product choice)
         static const int env_pool = [] { const char* e = std::getenv("DCT_TILE_POOL_DIV"); return e ? std::atoi(e) : 0; }();
         static const int env_pre = [] { const char* e = std::getenv("DCT_TILE_PREFETCH"); return e ? std::atoi(e) : -1; }();
         // 2 tiles per CTA (measured, profiles/r30/ab_prefetch.log: c2 step 102.3 -> 101.9 us, c3 52.6 -> 51.8, c1 11.3 -> 10.5;
         // 4 or 8 tiles queue so much ahead of the first real loads that the short KL launches get slower)
         a.prefetch = env_pre >= 0 ? env_pre : 2;
+        static const int env_refill = [] { const char* e = std::getenv("DCT_TILE_REFILL"); return e ? std::atoi(e) : -1; }();
+        // Measured (profiles/r34/ab_refill.log): immediate refill pays where the store group is a fraction of the stage and the
+        // stages are few -- the C = 19 KL kernels (2-3 tensors in, 1 out, 3 stages): c4 kl_adv 324 -> 305 us, kl_logit 301 -> 296;
+        // it costs where the store drains the whole stage (JSD: c4 407 -> 418 us, the producer lane sits in the read wait) and
+        // on the short c2 / c3 launches (+0.3 .. +0.9 us per kernel)
+        a.refill = env_refill >= 0 ? env_refill : ((TMAP && Op::NOUT < Op::NIN) ? 1 : 0);
         if (env_pool > 0 && a.pool_div == 0) a.pool_div = env_pool;
     }
     int grid = kSMs * MINB;

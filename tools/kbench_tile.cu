@@ -15,6 +15,7 @@ namespace dct {
 #include "dct_ce.cu"
 static bool g_pdl = true;
 static int g_pool_div = 0;
+static int g_refill = 0;
 static bool g_static = false;  // 1: no workspace -> static round-robin tile schedule (and no loss sum)
 namespace dct { bool pdl_enabled() { return g_pdl; } unsigned long long* trace_next(int) { return nullptr; } }
 
@@ -75,7 +76,7 @@ void run(const char* tag, int64_t B, int64_t HW, int reps, double bytes_per_px, 
         a.counts = counts; a.count_view_stride = B * CT * 3;
         a.HW = HW; a.map = nullptr; a.sum = Op::HAS_MAP ? sum : nullptr; a.up = Upstream{nullptr, nullptr, 1e-6f};
         a.eps = 1e-10f; a.ignore_index = 255; a.class_w = nullptr; a.flags = nullptr; a.ws = ws; a.force_static = g_static ? 1 : 0; a.pool_div = g_pool_div;
-        a.tiles_per_image = (int)((HW + Cfg::TP - 1) / Cfg::TP); a.num_tiles = (int)(a.tiles_per_image * B);
+        tile_set_geometry(a, B, Cfg::TP); a.refill = g_refill;
         sets[r] = a;
     }
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
@@ -142,7 +143,8 @@ int main(int argc, char** argv) {
     if (argc > 4) g_pdl = atoi(argv[4]) != 0;
     int which = argc > 5 ? atoi(argv[5]) : 0;
     if (argc > 6) g_static = atoi(argv[6]) != 0;
-    if (argc > 7) g_pool_div = atoi(argv[7]);  // 0: C=4 family, 1: C=19 family
+    if (argc > 7) g_pool_div = atoi(argv[7]);
+    if (const char* e = getenv("DCT_TILE_REFILL")) g_refill = atoi(e);  // 0: C=4 family, 1: C=19 family
     const int64_t HW = 65536;
     if (which == 0) {
         sweep<JsdOp<3, true, kFwdBwd, true>, 4>("jsd+dice c2", B, HW, reps, 104, true);
