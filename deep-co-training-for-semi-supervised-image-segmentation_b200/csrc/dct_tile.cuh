@@ -106,6 +106,11 @@ __device__ __forceinline__ void tile_st_row(unsigned char* row, int p0, const FV
 #ifndef DCT_TMAP
 #define DCT_TMAP 1
 #endif
+// 1 (product): 5..16-row stages (ACDC: K*C = 8..16, the KL family) run as 256-pixel tiles through tensor maps, 4 consumer warps,
+// 3 CTAs/SM; 0: the round-1 shape (512-pixel tiles, 8 warps, 2 CTAs/SM, row copies) for A/B builds
+#ifndef DCT_SMALL_TMAP
+#define DCT_SMALL_TMAP 1
+#endif
 constexpr int kTileMaxTensors = 8;
 constexpr int kTileMaxRows = 80;   // NIN*C rows per stage
 
@@ -897,12 +902,17 @@ int tile_launch_ct(TileArgs a, int64_t B, cudaStream_t stream) {
     //                    (profiles/r09/kbench_wide_more.log: 4245 GB/s; 6 warps 3750, 2 x 3 warps 3744, 5 warps x 4 stages 3205)
     //   DCT_STREAM_MIN_ROWS (off by default): ops with a shared-memory-resident body work on the stage in place; measured
     //                    equal or slower than the register-resident body at every shape (profiles/r08/kbench_wide_stream.log)
+    //   5 <= rows <= 16  (round 2, DCT_SMALL_TMAP) tiles of 256 pixels, 4 consumer warps, 3 CTAs/SM, one tensor-map box per tensor
+    //                    instead of C row copies: 3 independent producers per SM, 7 copies per tile instead of 25 at c2
+    //                    (profiles/r35/kbench_small.log: c2 JSD+Dice 40.9 -> 39.4 us, KL 25.4 -> 24.8, c1 9.4 -> 8.7)
+    constexpr bool SMALL = (DCT_TMAP != 0) && (DCT_SMALL_TMAP != 0) && ROWS > 4 && ROWS <= 16;
     constexpr int PPT = ROWS <= 4 ? 4 : (ROWS <= 40 ? 2 : 1);
-    constexpr int NCW = ROWS <= 16 ? 8 : (ROWS <= 24 ? 4 : (ROWS <= 40 ? (Op::NOUT == 0 ? 8 : 3) : (ROWS <= 60 ? 5 : 7)));
-    constexpr int MINB = ROWS <= 24 ? 2 : (ROWS <= 40 ? (Op::NOUT == 0 ? 1 : 2) : (ROWS <= 60 ? 2 : 1));
+    constexpr int NCW = SMALL ? 4 : (ROWS <= 16 ? 8 : (ROWS <= 24 ? 4 : (ROWS <= 40 ? (Op::NOUT == 0 ? 8 : 3) : (ROWS <= 60 ? 5 : 7))));
+    constexpr int MINB = SMALL ? 3 : (ROWS <= 24 ? 2 : (ROWS <= 40 ? (Op::NOUT == 0 ? 1 : 2) : (ROWS <= 60 ? 2 : 1)));
     constexpr int TPX = NCW * 32 * PPT;
-    // wide stages (C = 19) whose tile is one box (<= 256 pixels): tensor-map TMA, one copy per tensor instead of one per row
-    constexpr bool TMAP = (DCT_TMAP != 0) && CT > 4 && TPX <= 256;
+    // stages whose tile is one box (<= 256 pixels): tensor-map TMA, one copy per tensor instead of one per row -- the wide
+    // C = 19 stages (round 1) and the small ACDC-sized ones
+    constexpr bool TMAP = (DCT_TMAP != 0) && (CT > 4 || SMALL) && TPX <= 256;
     // bf16 tensors: same shapes (the register budget follows the number of rows, not their width); the 2-byte rows
     // simply buy more stages
     constexpr int STAGES = tile_stages<tile_stage_bytes<Op, CT, TPX, ET, TMAP>(), MINB>();

@@ -51,15 +51,16 @@ struct CopyOp {
     static __device__ __forceinline__ T apply(T (&)[N][CM], int, T, float, bool&) { return vset<T>(0.0f); }
 };
 
-template <class Op, int CT, int PPT, int NCW, int STAGES, int MINB>
+template <class Op, int CT, int PPT, int NCW, int STAGES, int MINB, bool TMAP = false>
 void run(const char* tag, int64_t B, int64_t HW, int reps, double bytes_per_px, bool labels) {
     constexpr int THREADS = NCW * 32 + 32;
-    using Cfg = TileCfg<Op, CT, PPT, NCW * 32, STAGES>;
-    auto kern = tile_kernel<Op, CT, PPT, NCW, STAGES, MINB>;
+    using Cfg = TileCfg<Op, CT, PPT, NCW * 32, STAGES, float, TMAP>;
+    auto kern = tile_kernel<Op, CT, PPT, NCW, STAGES, MINB, float, false, TMAP>;
     if (Cfg::kSmemBytes * MINB > 227 * 1024) { printf("%-14s skip (smem)\n", tag); return; }
     const int R = 4;
     size_t n = (size_t)B * CT * HW;
     std::vector<TileArgs> sets(R);
+    std::vector<TileMaps<TMAP>> maps(R);
     Workspace* ws; CK(cudaMalloc(&ws, sizeof(Workspace))); CK(cudaMemset(ws, 0, sizeof(Workspace)));
     double* sum; CK(cudaMalloc(&sum, 8));
     unsigned long long* counts; CK(cudaMalloc(&counts, 8 * 8 * B * CT * 3)); CK(cudaMemset(counts, 0, 8 * 8 * B * CT * 3));
@@ -78,14 +79,18 @@ void run(const char* tag, int64_t B, int64_t HW, int reps, double bytes_per_px, 
         a.eps = 1e-10f; a.ignore_index = 255; a.class_w = nullptr; a.flags = nullptr; a.ws = ws; a.force_static = g_static ? 1 : 0; a.pool_div = g_pool_div;
         tile_set_geometry(a, B, Cfg::TP); a.refill = g_refill;
         sets[r] = a;
+        if constexpr (TMAP) {
+            for (int k = 0; k < Op::NIN; ++k) if (!make_tmap_bchw(&maps[r].in[k], a.in[k], 4, HW, CT, B, Cfg::TP)) { printf("tensor map refused\n"); return; }
+            for (int k = 0; k < Op::NOUT; ++k) if (!make_tmap_bchw(&maps[r].out[k], a.out[k], 4, HW, CT, B, Cfg::TP)) { printf("tensor map refused\n"); return; }
+        }
     }
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
     int grid = 148 * MINB; if (grid > sets[0].num_tiles) grid = sets[0].num_tiles;
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    for (int i = 0; i < 5; ++i) launch_pdl(kern, dim3(grid), dim3(THREADS), Cfg::kSmemBytes, (cudaStream_t)0, sets[i % R], TileMaps<false>{});
+    for (int i = 0; i < 5; ++i) launch_pdl(kern, dim3(grid), dim3(THREADS), Cfg::kSmemBytes, (cudaStream_t)0, sets[i % R], maps[i % R]);
     CK(cudaDeviceSynchronize());
     CK(cudaEventRecord(e0));
-    for (int i = 0; i < reps; ++i) launch_pdl(kern, dim3(grid), dim3(THREADS), Cfg::kSmemBytes, (cudaStream_t)0, sets[i % R], TileMaps<false>{});
+    for (int i = 0; i < reps; ++i) launch_pdl(kern, dim3(grid), dim3(THREADS), Cfg::kSmemBytes, (cudaStream_t)0, sets[i % R], maps[i % R]);
     CK(cudaEventRecord(e1));
     CK(cudaDeviceSynchronize());
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
@@ -94,7 +99,7 @@ void run(const char* tag, int64_t B, int64_t HW, int reps, double bytes_per_px, 
     {
         const int NL = 8;
         unsigned long long* tr; CK(cudaMalloc(&tr, (size_t)NL * grid * 8 * kTraceSlots));
-        for (int i = 0; i < NL; ++i) { TileArgs t = sets[i % R]; t.trace = tr + (size_t)i * grid * kTraceSlots; launch_pdl(kern, dim3(grid), dim3(THREADS), Cfg::kSmemBytes, (cudaStream_t)0, t, TileMaps<false>{}); }
+        for (int i = 0; i < NL; ++i) { TileArgs t = sets[i % R]; t.trace = tr + (size_t)i * grid * kTraceSlots; launch_pdl(kern, dim3(grid), dim3(THREADS), Cfg::kSmemBytes, (cudaStream_t)0, t, maps[i % R]); }
         CK(cudaDeviceSynchronize());
         std::vector<unsigned long long> h((size_t)NL * grid * kTraceSlots);
         CK(cudaMemcpy(h.data(), tr, h.size() * 8, cudaMemcpyDeviceToHost));
@@ -111,7 +116,7 @@ void run(const char* tag, int64_t B, int64_t HW, int reps, double bytes_per_px, 
         cudaFree(tr);
     }
     cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
-    printf("%-14s C=%d PPT=%d thr=%4d stages=%d minb=%d regs=%3d smem=%3zuKB grid=%3d  %8.2f us  %7.1f GB/s  %6.2f Gpix/s\n", tag, CT, PPT,
+    printf("%-14s %s C=%d PPT=%d thr=%4d stages=%d minb=%d regs=%3d smem=%3zuKB grid=%3d  %8.2f us  %7.1f GB/s  %6.2f Gpix/s\n", tag, TMAP ? "tmap" : "rows", CT, PPT,
            THREADS, STAGES, MINB, fa.numRegs, Cfg::kSmemBytes / 1024, grid, us, bytes_per_px * B * HW / us / 1e3, B * HW / us / 1e3);
     for (void* p : allocs) cudaFree(p);
     cudaFree(ws); cudaFree(sum); cudaFree(counts);
@@ -119,11 +124,21 @@ void run(const char* tag, int64_t B, int64_t HW, int reps, double bytes_per_px, 
 
 static int g_only = -1, g_idx = 0;
 // STAGES = 0: as many as fit
-template <class Op, int CT, int PPT, int NCW, int MINB>
+template <class Op, int CT, int PPT, int NCW, int MINB, bool TMAP = false>
 void run_auto(const char* tag, int64_t B, int64_t HW, int reps, double bpp, bool labels) {
-    constexpr int S = tile_stages<tile_stage_bytes<Op, CT, NCW * 32 * PPT, float, false>(), MINB>();
-    if (g_only < 0 || g_only == g_idx) run<Op, CT, PPT, NCW, S, MINB>(tag, B, HW, reps, bpp, labels);
+    constexpr int S = tile_stages<tile_stage_bytes<Op, CT, NCW * 32 * PPT, float, TMAP>(), MINB>();
+    if (g_only < 0 || g_only == g_idx) run<Op, CT, PPT, NCW, S, MINB, TMAP>(tag, B, HW, reps, bpp, labels);
     ++g_idx;
+}
+// c2-sized launches (C <= 4): tile of 256 pixels, 4 consumer warps, 3..4 CTAs / SM, row copies vs one box per tensor
+template <class Op, int CT>
+void sweep_small(const char* tag, int64_t B, int64_t HW, int reps, double bpp, bool labels) {
+    run_auto<Op, CT, 2, 8, 2>(tag, B, HW, reps, bpp, labels);
+    run_auto<Op, CT, 2, 4, 4>(tag, B, HW, reps, bpp, labels);
+    run_auto<Op, CT, 2, 4, 4, true>(tag, B, HW, reps, bpp, labels);
+    run_auto<Op, CT, 2, 4, 3, true>(tag, B, HW, reps, bpp, labels);
+    run_auto<Op, CT, 2, 4, 2, true>(tag, B, HW, reps, bpp, labels);
+    run_auto<Op, CT, 1, 8, 2, true>(tag, B, HW, reps, bpp, labels);
 }
 template <class Op, int CT>
 void sweep(const char* tag, int64_t B, int64_t HW, int reps, double bpp, bool labels) {
@@ -276,6 +291,14 @@ int main(int argc, char** argv) {
         run_auto<J3, 19, 1, 4, 2>("jsd K3 C19", B, HWc, reps, 456, false);
         run_auto<J3, 19, 1, 6, 2>("jsd K3 C19", B, HWc, reps, 456, false);
         run_auto<J3, 19, 1, 3, 3>("jsd K3 C19", B, HWc, reps, 456, false);
+    }
+    if (which == 8) {
+        sweep_small<JsdOp<3, true, kFwdBwd, true>, 4>("jsd+dice c2", B, HW, reps, 104, true);
+        sweep_small<KlFromLogits, 4>("klfromlogits", B, HW, reps, 48, false);
+        sweep_small<KlLogit<true>, 4>("kllogit", B, HW, reps, 64, false);
+        sweep_small<CopyOp<3>, 4>("copy3x4", B, HW, reps, 96, false);
+        sweep_small<JsdOp<2, true, kFwdBwd, true>, 2>("jsd+dice c3", B / 4, 262144, reps, 40, true);
+        sweep_small<JsdOp<2, true, kFwdBwd, true>, 4>("jsd+dice c1", B / 8, 65536, reps, 72, true);
     }
     if (which == 4) {
         // ACDC-sized cross-entropy + Dice (C = 4, 256x256) and the plain variant
