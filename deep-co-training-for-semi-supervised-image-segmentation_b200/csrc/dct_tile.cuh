@@ -475,6 +475,11 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
         };
         if (lane == 0) {
             pending = draw();
+            // (A staggered initial fill -- only 1..3 stages up front, stage s following the landing of stage s - ramp, so that no
+            // CTA's first tile queues behind its neighbours' whole look-ahead -- was measured and removed: the first data lands
+            // 2.3 .. 4.7 us after the start either way (it is the memory system's queue, in-flight bytes / bandwidth, not the
+            // order of issue), and the thinner start costs: c2 step 92.0 -> 101.6 (1 stage) / 93.9 (2) / 91.9 us (3);
+            // profiles/r38/ab_ramp.log, kbench_ramp.log.)
 #pragma unroll 1
             for (int s = 0; s < STAGES; ++s) try_issue();
         }
@@ -595,6 +600,12 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
         }
         if constexpr (NOUT > 0) {
             if (lane == 0) tma::bulk_wait_all<0>();
+        }
+        if (a.trace != nullptr && lane == 0) {   // developer tracing: tiles this CTA processed, pool draws among them, its SM
+            unsigned int smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            const int pool_draws = draws > my_static ? draws - my_static : 0;
+            a.trace[kTraceSlots * blockIdx.x + 2] = ((unsigned long long)smid << 32) | ((unsigned long long)(unsigned)pool_draws << 16) | (unsigned)(issued & 0xffff);
         }
         __syncwarp();
     } else {

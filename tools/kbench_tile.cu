@@ -110,6 +110,28 @@ void run(const char* tag, int64_t B, int64_t HW, int reps, double bytes_per_px, 
             if (i >= 2) { win += (double)(e1_ - s0); gap += (double)(s0 - prev_end); cta += d / grid; spread_s += (double)(s1 - s0); spread_e += (double)(e1_ - e0_); spacing += (double)(s0 - prev_start); }
             prev_end = e1_; prev_start = s0;
         }
+        if (getenv("KB_DUMP")) {   // per-CTA detail of the last traced launch: end time after the launch's first start, tiles, pool draws, SM
+            int i = NL - 1;
+            unsigned long long s0 = ~0ull;
+            for (int c = 0; c < grid; ++c) s0 = std::min(s0, h[((size_t)i * grid + c) * kTraceSlots]);
+            std::vector<std::pair<double, int>> ends;
+            for (int c = 0; c < grid; ++c) ends.push_back({(double)(h[((size_t)i * grid + c) * kTraceSlots + 3] - s0) / 1e3, c});
+            std::sort(ends.begin(), ends.end());
+            printf("      per-CTA (sorted by end): end_us cta sm tiles pool_draws first_data_us\n");
+            for (int k = 0; k < grid; ++k) {
+                if (k >= 12 && k < grid - 24 && (k % 16) != 0) continue;
+                int c = ends[k].second; unsigned long long w = h[((size_t)i * grid + c) * kTraceSlots + 2];
+                printf("        %7.2f %4d sm%3llu tiles %3llu pool %3llu first %5.2f\n", ends[k].first, c, w >> 32, w & 0xffff, (w >> 16) & 0xffff,
+                       (double)(h[((size_t)i * grid + c) * kTraceSlots + 1] - s0) / 1e3);
+            }
+            // per SM: latest end and total tiles
+            std::vector<double> sm_end(256, 0); std::vector<int> sm_tiles(256, 0);
+            for (int c = 0; c < grid; ++c) { unsigned long long w = h[((size_t)i * grid + c) * kTraceSlots + 2]; int sm = (int)(w >> 32) & 255;
+                sm_end[sm] = std::max(sm_end[sm], (double)(h[((size_t)i * grid + c) * kTraceSlots + 3] - s0) / 1e3); sm_tiles[sm] += (int)(w & 0xffff); }
+            printf("      per-SM (sm: last end us / tiles):");
+            for (int sm = 0; sm < 160; ++sm) if (sm_tiles[sm]) printf(" %d:%.1f/%d", sm, sm_end[sm], sm_tiles[sm]);
+            printf("\n");
+        }
         int n = NL - 2;
         printf("      trace: spacing %.2f us = window %.2f (first start -> last end) + gap %.2f | mean CTA life %.2f, start spread %.2f, end spread %.2f\n",
                spacing / n / 1e3, win / n / 1e3, gap / n / 1e3, cta / n / 1e3, spread_s / n / 1e3, spread_e / n / 1e3);
@@ -151,6 +173,7 @@ void sweep(const char* tag, int64_t B, int64_t HW, int reps, double bpp, bool la
     run_auto<Op, CT, 2, 6, 3>(tag, B, HW, reps, bpp, labels);
     run_auto<Op, CT, 2, 12, 1>(tag, B, HW, reps, bpp, labels);
 }
+#ifndef KB_NO_MAIN
 int main(int argc, char** argv) {
     int reps = argc > 1 ? atoi(argv[1]) : 40;
     if (argc > 2) g_only = atoi(argv[2]);
@@ -310,3 +333,4 @@ int main(int argc, char** argv) {
     }
     return 0;
 }
+#endif  // KB_NO_MAIN
