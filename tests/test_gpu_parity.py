@@ -290,6 +290,9 @@ CONFIGS = [  # (name, K, C, B, H, W)
     ("rt_c5", 3, 5, 2, 40, 52),      # runtime-C fallback
     ("rt_k5", 5, 3, 2, 40, 52),      # runtime-K fallback
     ("odd", 2, 4, 3, 37, 41),        # HW not a multiple of 4: scalar fallback
+    ("ragged_c4", 3, 4, 3, 36, 44),   # HW = 6 * 256 + 48: a ragged last tile per image in the 256-pixel tensor-map stages
+    ("ragged_c2", 2, 2, 3, 100, 100), # HW = 9 * 1024 + 784: ragged last tile of the 4-row shape (1024-pixel tiles, row copies)
+    ("ragged_c19", 2, 19, 2, 36, 44), # the same for the wide tensor-map stages
 ]
 
 
