@@ -73,6 +73,7 @@ _SIGNATURES = {
     "dct_ce_fwdbwd_bf16": [_p, _p, _i, _i64, _i64, _p, _i64, _p, _f, _p, _p, _p, _p, _p, _p, _p],
     "dct_dev_trace_begin": [_p, _i, _i],
     "dct_dev_trace_end": [],
+    "dct_dev_tile_image": [_i, _i],
     "dct_peer_pub_bytes": [],
     "dct_mailbox_create": [C.c_size_t, _p, _p],
     "dct_mailbox_open": [_p, _p],

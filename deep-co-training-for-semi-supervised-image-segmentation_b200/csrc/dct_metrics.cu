@@ -353,3 +353,14 @@ extern "C" int dct_confusion_labels_i64(const int64_t* pred, const int64_t* labe
         pred, labels, n, C, conf, flags);
     return check_launch();
 }
+
+// Developer check (host only, no GPU needed): the image index the tile pipeline's schedule computes for `tile` when an image
+// holds `tiles_per_image` tiles -- the multiplier form of tile / tiles_per_image (tile_set_geometry / tile_image, dct_tile.cuh).
+// tests/test_abi_and_host.py compares it with the integer division over the whole range of divisors and edge tiles.
+extern "C" int dct_dev_tile_image(int tiles_per_image, int tile) {
+    if (tiles_per_image < 1 || tile < 0) return DCT_ERR_BAD_ARG;
+    TileArgs a{};
+    a.HW = tiles_per_image;   // one-pixel tiles: tiles_per_image == HW
+    tile_set_geometry(a, 1, 1);
+    return tile_image(a, tile);
+}

@@ -218,8 +218,13 @@ struct TileCfg {
 // image index of a tile: division by the launch's tiles_per_image through a precomputed multiplier (the hardware has no
 // integer divide: `tile / tpi` is ~25 dependent instructions incl. a MUFU.RCP, once per tile in the producer lane's critical
 // path and -- before the producer published the image index with the tile -- once per tile in every consumer thread)
-__device__ __forceinline__ int tile_image(const TileArgs& a, int tile) {
-    const unsigned int n = (unsigned int)tile, t = __umulhi(a.tpi_mul, n);
+__host__ __device__ __forceinline__ int tile_image(const TileArgs& a, int tile) {
+    const unsigned int n = (unsigned int)tile;
+#ifdef __CUDA_ARCH__
+    const unsigned int t = __umulhi(a.tpi_mul, n);
+#else
+    const unsigned int t = (unsigned int)(((unsigned long long)a.tpi_mul * n) >> 32);   // (dct_dev_tile_image: host-side check)
+#endif
     return (int)((t + ((n - t) >> a.tpi_sh1)) >> a.tpi_sh2);
 }
 inline void tile_set_geometry(TileArgs& a, int64_t B, int tile_pixels) {

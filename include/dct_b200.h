@@ -385,11 +385,15 @@ DCT_API int dct_ce_fwdbwd_bf16(const void* logits, const int64_t* labels, int C,
  * Developer tracing (tools/step_trace.py; not used by the product).  Between _begin and _end every launch of the tile
  * pipeline and of the perturbation normalisation takes the next 4 * max_ctas uint64 words of `buf` (device memory, zeroed
  * by the caller) and each of its CTAs stamps %globaltimer (ns) there: [0] after the programmatic-dependency wait,
- * [1] first tile landed / after the first per-sample exchange, [2] after the last exchange, [3] at its end.  _end returns the
- * number of launches recorded.  Process-global state: do not trace from two host threads at once.
+ * [1] first tile landed / after the first per-sample exchange, [2] tile pipeline: (SM id << 32) | (pool draws << 16) | tiles
+ * processed; normalisation: after the last exchange, [3] at its end.  _end returns the number of launches recorded.
+ * Process-global state: do not trace from two host threads at once.
  * ------------------------------------------------------------------------------------------ */
 DCT_API int dct_dev_trace_begin(void* buf, int max_ctas, int max_launches);
 DCT_API int dct_dev_trace_end(void);
+/* Developer check, host only (no GPU): the image index the tile schedule derives for `tile` with `tiles_per_image` tiles per
+ * image (a multiply-shift form of the division; csrc/dct_tile.cuh tile_image).  Negative: DCT_ERR_BAD_ARG. */
+DCT_API int dct_dev_tile_image(int tiles_per_image, int tile);
 
 #ifdef __cplusplus
 }

@@ -49,6 +49,25 @@ def test_library_basics_without_gpu():
         assert h.dct_device_check(0) == -5
 
 
+def test_tile_schedule_division_is_exact():
+    """The tile pipeline never divides on the device: the producer lane derives a tile's image index through a multiply-shift
+    (csrc/dct_tile.cuh tile_set_geometry / tile_image).  Host-side check of that exact code against integer division: every
+    divisor up to 4096 plus large and power-of-two-adjacent ones, tiles at the edges of every image boundary and of int32."""
+    import dct_b200
+    f = dct_b200._lib.lib().dct_dev_tile_image
+    divisors = list(range(1, 4097)) + [4097, 65535, 65536, 65537, 1 << 20, (1 << 20) + 1, 3 ** 12, (1 << 24) - 1, 1 << 24,
+                                       (1 << 30) - 1, 1 << 30, (1 << 31) - 1]
+    rng = np.random.default_rng(7)
+    top = (1 << 31) - 1
+    for d in divisors:
+        tiles = {0, 1, d - 1, d, d + 1, 2 * d - 1, 2 * d, 7 * d - 1, 7 * d, top, top - 1, top // d * d, max(top // d * d - 1, 0)}
+        tiles |= {int(t) for t in rng.integers(0, top, size=6)}
+        for t in tiles:
+            if 0 <= t <= top:
+                assert f(d, t) == t // d, (d, t)
+    assert f(0, 1) < 0 and f(4, -1) < 0
+
+
 def test_exchange_descriptor_layout_matches_header():
     """dct_peer_pub (include/dct_b200.h) is built word by word in distributed.PeerExchange._descriptor."""
     import dct_b200
