@@ -954,12 +954,17 @@ int tile_launch_ct(TileArgs a, int64_t B, cudaStream_t stream) {
     tile_set_geometry(a, B, Cfg::TP);
     {   // schedule knobs (developer A/B through the environment; the defaults are the measured product choice)
         static const int env_pool = [] { const char* e = std::getenv("DCT_TILE_POOL_DIV"); return e ? std::atoi(e) : 0; }();
-        static const int env_pre = [] { const char* e = std::getenv("DCT_TILE_PREFETCH"); return e ? std::atoi(e) : -1; }();
+        static const int env_pre = [] { const char* e = std::getenv("DCT_TILE_PREFETCH"); return (e && *e) ? std::atoi(e) : -1; }();
         // 2 tiles per CTA (measured, profiles/r30/ab_prefetch.log: c2 step 102.3 -> 101.9 us, c3 52.6 -> 51.8, c1 11.3 -> 10.5).
-        // Ops that write fewer tensors than they read (the KL family: many small stages) take 4: c2 kl_logit 19.0 -> 18.5 us,
-        // kl_adv 19.8 -> 19.4, c3 kl_logit 9.5 -> 9.4; the JSD launches lose with more than 2 (c3 12.9 -> 13.3 us) --
-        // profiles/r39/ab_env.log
-        a.prefetch = env_pre >= 0 ? env_pre : (Op::NOUT < Op::NIN && Op::NOUT > 0 ? 4 : 2);
+        // Deeper (3..4) makes the KL launches faster when timed alone (c2 kl_logit 19.0 -> 18.5 us) but not the chained step
+        // (91.6 -> 91.6 / 91.9 us) and costs the JSD launch at c3 (12.9 -> 13.3 us): profiles/r39/ab_env.log, r42/ab_refill.log
+        a.prefetch = env_pre >= 0 ? env_pre : 2;
+        static const int env_refill = [] { const char* e = std::getenv("DCT_TILE_REFILL"); return (e && *e) ? std::atoi(e) : -1; }();
+        // Measured (profiles/r34/ab_refill.log): immediate refill pays where the store group is a fraction of the stage and the
+        // stages are few -- the C = 19 KL kernels (2-3 tensors in, 1 out, 3 stages): c4 kl_adv 324 -> 305 us, kl_logit 301 -> 296;
+        // it costs where the store drains the whole stage (JSD: c4 407 -> 418 us, c2 37.5 -> 37.9: the producer lane sits in
+        // the read wait); on the short c2 / c3 KL launches it is neutral within 0.3 us either way (profiles/r42/ab_refill.log)
+        a.refill = env_refill >= 0 ? env_refill : ((TMAP && Op::NOUT < Op::NIN) ? 1 : 0);
         if (env_pool > 0 && a.pool_div == 0) a.pool_div = env_pool;
     }
     int grid = kSMs * MINB;
