@@ -345,6 +345,8 @@ __device__ __forceinline__ void l2_finish_sums(double ss, Workspace* ws, int gx)
 }
 
 // launch A: sum of squares of every sample.  VEC = 4: 128-bit streaming loads (M % 4 == 0, 16-byte aligned rows)
+// (Four independent loads per thread and iteration, a grid stride apart, were measured and removed: c4 l2_direction 63 -> 68 us,
+// l2_radv 89 -> 92 us -- 8 CTAs x 256 threads per SM already keep enough lines in flight, profiles/r43/bench_quick.log.)
 template <int VEC>
 __global__ void __launch_bounds__(256) l2_sumsq_kernel(const L2Args a, int gx) {
     pdl_wait();
