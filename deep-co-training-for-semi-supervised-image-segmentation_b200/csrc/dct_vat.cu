@@ -507,6 +507,9 @@ extern "C" int dct_l2_normalize_f32(const float* d, float* out, int64_t B, int64
     }
     if (workspace == nullptr) return DCT_ERR_BAD_ARG;
     if (B > 65535 || B > kMaxPartials / 2) return DCT_ERR_UNSUPPORTED;
+    // (Chunking the samples -- a pair of launches per 16 / 32 / 64 MB of `d`, so that the scale launch's read comes out of L2 --
+    // was measured and removed: every extra pair of launches costs more in ramp and tail than the L2 hits save: c4 l2_direction
+    // 64 -> 144 / 86 / 74 us, l2_radv 90 -> 170 / 115 / 102 us; profiles/r44/ab_DCT_L2_CHUNK_MB.log.)
     // CTAs per sample: about eight 256-thread CTAs per SM over the whole grid, grid-stride loops inside
     const int vec = vec_ok ? 4 : 1;
     int64_t gx = (kSMs * 8 + B - 1) / B;
