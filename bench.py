@@ -263,15 +263,17 @@ def run_ours(args, wl):
     # CoTrainer_City keeps its IoU meters on the labeled branch only (trainer/cotraining_city.py:236-241 vs :250-257)
     with_dice = args.workload != "c4"
     n_local = B * H * W
-    # The path's only exchange: the loss sums of every step.  "p2p" (default at N > 1): they are stored into
-    # every rank's mailbox over NVLink peer memory (distributed.PeerExchange) by a one-CTA kernel chained to the step's
-    # last kernel -- no collective launch; "p2p-fused": by that last kernel itself, "p2p-deferred": one step late on a
-    # forked graph branch (both measured slower);
+    # The path's only exchange: the loss sums of every step.  They are stored into every rank's mailbox over
+    # NVLink peer memory (distributed.PeerExchange) -- no collective launch.  "p2p-early" (default at N > 1): by the first
+    # CTA to finish the NEXT step's first kernel (the sums are final by then; the ~2 us of the publication sit in that
+    # launch's own tail); "p2p": by a one-CTA kernel chained to the step's last kernel (+2.3 us per step); "p2p-fused":
+    # by that last kernel's last CTA (+2.2 us); "p2p-deferred": one step late on a forked graph branch (+6.8 us) --
+    # profiles/r45, r46, DESIGN.md 5;
     # "nccl": one all-reduce per step on a side stream (the baseline this replaces, kept for A/B).
     px, exchange = None, "none"
-    if world > 1 or args.exchange in ("p2p", "p2p-fused", "p2p-deferred"):   # (at N = 1: loopback on the own mailbox, for A/B)
+    if world > 1 or args.exchange in ("p2p", "p2p-fused", "p2p-deferred", "p2p-early"):   # (at N = 1: loopback on the own mailbox, for A/B)
         exchange = args.exchange
-        if exchange in ("p2p", "p2p-fused", "p2p-deferred", "auto"):
+        if exchange in ("p2p", "p2p-fused", "p2p-deferred", "p2p-early", "auto"):
             try:
                 from dct_b200.distributed import PeerExchange
                 px = PeerExchange(dev, n=4, nslots=64)
@@ -285,17 +287,17 @@ def run_ours(args, wl):
                 dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             if ok.item() == 0:
                 px = None
-            exchange = (args.exchange if args.exchange in ("p2p-fused", "p2p-deferred") else "p2p") if px is not None else "nccl"
+            exchange = (args.exchange if args.exchange in ("p2p", "p2p-fused", "p2p-deferred") else "p2p-early") if px is not None else "nccl"
     step = ConsistencyStep(K, C, B, H, W, cin=cin, jsd_weight=1.0, adv_weight=1.0, n_global=n_local * world,
                            with_vat=with_vat, with_dice=with_dice, exchange=px,
-                           exchange_mode={"p2p-fused": "fused", "p2p-deferred": "deferred"}.get(exchange, "chained"))
+                           exchange_mode={"p2p-fused": "fused", "p2p-deferred": "deferred", "p2p-early": "early"}.get(exchange, "chained"))
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     # R independent buffer sets, rotated every step so that no step finds its inputs in the 126 MB L2
     per_set = sum(t.numel() * t.element_size() for t in StepBuffers.allocate(K, C, 1, H, W, cin, dev).input_tensors()) * B
     R = max(2, min(8, int(1.5e9 // max(per_set, 1)) or 2))
     sets = [StepBuffers.allocate(K, C, B, H, W, cin, dev, gen) for _ in range(R)]
     dct_b200.set_check_mode("deferred")  # no host sync inside the path; flags are read once at the end
-    deferred = px is not None and step.exchange_mode == "deferred"
+    deferred = px is not None and step.exchange_mode in ("deferred", "early")
     prev_of = (lambda j: sets[(j - 1) % R]) if deferred else (lambda j: None)   # step i publishes step i-1's sums
     graphs = [step.capture(s, publish_prev=prev_of(j)) for j, s in enumerate(sets)] if args.graph else None
     # One graph holding R consecutive steps (one per buffer set): inside a graph consecutive launches chain by programmatic
@@ -303,8 +305,9 @@ def run_ours(args, wl):
     # (~2.5 us, profiles/r26): the timed loop replays this graph for every full round of R steps and the single-step graphs
     # for the remainder.  Every step still is the full 5 launches on its own buffer set.
     round_graph = None
-    if args.graph and not deferred and not use_nccl_later(world, px):
-        round_graph = step.capture_many(sets)
+    early = px is not None and step.exchange_mode == "early"
+    if args.graph and (not deferred or early) and not use_nccl_later(world, px):
+        round_graph = step.capture_many(sets, publish_chain=early)
     # the path's only exchange: the loss scalars of every step, all-reduced over NCCL on a side stream
     # so that the collective of step i overlaps the kernels of step i+1 (the gradients never depend on it: the
     # global 1/N is folded into the kernels through n_global)
@@ -480,6 +483,9 @@ def run_ours(args, wl):
                                         "p2p": "a one-CTA kernel chained to the step's last kernel by programmatic dependent "
                                                "launch stores the loss sums into every rank's mailbox over NVLink peer memory "
                                                "(no collective, no NCCL kernel)",
+                                        "p2p-early": "the first CTA to finish the NEXT step's first kernel stores the step's loss sums into "
+                                                     "every rank's mailbox over NVLink peer memory (no collective, no extra launch; "
+                                                     "the last step's sums by a one-CTA kernel)",
                                         "p2p-deferred": "a one-CTA kernel on a forked graph branch stores step i-1's loss sums into "
                                                         "every rank's mailbox next to step i's first kernel",
                                         "p2p-fused": "the step's last kernel itself stores the loss sums into every rank's "
@@ -773,7 +779,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--graph", type=int, default=1, help="replay the step as a CUDA graph (1) or launch eagerly (0)")
     ap.add_argument("--e2e-steps", type=int, default=50)
-    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "p2p-deferred", "p2p-fused", "nccl"],
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "p2p-early", "p2p-deferred", "p2p-fused", "nccl"],
                     help="N > 1: how the loss sums cross ranks (auto = p2p, NCCL if peer mapping is refused)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true",

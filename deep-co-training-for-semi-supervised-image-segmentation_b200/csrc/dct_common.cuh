@@ -288,7 +288,7 @@ __device__ __forceinline__ long long warp_sum(long long v) {
 // Also re-arms the workspace header (ticket, tile counter, accumulators) when the last CTA is through.
 template <bool PUB = false>
 __device__ __forceinline__ void tile_grid_finish(long long acc_fx, bool nonfinite, Workspace* ws, double* out, int num_ctas,
-                                                 const PeerPub* pub = nullptr) {
+                                                 const PeerPub* pub = nullptr, int pub_early = 0) {
     if (ws == nullptr) return;
     __shared__ long long s_lo[20], s_hi[20];  // <= 17 warps per CTA
     __shared__ int s_nf;
@@ -313,6 +313,16 @@ __device__ __forceinline__ void tile_grid_finish(long long acc_fx, bool nonfinit
         }
         __threadfence();
         const unsigned int ticket = atomicAdd(&ws->ticket, 1u);
+        if constexpr (PUB) {
+            // Early publication: `pub->src` holds sums that were final BEFORE this launch started (the previous step's: every
+            // kernel that wrote them completed ahead of this grid's dependency wait).  The FIRST CTA to finish pushes them to
+            // the peers while the other CTAs are still working -- the CTAs of a launch end 3-4 us apart, so the ~2 us of the
+            // publication (counter and sums read back, remote stores) sit in the launch's own tail instead of between two
+            // launches of the stream.
+            if (pub_early && ticket == 0u)
+                peer_publish(pub->src, pub->seq, __ldcg(pub->seq), pub->n, pub->rank, pub->world, pub->nslots,
+                             pub->mailbox_table, nullptr, 0.0);
+        }
         if (ticket == (unsigned int)num_ctas - 1u) {  // last CTA: publish the sum and re-arm the header
             __threadfence();
             if (out != nullptr) {
@@ -323,7 +333,7 @@ __device__ __forceinline__ void tile_grid_finish(long long acc_fx, bool nonfinit
                 const double fin = nf ? __longlong_as_double(0x7ff8000000000000ll) : total;
                 *out = fin;
                 if constexpr (PUB)  // the step's sums -> every rank's mailbox (NVLink)
-                    peer_publish(pub->src, pub->seq, __ldcg(pub->seq), pub->n, pub->rank, pub->world, pub->nslots,
+                    if (!pub_early) peer_publish(pub->src, pub->seq, __ldcg(pub->seq), pub->n, pub->rank, pub->world, pub->nslots,
                                  pub->mailbox_table, out, fin);
                 ws->fx_lo = 0ull;
                 ws->fx_hi = 0ll;

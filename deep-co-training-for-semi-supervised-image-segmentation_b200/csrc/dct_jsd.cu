@@ -70,10 +70,10 @@ extern "C" int dct_jsd_bwd_f32(const float* const* views, int K, int C, int64_t 
     return jsd_dispatch(c);
 }
 
-extern "C" int dct_jsd_fwdbwd_f32(const float* const* views, int K, int C, int64_t B, int64_t HW, int in_kind,
-                                  float gconst, float* map, double* sum, float* const* grad_views,
-                                  const int64_t* labels, int64_t* counts, int counts_mode, int32_t* flags,
-                                  void* workspace, void* stream) {
+static int jsd_fwdbwd_f32_impl(const float* const* views, int K, int C, int64_t B, int64_t HW, int in_kind,
+                               float gconst, float* map, double* sum, float* const* grad_views,
+                               const int64_t* labels, int64_t* counts, int counts_mode, int32_t* flags,
+                               void* workspace, const dct_peer_pub* pub, void* stream) {
     if (labels != nullptr && counts == nullptr) return DCT_ERR_BAD_ARG;
     if (counts_mode != DCT_COUNTS_ACCUMULATE && counts_mode != DCT_COUNTS_OVERWRITE) return DCT_ERR_BAD_ARG;
     if (labels != nullptr && counts_mode == DCT_COUNTS_OVERWRITE && workspace == nullptr) return DCT_ERR_BAD_ARG;
@@ -82,8 +82,15 @@ extern "C" int dct_jsd_fwdbwd_f32(const float* const* views, int K, int C, int64
               Upstream{nullptr, nullptr, gconst}, flags, static_cast<Workspace*>(workspace),
               static_cast<cudaStream_t>(stream)};
     c.counts_overwrite = counts_mode == DCT_COUNTS_OVERWRITE;
+    bool pub_done = false;
+    c.pub = pub;
+    c.pub_done = &pub_done;
     int rc = jsd_dispatch(c);
     if (rc != DCT_OK) return rc;
+    if (pub != nullptr && !pub_done) {   // shapes outside the tile pipeline: the stand-alone publication behind the launch
+        rc = dct_exchange_publish(pub, stream);
+        if (rc != DCT_OK) return rc;
+    }
     if (labels != nullptr && !dice_done) {
         // Dice counting of the K views against the same labels (unlabdiceMeters,
         // generalframework/trainer/cotraining_totalloss.py:224).  C <= 4 with aligned rows is fused
@@ -95,6 +102,27 @@ extern "C" int dct_jsd_fwdbwd_f32(const float* const* views, int K, int C, int64
         }
     }
     return DCT_OK;
+}
+
+extern "C" int dct_jsd_fwdbwd_f32(const float* const* views, int K, int C, int64_t B, int64_t HW, int in_kind,
+                                  float gconst, float* map, double* sum, float* const* grad_views,
+                                  const int64_t* labels, int64_t* counts, int counts_mode, int32_t* flags,
+                                  void* workspace, void* stream) {
+    return jsd_fwdbwd_f32_impl(views, K, C, B, HW, in_kind, gconst, map, sum, grad_views, labels, counts, counts_mode, flags,
+                               workspace, nullptr, stream);
+}
+
+// The fused JSD launch is the FIRST kernel of a consistency step: this variant also carries the publication of sums that
+// were final before the launch (the previous step's): its first finishing CTA pushes them into every rank's mailbox while
+// the rest of the grid is still working (include/dct_b200.h, "Fused cross-rank exchange").
+extern "C" int dct_jsd_fwdbwd_pub_f32(const float* const* views, int K, int C, int64_t B, int64_t HW, int in_kind,
+                                      float gconst, float* map, double* sum, float* const* grad_views,
+                                      const int64_t* labels, int64_t* counts, int counts_mode, int32_t* flags,
+                                      void* workspace, const dct_peer_pub* pub_desc, void* stream) {
+    const int prc = check_pub(pub_desc);
+    if (prc != DCT_OK) return prc;
+    return jsd_fwdbwd_f32_impl(views, K, C, B, HW, in_kind, gconst, map, sum, grad_views, labels, counts, counts_mode, flags,
+                               workspace, pub_desc, stream);
 }
 
 // bf16 tensors (networks under autocast): logits in, fp32 math in registers, bf16 gradients out; the tile pipeline

@@ -10,6 +10,7 @@
 // gradients are stored back with the same access pattern.  No shared memory, no tensor cores:
 // the kernel is an HBM-bound map/reduce ("JSD kernel").
 #pragma once
+#include <cstring>
 #include "dct_common.cuh"
 #include "dct_tile.cuh"
 
@@ -457,6 +458,8 @@ struct JsdCall {
     cudaStream_t stream;
     int elem = 0;               // 0: float32 tensors; 1: bfloat16 tensors (views / grads point to bf16; tile pipeline only)
     bool counts_overwrite = false;   // DCT_COUNTS_OVERWRITE: the fused launch clears `counts` itself
+    const dct_peer_pub* pub = nullptr;   // dct_jsd_fwdbwd_pub_f32: sums (final before this launch) its first finishing CTA publishes
+    bool* pub_done = nullptr;            // set to true when the launch carried the publication
 };
 
 // returns DCT_ERR_UNSUPPORTED when (K,C) has no register-tiled instantiation
@@ -495,17 +498,30 @@ int jsd_launch_tile(const JsdCall& c) {
         return tile_launch_ct<JsdOp<K, true, kFwdBwd, false>, C, ET>(a, c.B, c.stream);
     } else {
     if (c.mode == kFwdBwd) {
+        // logits in, with a loss sum: the launch can also carry the early publication of the previous step's sums (PUB kernels)
+        const bool pub = lg && c.pub != nullptr && c.sum != nullptr && c.ws != nullptr;
+        if (pub) {
+            std::memcpy(&a.pub, c.pub, sizeof(a.pub));
+            a.pub_early = 1;
+        }
         if constexpr (C <= 4) {
             if (lg && c.labels != nullptr && aligned(c.labels, 16)) {
                 a.labels = c.labels;
                 a.counts = reinterpret_cast<unsigned long long*>(c.counts);
                 if (!tile_eligible<JsdOp<K, true, kFwdBwd, true>, ET>(a, c.B)) return DCT_ERR_UNSUPPORTED;
-                int rc = tile_launch_ct<JsdOp<K, true, kFwdBwd, true>, C, ET>(a, c.B, c.stream);
+                int rc = pub ? tile_launch_ct<JsdOp<K, true, kFwdBwd, true>, C, ET, true>(a, c.B, c.stream)
+                             : tile_launch_ct<JsdOp<K, true, kFwdBwd, true>, C, ET>(a, c.B, c.stream);
                 if (rc == DCT_OK && c.dice_done) *c.dice_done = true;
+                if (rc == DCT_OK && pub && c.pub_done) *c.pub_done = true;
                 return rc;
             }
         }
         if (!tile_eligible<JsdOp<K, true, kFwdBwd, false>, ET>(a, c.B)) return DCT_ERR_UNSUPPORTED;
+        if (pub) {
+            int rc = tile_launch_ct<JsdOp<K, true, kFwdBwd, false>, C, ET, true>(a, c.B, c.stream);
+            if (rc == DCT_OK && c.pub_done) *c.pub_done = true;
+            return rc;
+        }
         return lg ? tile_launch_ct<JsdOp<K, true, kFwdBwd, false>, C, ET>(a, c.B, c.stream)
                   : tile_launch_ct<JsdOp<K, false, kFwdBwd, false>, C, ET>(a, c.B, c.stream);
     }

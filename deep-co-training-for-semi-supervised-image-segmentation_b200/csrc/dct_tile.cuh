@@ -129,6 +129,8 @@ struct TileArgs {
     int64_t count_view_stride;     // B*C*3
     int counts_overwrite;          // Dice: 1 = this launch clears `counts` first (CTA 0; the others wait for ws->counts_zeroed)
     PeerPub pub;                   // *_pub launches (PUB kernels): publication descriptor of the step's sums, by value
+    int pub_early;                 // PUB kernels: 1 = `pub.src` is already final (the PREVIOUS step's sums): the first CTA to finish
+                                   // publishes it; 0 = the last CTA publishes, with the sum this launch has just produced
     unsigned long long* conf;      // CONF ops: [C][C] int64 (rows = ground truth), accumulated into; null = not counted
     const float* class_w;          // LABELS ops: per-class weight [C] (device) or null = 1
     int64_t ignore_index;          // LABELS ops: label value that contributes nothing (nn.NLLLoss ignore_index)
@@ -881,7 +883,7 @@ __global__ void __launch_bounds__(NCW * 32 + 32, MINB) tile_kernel(const TileArg
             if (bad) atomicAdd(&a.flags[DCT_FLAG_SIMPLEX], 1);
         }
     }
-    tile_grid_finish<PUB>(acc_fx, nonfinite, a.ws, Op::HAS_MAP ? a.sum : nullptr, gridDim.x, &a.pub);
+    tile_grid_finish<PUB>(acc_fx, nonfinite, a.ws, Op::HAS_MAP ? a.sum : nullptr, gridDim.x, &a.pub, a.pub_early);
     if (a.trace != nullptr && tid == 0) a.trace[kTraceSlots * blockIdx.x + 3] = globaltimer_ns();
 }
 

@@ -94,7 +94,9 @@ class ConsistencyStep:
         # "deferred": like "chained", but the publication of step i-1's sums runs on a forked branch next to step i's
         #            first kernel (run(bufs, publish_prev=previous buffers)): nothing is added to the step's critical path;
         #            the caller publishes the last step's sums itself (exchange.publish) when the loop ends
-        assert exchange_mode in ("fused", "chained", "deferred")
+        # "early":   like "deferred", without a launch: the step's FIRST kernel (dct_jsd_fwdbwd_pub_f32) carries the previous
+        #            step's sums and its first finishing CTA publishes them inside the launch's own tail (CTAs end 3-4 us apart)
+        assert exchange_mode in ("fused", "chained", "deferred", "early")
         self.exchange_mode = exchange_mode
         self._pub_stream = None
         self._h = _lib.lib()
@@ -104,7 +106,7 @@ class ConsistencyStep:
         big = (self.M > 16 * 256 * 64) or (self.M % 4 != 0)   # (a cluster of 16 CTAs serves samples up to 1 MB)
         self.launches_per_step = 1 + (0 if (not with_dice or (C <= 4 and K * C <= 16)) else K) + \
             ((2 + (2 + 2 if big else 2)) if with_vat else 0) + \
-            (1 if (exchange is not None and (not with_vat or exchange_mode != "fused")) else 0)
+            (1 if (exchange is not None and exchange_mode != "early" and (not with_vat or exchange_mode != "fused")) else 0)
 
     # bytes that MUST move per step (algorithmic, fp32): see DESIGN.md "Algorithmic bytes"
     def algorithmic_bytes(self):
@@ -132,7 +134,7 @@ class ConsistencyStep:
         if self.exchange is not None and self.exchange_mode == "deferred" and publish_prev is not None:
             joined = self._publish_forked(publish_prev, dev)
         try:
-            self._run(bufs, zero_counts)
+            self._run(bufs, zero_counts, publish_prev if self.exchange_mode == "early" else None)
         finally:
             if joined is not None:
                 torch.cuda.current_stream(dev).wait_event(joined)
@@ -157,14 +159,23 @@ class ConsistencyStep:
                       "kl_adv": n * 3 * C * 4})
         return b
 
-    def run_part(self, bufs: StepBuffers, part: str, zero_counts: bool = True) -> None:
+    def run_part(self, bufs: StepBuffers, part: str, zero_counts: bool = True, publish_prev: Optional[StepBuffers] = None) -> None:
         h, K, C, B, HW = self._h, self.K, self.C, self.B, self.HW
         dev = bufs.logits[0].device
         st = _runtime.state(dev)
         ws, s = st.workspace.data_ptr(), _runtime.stream_ptr(dev)
         fl = _runtime.flags_ptr(st)
         sums = bufs.sums.data_ptr()
-        if part == "jsd":
+        if part == "jsd" and self.exchange is not None and publish_prev is not None:
+            # the step's first kernel also publishes the PREVIOUS step's sums (final since that step's last kernel completed)
+            _lib.check(h.dct_jsd_fwdbwd_pub_f32(_lib.ptr_array(bufs.logits), K, C, B, HW, _lib.IN_LOGITS,
+                                                self.jsd_weight / self.n, None, sums, _lib.ptr_array(bufs.grad_logits),
+                                                bufs.labels.data_ptr() if self.with_dice else None,
+                                                bufs.dice_counts.data_ptr() if self.with_dice else None,
+                                                _lib.COUNTS_OVERWRITE if zero_counts else _lib.COUNTS_ACCUMULATE, fl, ws,
+                                                ctypes.byref(self.exchange.descriptor(publish_prev.sums)), s),
+                       "dct_jsd_fwdbwd_pub_f32")
+        elif part == "jsd":
             # counts_mode 1: the launch overwrites the counters (zeroed by its own first CTA) -- no fill launch per step
             _lib.check(h.dct_jsd_fwdbwd_f32(_lib.ptr_array(bufs.logits), K, C, B, HW, _lib.IN_LOGITS,
                                             self.jsd_weight / self.n, None, sums, _lib.ptr_array(bufs.grad_logits),
@@ -201,9 +212,9 @@ class ConsistencyStep:
         else:
             raise ValueError(part)
 
-    def _run(self, bufs: StepBuffers, zero_counts: bool) -> None:
+    def _run(self, bufs: StepBuffers, zero_counts: bool, publish_prev: Optional[StepBuffers] = None) -> None:
         for part in self.parts():
-            self.run_part(bufs, part, zero_counts)
+            self.run_part(bufs, part, zero_counts, publish_prev if part == "jsd" else None)
         if self.exchange is not None and self.exchange_mode == "chained":
             self.exchange.publish(bufs.sums)   # the one-CTA publication kernel behind the step's last kernel
         elif self.exchange is not None and self.exchange_mode == "fused" and not self.with_vat:
@@ -223,20 +234,23 @@ class ConsistencyStep:
             self.run(bufs, publish_prev=publish_prev)
         return g
 
-    def capture_many(self, sets) -> "torch.cuda.CUDAGraph":
+    def capture_many(self, sets, publish_chain: bool = False) -> "torch.cuda.CUDAGraph":
         """One CUDA graph holding ``run(s)`` for every buffer set of ``sets`` in order (a round of consecutive steps: the
-        launches of neighbouring steps chain by programmatic dependent launch, which two separate graph launches do not)."""
+        launches of neighbouring steps chain by programmatic dependent launch, which two separate graph launches do not).
+        ``publish_chain`` ("early" exchange): every step publishes the sums of the set before it, the first one those of the
+        last set (the previous round's last step)."""
         dev = sets[0].logits[0].device
+        prev = (lambda j: sets[(j - 1) % len(sets)]) if publish_chain else (lambda j: None)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            self.run(sets[0])
+            self.run(sets[0], publish_prev=prev(0))
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=side):
-            for s in sets:
-                self.run(s)
+            for j, s in enumerate(sets):
+                self.run(s, publish_prev=prev(j))
         return g
 
     def losses(self, bufs: StepBuffers):

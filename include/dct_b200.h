@@ -126,6 +126,15 @@ DCT_API int dct_kl_from_logits_fwdbwd_pub_f32(const float* p_logit, const float*
                                               float eps, float gconst, float* map, double* sum, float* grad_p_logit,
                                               int32_t* flags, void* workspace, const dct_peer_pub* pub_desc,
                                               void* stream);
+/* dct_jsd_fwdbwd_f32 (below) that also carries an EARLY publication: desc->src[0..n) must be final before the launch starts
+ * (the previous step's sums, written by earlier launches of `stream`); the first CTA of the grid to finish publishes them while
+ * the others are still working, so the publication adds nothing between two launches of the stream (the product's choice at
+ * world > 1: every step's first kernel publishes the step before; the caller publishes the last step with
+ * dct_exchange_publish).  Shapes outside the tile pipeline: the plain launch followed by dct_exchange_publish. */
+DCT_API int dct_jsd_fwdbwd_pub_f32(const float* const* views, int K, int C, int64_t B, int64_t HW, int in_kind,
+                                   float gconst, float* map, double* sum, float* const* grad_views,
+                                   const int64_t* labels, int64_t* counts, int counts_mode, int32_t* flags,
+                                   void* workspace, const dct_peer_pub* pub_desc, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K-view Jensen-Shannon divergence.

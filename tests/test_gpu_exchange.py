@@ -122,9 +122,11 @@ def test_fallback_shapes_and_plain_entry_points(dev):
         dct_b200.set_check_mode(old)
 
 
+@pytest.mark.parametrize("mode", ["deferred", "early"])
 @pytest.mark.parametrize("graph", [False, True])
-def test_deferred_publication_runs_beside_the_next_step(dev, graph):
-    """exchange_mode='deferred': step i publishes step i-1's sums on a forked branch (eager and captured)."""
+def test_deferred_publication_runs_beside_the_next_step(dev, graph, mode):
+    """exchange_mode='deferred': step i publishes step i-1's sums on a forked branch (eager and captured);
+    'early' (the product's choice at world > 1): the first CTA to finish step i's first kernel does (dct_jsd_fwdbwd_pub_f32)."""
     import dct_b200
     from dct_b200.distributed import PeerExchange
     from dct_b200.engine import ConsistencyStep, StepBuffers
@@ -132,7 +134,7 @@ def test_deferred_publication_runs_beside_the_next_step(dev, graph):
     try:
         px = PeerExchange(dev, n=4, nslots=8)
         K, C, B, H, W = 2, 4, 2, 64, 64
-        step = ConsistencyStep(K, C, B, H, W, cin=1, n_global=B * H * W, exchange=px, exchange_mode="deferred")
+        step = ConsistencyStep(K, C, B, H, W, cin=1, n_global=B * H * W, exchange=px, exchange_mode=mode)
         g = torch.Generator(device=dev).manual_seed(5)
         sets = [StepBuffers.allocate(K, C, B, H, W, 1, dev, g) for _ in range(3)]
         step.run(sets[2])                                    # produces the sums the first publication carries
@@ -155,6 +157,47 @@ def test_deferred_publication_runs_beside_the_next_step(dev, graph):
         assert torch.equal(px.read(4), sets[2].sums[:4])
         if not graph:
             assert torch.equal(px.read(1), want2)
+        px.close()
+    finally:
+        dct_b200.set_check_mode(old)
+
+
+@pytest.mark.parametrize("shape", [(3, 4, 2, 64, 64), (2, 2, 2, 64, 64), (2, 19, 1, 32, 64), (2, 4, 2, 37, 41), (5, 3, 1, 40, 52)])
+def test_early_publication_every_kernel_family_and_round_graph(dev, shape):
+    """The early publication through every JSD launch family -- 256-pixel tensor-map stages with fused Dice, the 4-row
+    row-copy stages, C = 19, and shapes outside the tile pipeline (odd HW, runtime K: plain launch + stand-alone publication)
+    -- and under the graph of R consecutive steps bench.py replays; losses and Dice counts must not notice the passenger."""
+    import dct_b200
+    from dct_b200.distributed import PeerExchange
+    from dct_b200.engine import ConsistencyStep, StepBuffers
+    old = dct_b200.set_check_mode("deferred")
+    try:
+        K, C, B, H, W = shape
+        px = PeerExchange(dev, n=4, nslots=8)
+        plain = ConsistencyStep(K, C, B, H, W, cin=1, n_global=B * H * W, with_vat=False, with_dice=C <= 4)
+        early = ConsistencyStep(K, C, B, H, W, cin=1, n_global=B * H * W, with_vat=False, with_dice=C <= 4, exchange=px,
+                                exchange_mode="early")
+        g = torch.Generator(device=dev).manual_seed(11)
+        sets = [StepBuffers.allocate(K, C, B, H, W, 1, dev, g) for _ in range(3)]
+        want = []
+        for s in sets:                                       # reference results without any exchange
+            plain.run(s)
+            torch.cuda.synchronize()
+            want.append((s.sums.clone(), [t.clone() for t in s.grad_logits], s.dice_counts.clone()))
+        graph = early.capture_many(sets, publish_chain=True)
+        torch.cuda.synchronize()
+        px.seq.zero_()
+        for _ in range(2):                                   # two rounds: 6 steps, 6 publications (the first one of set 2's sums)
+            graph.replay()
+        px.publish(sets[2].sums)
+        torch.cuda.synchronize()
+        assert px.published() == 7
+        for j, s in enumerate(sets):
+            assert torch.equal(s.sums, want[j][0]) and torch.equal(s.dice_counts, want[j][2])
+            assert all(torch.equal(a, b) for a, b in zip(s.grad_logits, want[j][1]))
+        # ring of 8: publications 1..7 = sums of sets 2,0,1,2,0,1 and the final 2
+        for q, j in zip(range(1, 8), [2, 0, 1, 2, 0, 1, 2]):
+            assert torch.equal(px.read(q), sets[j].sums[:4]), (q, j)
         px.close()
     finally:
         dct_b200.set_check_mode(old)
