@@ -1,10 +1,12 @@
 // dct_tile.cuh -- the tile pipeline: one persistent-CTA skeleton for every per-pixel op of the path.
 //
-//   HBM --(TMA 1-D bulk copies, mbarrier)--> smem stage [NIN*C][TP] --> registers --> math
-//   HBM <--(TMA bulk stores, bulk groups)---- smem stage (results written in place) <----'
+//   HBM --(TMA: tensor-map boxes or 1-D bulk copies, mbarrier)--> smem stage [NIN*C][TP] --> registers --> math
+//   HBM <--(TMA stores, bulk groups)------------------------------- smem stage (results written in place) <----'
 //
 // A tile is TP = THREADS*PPT consecutive pixels of one image; in NCHW every (tensor, class) plane
-// contributes one contiguous TP*4-byte row segment, fetched by ONE cp.async.bulk (SASS UBLKCP).
+// contributes one contiguous TP*4-byte row segment.  Stages of 5 or more rows whose tile is one box of
+// <= 256 pixels are moved by ONE cp.async.bulk.tensor per tensor (SASS UTMALDG / UTMASTG, dct_tmap.cuh);
+// the 4-row stages by one cp.async.bulk per row (SASS UBLKCP).
 // STAGES-1 tiles are in flight per CTA at all times, so HBM latency is covered by shared-memory
 // depth rather than by resident warps and registers (the register-tiled kernels top out at
 // ~68% of the measured HBM peak on ACDC-sized inputs because raising occupancy forces spills).
@@ -247,7 +249,7 @@ inline void tile_set_geometry(TileArgs& a, int64_t B, int tile_pixels) {
 //       with outputs, when the bulk store group that drains it has finished reading shared memory.  Fused Dice: lane 0
 //       marks the last tile of every run of one image (s_info.w); on those tiles all 32 lanes add the counters the
 //       consumer warps hand over through the label row to the global int64 counters (see DCT_DICE_LOCAL above).
-//   consumers: wait on the stage's `full` mbarrier (transaction bytes), read the tile index (-1 = no more work),
+//   consumers: wait on the stage's `full` mbarrier (transaction bytes), read the stage's info word (tile -1 = no more work),
 //       compute in registers, write results back in place, fence to the async proxy, arrive on `done`.
 //       No CTA-wide barrier in the tile loop: a fast warp runs ahead by up to STAGES-1 tiles.
 // Nothing depends on WHICH CTA processes a tile: Dice counts are integer atomics, the loss sum is accumulated in

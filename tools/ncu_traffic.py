@@ -19,11 +19,19 @@ CSRC = os.path.join(ROOT, "deep-co-training-for-semi-supervised-image-segmentati
 
 
 def csrc_sha16():
+    """Hash of the kernel sources the loaded library was built from (tools/ncu_traffic.py stamps captures with it).
+    Comments and white space are stripped first: only a change that can alter the generated code invalidates a capture."""
+    import hashlib
+    import re
+    d = CSRC
     h = hashlib.sha256()
-    for f in sorted(os.listdir(CSRC)):
+    for f in sorted(os.listdir(d)):
         if f.endswith((".cu", ".cuh")):
+            src = open(os.path.join(d, f), "r", encoding="utf-8", errors="replace").read()
+            src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+            src = re.sub(r"//[^\n]*", "", src)
             h.update(f.encode())
-            h.update(open(os.path.join(CSRC, f), "rb").read())
+            h.update("".join(src.split()).encode())
     return h.hexdigest()[:16]
 
 
