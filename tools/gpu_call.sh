@@ -9,6 +9,7 @@
 #                                             kb:<group>                      tools/kbench_c2 (0: c2 launches + per-CTA dump, 1: c3 / c1 shapes)
 #                                             multi                           both bench arms under torch.distributed.run on all visible GPUs
 #                                             extras                          configs[4] sweep, sanitizer memcheck, step timeline
+#                                             exchange                        who publishes the loss sums: loopback A/B of bench.py --exchange
 # Every command is bounded by its own timeout (a hung A/B run once cost 25 GPU-minutes).
 step_line() { python -c "
 import json,sys
@@ -43,6 +44,12 @@ for sec in "$@"; do
     extras)   ( timeout 300 python tools/sweep.py --no-aten --out $out/sweep 2>&1 | tail -20 ) > $out/sweep.log; cat $out/sweep.log
               ( timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py tests/test_gpu_supervised.py -m gpu -q -x -k "consistency_step or ragged or dice or fused or confusion or ce_" 2>&1 | tail -12 ) > $out/sanitizer_memcheck.log; tail -6 $out/sanitizer_memcheck.log
               ( timeout 120 python tools/step_trace.py 2>&1 | tail -8 ) > $out/step_trace_c2.log; cat $out/step_trace_c2.log ;;
+    exchange) for rep in 1 2; do for ex in auto p2p p2p-early p2p-fused p2p-deferred; do
+                timeout 90 python bench.py --exchange $ex --steps 1200 --no-cpu-baseline --no-extras --e2e-steps 3 2>&1 | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); r=d['roofline']
+print('c2 exchange=$ex ms_per_step=%.4f launches/step=%d | ' % (d['ms_per_step'], d['gpu_launches']//d['steps']) + ' '.join('%s=%.2fus' % (k['part'], k['us']) for k in r['step_kernels']))"
+              done; done | tee $out/ab_exchange_loopback.log ;;
     sh:*)     s=${sec#sh:}; ( timeout 1500 bash $s $out 2>&1 | tail -80 ) > $out/$(basename $s .sh).log; tail -40 $out/$(basename $s .sh).log ;;
     py:*)     s=${sec#py:}; ( timeout 1500 python $s 2>&1 | tail -80 ) > $out/$(basename $s .py).log; tail -40 $out/$(basename $s .py).log ;;
     *) echo "unknown section $sec" ;;
