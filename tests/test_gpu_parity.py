@@ -389,6 +389,51 @@ def test_dice_near_ties_bit_exact(C, dct, dev, oracle):
     assert np.array_equal(pred_aten, oracle.predict(z.numpy(), "dice"))
 
 
+@pytest.mark.parametrize("K,C", [(3, 4), (2, 2), (4, 4), (2, 4), (3, 3)])
+def test_fused_dice_groups_with_adversarial_members(K, C, dct, dev, oracle):
+    """The fused K-view Dice path evaluates the fast-path arg-max test of all K x 2 predictions of a pixel pair together and
+    redoes the whole group with the pinned arithmetic if ANY member fails it (csrc/dct_tile.cuh).  Inputs where single
+    members of a group are exact ties, 1..64-ulp near-ties, NaN / +-inf rows -- next to ordinary members, in either pixel of
+    the pair and in any view -- must give the oracle's counts bit for bit, view by view (also through the cross-entropy
+    launch: one prediction per pixel)."""
+    g = torch.Generator().manual_seed(100 * K + C)
+    B, H, W = 2, 48, 44                       # HW = 2112 = 8 * 256 + 64: ragged last tile included
+    views = []
+    for k in range(K):
+        x = 3 * torch.randn(B, C, H, W, generator=g)
+        mx, am = x.max(1, keepdim=True)
+        other = (am + 1 + torch.randint(0, max(C - 1, 1), am.shape, generator=g)) % C
+        ulps = torch.randint(0, 65, am.shape, generator=g)
+        hit = torch.rand(am.shape, generator=g) < 0.3          # 30 % of the pixels of this view carry a (near-)tie
+        near = mx.clone()
+        for _ in range(64):
+            near = torch.where(ulps > 0, torch.nextafter(near, torch.full_like(near, -1e30)), near)
+            ulps = ulps - 1
+        x.scatter_(1, other, torch.where(hit, near, x.gather(1, other)))
+        # special rows in a few odd / even pixels of different rows, different per view
+        x[0, 0, 1 + k, 1:9:2] = float("nan")
+        x[0, C - 1, 5 + k, 0:8:2] = float("inf")
+        x[1, :, 9 + k, 3:11] = float("-inf")
+        x[1, 0, 13 + k, 2:6] = float("inf"); x[1, C - 1, 13 + k, 2:6] = float("inf")
+        x[1, :, 17 + k, 5:7] = float("nan")
+        views.append(x)
+    gt = torch.randint(0, C, (B, 1, H, W), generator=g)
+    want = [oracle.dice_counts(v.numpy(), gt.numpy())[0] for v in views]
+    old = dct.set_check_mode("off")          # the loss of these inputs is NaN by construction; only the counts are examined
+    try:
+        counts = torch.zeros(K, B, C, 3, dtype=torch.int64, device=dev)
+        zr = [v.to(dev).requires_grad_() for v in views]
+        dct.jsd_consistency_from_logits(zr, weight=1.0, labels=gt.to(dev), dice_counts=counts).backward()
+        for k in range(K):
+            assert np.array_equal(N(counts[k]), want[k]), f"fused JSD + Dice, view {k}"
+            assert np.array_equal(N(dct.dice_counts(views[k].to(dev), gt.to(dev))), want[k]), f"dice_counts, view {k}"
+        c1 = torch.zeros(B, C, 3, dtype=torch.int64, device=dev)
+        dct.supervised_from_logits(views[0].to(dev).requires_grad_(), gt.to(dev), dice_counts=c1).backward()
+        assert np.array_equal(N(c1), want[0]), "fused cross-entropy + Dice"
+    finally:
+        dct.set_check_mode(old)
+
+
 def test_flags_and_errors_through_c_abi(dct, dev):
     """Error behaviour of the raw C ABI: bad args return negative codes, nothing is launched."""
     h = dct._lib.lib()
