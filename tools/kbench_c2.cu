@@ -18,6 +18,18 @@ int main(int argc, char** argv) {
         run_auto<KlFromLogits, 4, 2, 4, 3, true>("klfromlogits c2", 32, HW, reps, 48, false);
         run_auto<CopyOp<3>, 4, 2, 4, 3, true>("copy3x4", 32, HW, reps, 96, false);
     }
+    if (group == 2) {   // c2 launches: fewer stages than fit (a shorter committed look-ahead: smaller end spread vs less bandwidth in flight)
+        if (g_only < 0 || g_only == g_idx) run<JD, 4, 2, 4, 5, 3, true>("jsd+dice c2", 32, HW, reps, 104, true); ++g_idx;
+        if (g_only < 0 || g_only == g_idx) run<JD, 4, 2, 4, 4, 3, true>("jsd+dice c2", 32, HW, reps, 104, true); ++g_idx;
+        if (g_only < 0 || g_only == g_idx) run<JD, 4, 2, 4, 3, 3, true>("jsd+dice c2", 32, HW, reps, 104, true); ++g_idx;
+        if (g_only < 0 || g_only == g_idx) run<KlLogit<true>, 4, 2, 4, 8, 3, true>("kllogit c2", 32, HW, reps, 64, false); ++g_idx;
+        if (g_only < 0 || g_only == g_idx) run<KlLogit<true>, 4, 2, 4, 6, 3, true>("kllogit c2", 32, HW, reps, 64, false); ++g_idx;
+        if (g_only < 0 || g_only == g_idx) run<KlLogit<true>, 4, 2, 4, 5, 3, true>("kllogit c2", 32, HW, reps, 64, false); ++g_idx;
+        if (g_only < 0 || g_only == g_idx) run<KlLogit<true>, 4, 2, 4, 4, 3, true>("kllogit c2", 32, HW, reps, 64, false); ++g_idx;
+        if (g_only < 0 || g_only == g_idx) run<KlFromLogits, 4, 2, 4, 8, 3, true>("klfromlogits c2", 32, HW, reps, 48, false); ++g_idx;
+        if (g_only < 0 || g_only == g_idx) run<KlFromLogits, 4, 2, 4, 6, 3, true>("klfromlogits c2", 32, HW, reps, 48, false); ++g_idx;
+        if (g_only < 0 || g_only == g_idx) run<KlFromLogits, 4, 2, 4, 4, 3, true>("klfromlogits c2", 32, HW, reps, 48, false); ++g_idx;
+    }
     if (group == 1) {   // c3: K = 2, C = 2, B = 4, 512 x 512; c1: K = 2, C = 4, B = 4, 256 x 256
         using J3 = JsdOp<2, true, kFwdBwd, true>;
         run_auto<J3, 2, 4, 8, 2>("jsd+dice c3", 4, 262144, reps, 40, true);
