@@ -30,6 +30,17 @@ int main(int argc, char** argv) {
         if (g_only < 0 || g_only == g_idx) run<KlFromLogits, 4, 2, 4, 6, 3, true>("klfromlogits c2", 32, HW, reps, 48, false); ++g_idx;
         if (g_only < 0 || g_only == g_idx) run<KlFromLogits, 4, 2, 4, 4, 3, true>("klfromlogits c2", 32, HW, reps, 48, false); ++g_idx;
     }
+    if (group == 3) {   // c2 launches: smaller tiles (128 / 192 pixels) for a finer end-of-launch granularity
+        run_auto<JD, 4, 2, 4, 3, true>("jsd+dice c2", 32, HW, reps, 104, true);
+        run_auto<JD, 4, 2, 2, 6, true>("jsd+dice c2", 32, HW, reps, 104, true);
+        run_auto<JD, 4, 2, 2, 5, true>("jsd+dice c2", 32, HW, reps, 104, true);
+        run_auto<JD, 4, 2, 3, 4, true>("jsd+dice c2", 32, HW, reps, 104, true);
+        run_auto<JD, 4, 2, 3, 3, true>("jsd+dice c2", 32, HW, reps, 104, true);
+        run_auto<KlLogit<true>, 4, 2, 2, 6, true>("kllogit c2", 32, HW, reps, 64, false);
+        run_auto<KlLogit<true>, 4, 2, 3, 4, true>("kllogit c2", 32, HW, reps, 64, false);
+        run_auto<KlFromLogits, 4, 2, 2, 6, true>("klfromlogits c2", 32, HW, reps, 48, false);
+        run_auto<KlFromLogits, 4, 2, 3, 4, true>("klfromlogits c2", 32, HW, reps, 48, false);
+    }
     if (group == 1) {   // c3: K = 2, C = 2, B = 4, 512 x 512; c1: K = 2, C = 4, B = 4, 256 x 256
         using J3 = JsdOp<2, true, kFwdBwd, true>;
         run_auto<J3, 2, 4, 8, 2>("jsd+dice c3", 4, 262144, reps, 40, true);
