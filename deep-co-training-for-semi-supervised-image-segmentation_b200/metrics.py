@@ -87,10 +87,13 @@ class DiceMeter(Metric):
         self.diceLog = []
         self.C = C
         self._cat = None
+        self._value = None       # value() of the current log (trainers ask for it ~8 times per meter and iteration)
+        self._axis_index = None  # report axes as a device index tensor (a Python-list index costs a blocking H2D copy per use)
 
     def reset(self):
         self.diceLog = []
         self._cat = None
+        self._value = None
 
     def add(self, pred_logit, gt):
         counts = dice_counts(pred_logit, gt)
@@ -102,19 +105,42 @@ class DiceMeter(Metric):
         assert dice_value.shape.__len__() == 2
         self.diceLog.append(dice_value)
         self._cat = None
+        self._value = None
 
     def value(self, **kwargs):
+        """Same statistics, same tensor ops as the reference (dice_meter.py:57-64).  The result is kept until the log
+        changes: the reference trainer evaluates ``value()`` once per (model, axis) per iteration for its progress bar
+        (cotraining_totalloss.py:252-258) -- eight times per meter on an unchanged log; the tensors returned are the same
+        objects then (the reference builds new ones each time: do not modify them in place)."""
+        key = self._log_key()
+        if self._value is not None and self._value[0] == key:
+            return self._value[1]
         log = self.log
         means = log.mean(0)
         stds = log.std(0)
-        report_means = log.mean(1) if self.report_axis == 'all' else log[:, self.report_axis].mean(1)
+        if self.report_axis == 'all':
+            report_means = log.mean(1)
+        elif log.is_cuda:
+            if self._axis_index is None or self._axis_index.device != log.device:
+                self._axis_index = torch.tensor(self.report_axis, dtype=torch.long, device=log.device)
+            report_means = log.index_select(1, self._axis_index).mean(1)   # == log[:, self.report_axis].mean(1)
+        else:
+            report_means = log[:, self.report_axis].mean(1)
         report_std = report_means.std()
         report_mean = report_means.mean()
-        return (report_mean, report_std), (means, stds)
+        self._value = (key, ((report_mean, report_std), (means, stds)))   # keyed on the log's identity: ``diceLog`` is a public list
+        return self._value[1]
+
+    def _log_key(self):
+        # identity of the log's content as far as a list of immutable-by-convention rows goes: ``diceLog`` is a public
+        # attribute of the reference's meter (callers read it, tests append to it), so the caches below cannot rely on
+        # add() / reset() alone
+        return (len(self.diceLog), id(self.diceLog[-1]) if self.diceLog else 0)
 
     @property
     def log(self):
-        if self._cat is None:
+        key = self._log_key()
+        if self._cat is None or self._cat[0] != key:
             if len(self.diceLog) > 0:
                 log = torch.cat(self.diceLog)
             else:
@@ -122,8 +148,8 @@ class DiceMeter(Metric):
             if len(log.shape) == 1:
                 log = log.unsqueeze(0)
             assert len(log.shape) == 2
-            self._cat = log
-        return self._cat
+            self._cat = (key, log)
+        return self._cat[1]
 
     def detailed_summary(self) -> dict:
         _, (means, _) = self.value()

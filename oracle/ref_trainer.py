@@ -77,7 +77,7 @@ class SynthSet(torch.utils.data.Dataset):
 
 def run_train_loop(device, use_dropins, iters=3, K=2, arch="enet", C=4, B=4, H=256, W=256, seed=1234, train_jsd=True,
                    train_adv=True, cot_weight=0.5, adv_weight=0.05, eps=0.03, deterministic=True, warmup_iters=0,
-                   keep_inputs=0, tf32=False):
+                   keep_inputs=0, tf32=False, check_mode=None):
     """One truncated epoch of the reference's co-training loop, stock (``use_dropins=False``) or after
     ``dct_b200.install()``.  Returns a dict of recorded values (numpy) and timings."""
     ref_shim.install()
@@ -87,9 +87,12 @@ def run_train_loop(device, use_dropins, iters=3, K=2, arch="enet", C=4, B=4, H=2
     from generalframework.loss import get_loss_fn
     from generalframework.models import Segmentator
 
+    old_check = None
     if use_dropins:
         import dct_b200
         dct_b200.install()
+        if check_mode is not None:   # 'deferred': the drop-ins' contract flags are read once, after the loop, not after every call
+            old_check = dct_b200.set_check_mode(check_mode)
     # process-wide torch switches: saved here, restored in the `finally` below.  ``tf32=False`` (parity runs): exact fp32
     # convolutions, so that both arms see the same network outputs; ``tf32=None`` (timing runs): PyTorch's defaults untouched
     saved_flags = (torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32,
@@ -164,6 +167,11 @@ def run_train_loop(device, use_dropins, iters=3, K=2, arch="enet", C=4, B=4, H=2
         ct.DiceMeter = Meter
         if use_dropins:
             import dct_b200
+            if old_check is not None:
+                try:
+                    dct_b200.raise_if_flagged()
+                finally:
+                    dct_b200.set_check_mode(old_check)
             dct_b200.uninstall()
         (torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32,
          torch.backends.cuda.matmul.allow_tf32) = saved_flags

@@ -127,11 +127,15 @@ def test_meter_host_logic_matches_reference_structures():
     m = dct_b200.DiceMeter(method="2d", C=4, report_axises=[1, 2, 3])
     (rm, rs), (ms, ss) = m.value()           # empty log fallback, dice_meter.py:68-71
     assert ms.shape == (4,) and float(ms.sum()) == 0.0
-    m.diceLog.append(torch.tensor([[1.0, 0.5, 0.25, 0.75], [1.0, 0.0, 0.5, 0.25]]))
-    m._cat = None
+    m.diceLog.append(torch.tensor([[1.0, 0.5, 0.25, 0.75], [1.0, 0.0, 0.5, 0.25]]))   # the public list, behind add()'s back
     (rm, rs), (ms, ss) = m.value()
     assert torch.allclose(ms, torch.tensor([1.0, 0.25, 0.375, 0.5]))
     assert abs(rm.item() - (0.5 + 0.25) / 2) < 1e-7
+    assert m.value()[1][0] is ms                                   # unchanged log: the kept result
+    m.diceLog.append(torch.tensor([[0.0, 0.0, 0.0, 0.0]]))
+    assert torch.allclose(m.value()[1][0], torch.tensor([2.0, 0.5, 0.75, 1.0]) / 3)   # changed log: recomputed
+    m.reset()
+    assert float(m.value()[1][0].sum()) == 0.0 and m.value()[1][0].shape == (4,)
     iou = dct_b200.IoU(3)
     iou.conf_metric._host[:] = np.array([[5, 1, 0], [2, 3, 0], [0, 0, 0]])
     v = iou.value()
