@@ -368,25 +368,47 @@ __global__ void __launch_bounds__(256) l2_sumsq_kernel(const L2Args a, int gx) {
 
 // launch B: out = scale * d / n1 [/ n2] [, adv = clamp(img + out, 0, 1)] -- both normalisations of passes == 2 in one sweep
 // (the second norm follows from the first sum, l2_scales): d is read twice and written once per call, whatever `passes`.
-template <int VEC>
+template <int VEC, int kU = 4>
 __global__ void __launch_bounds__(256) l2_scale_kernel(const L2Args a, int gx) {
     pdl_wait();
     if (a.trace != nullptr && threadIdx.x == 0) a.trace[kTraceSlots * (blockIdx.y * gridDim.x + blockIdx.x)] = globaltimer_ns();
     const int64_t base = (int64_t)blockIdx.y * a.M;
     const L2Scale sc = l2_scales((float)__ldcg(&a.ws->partials[(size_t)blockIdx.y * (gx + 1) + gx]), a.passes, a.scale);
     const int64_t n = a.M / VEC;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t off = base + i * VEC;
-        FVec<VEC> v = ld_stream<VEC>(a.d + off), o;
+    const bool tail = a.img != nullptr;
+    // A CTA walks the sample in chunks of kU x 256 elements; every thread has kU loads in flight, 256 elements apart, so a warp
+    // reads kU runs of 512 contiguous bytes out of one 16 KB chunk.  One load per thread and iteration (the loads cannot move
+    // above the previous iteration's stores: `out` may alias `d`) left 32 KB in flight per SM: c4 l2_direction 63 -> 55 us
+    // with kU = 4 (2: 58 us; profiles/r61/ab_DCT_L2_SCALE_U.log).  The launch with the clamp tail (four streams) does not
+    // react (91 us either way), nor does the sum-of-squares launch.
+    const int64_t nchunks = (n + kU * 256 - 1) / (kU * 256);
+    for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        const int64_t i0 = ch * (kU * 256) + threadIdx.x;
+        FVec<VEC> v[kU], im[kU];
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) o.v[e] = l2_apply(v.v[e], sc);
-        st_stream<VEC>(a.out + off, o);
-        if (a.img != nullptr) {
-            const FVec<VEC> im = ld_stream<VEC>(a.img + off);
-            FVec<VEC> ad;
+        for (int u = 0; u < kU; ++u) {
+            const int64_t i = i0 + u * 256;
+            if (i < n) {
+                v[u] = ld_stream<VEC>(a.d + base + i * VEC);
+                if (tail) im[u] = ld_stream<VEC>(a.img + base + i * VEC);
+            }
+        }
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) ad.v[e] = fminf(fmaxf(im.v[e] + o.v[e], 0.0f), 1.0f);
-            st_stream<VEC>(a.adv + off, ad);
+        for (int u = 0; u < kU; ++u) {
+            const int64_t i = i0 + u * 256;
+            if (i < n) {
+                const int64_t off = base + i * VEC;
+                FVec<VEC> o;
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) o.v[e] = l2_apply(v[u].v[e], sc);
+                st_stream<VEC>(a.out + off, o);
+                if (tail) {
+                    FVec<VEC> ad;
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) ad.v[e] = fminf(fmaxf(im[u].v[e] + o.v[e], 0.0f), 1.0f);
+                    st_stream<VEC>(a.adv + off, ad);
+                }
+            }
         }
     }
     pdl_launch_dependents();
