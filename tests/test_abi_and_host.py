@@ -47,6 +47,10 @@ def test_library_basics_without_gpu():
     assert b"unsupported" in h.dct_error_string(-2)
     if not torch.cuda.is_available():
         assert h.dct_device_check(0) == -5
+    # argument errors are detected before anything touches the device: publication variants without a descriptor
+    assert h.dct_jsd_fwdbwd_pub_f32(None, 2, 4, 1, 64, 1, 1.0, None, None, None, None, None, 0, None, None, None, None) == -1
+    assert h.dct_exchange_publish(None, None) == -1
+    assert h.dct_dev_tile_image(0, 0) == -1
 
 
 def test_tile_schedule_division_is_exact():
