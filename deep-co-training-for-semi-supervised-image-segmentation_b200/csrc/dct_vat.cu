@@ -532,9 +532,10 @@ extern "C" int dct_l2_normalize_f32(const float* d, float* out, int64_t B, int64
     // (Chunking the samples -- a pair of launches per 16 / 32 / 64 MB of `d`, so that the scale launch's read comes out of L2 --
     // was measured and removed: every extra pair of launches costs more in ramp and tail than the L2 hits save: c4 l2_direction
     // 64 -> 144 / 86 / 74 us, l2_radv 90 -> 170 / 115 / 102 us; profiles/r44/ab_DCT_L2_CHUNK_MB.log.)
-    // CTAs per sample: about eight 256-thread CTAs per SM over the whole grid, grid-stride loops inside
+    // CTAs per sample: about sixteen 256-thread CTAs per SM over the whole grid (two waves), grid-stride loops inside
+    // (2 / 4 / 8 / 16 / 32 per SM at c4: l2_direction 63 / 58 / 57 / 57 / 59 us, l2_radv 99 / 94 / 93 / 90 / 91 us; profiles/r65)
     const int vec = vec_ok ? 4 : 1;
-    int64_t gx = (kSMs * 8 + B - 1) / B;
+    int64_t gx = (kSMs * 16 + B - 1) / B;
     const int64_t need = (M / vec + 255) / 256;
     if (gx > need) gx = need;
     const int64_t cap = kMaxPartials / B - 1;
